@@ -1,0 +1,226 @@
+"""TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-ends for the checkers under ``oracle/``:
+
+* ``Oracle``   -- our plain-C restatement (``bcr_oracle.c`` -> ``_build/liboracle.so``)
+* ``RefLib``   -- the UNMODIFIED reference hot path compiled from ``/root/reference``
+                  (``_ref/libref.so``: rle.c + rope.c + mrope.c), driven through the
+                  reference's own ``mrope.h`` entry points
+* ``ref_cli``  -- the UNMODIFIED reference binary (``_ref/ropebwt2``)
+* ``decode_index`` -- decode any library that exports ``mr_itr_first`` /
+                  ``mr_itr_next_block`` (reference or ours) into nt6 text via ``itr_text.c``
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / --impl
+reference legs may import this module.  Nothing here may read ``/root/reference`` at
+run time: the ``_ref`` artefacts are prebuilt by ``oracle/Makefile`` and travel with the
+repo snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+REF = os.path.join(HERE, "_ref")
+
+_u8p = C.POINTER(C.c_uint8)
+_i64p = C.POINTER(C.c_int64)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile the C restatement + helpers, and (only if the reference tree is mounted,
+    i.e. in the build container) the reference artefacts under ``_ref``."""
+    r = subprocess.run(["make", "-C", HERE, "oracle", "ref"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+
+
+def _need(path: str) -> str:
+    if not os.path.exists(path):
+        build()
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    return path
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(REF, "libref.so")) and os.path.exists(os.path.join(REF, "ropebwt2"))
+
+
+def _as_u8(buf) -> np.ndarray:
+    a = np.ascontiguousarray(buf, dtype=np.uint8)
+    assert a.ndim == 1 and a.size > 0 and a[-1] == 0, "batch must end with a NUL (mrope.c:268)"
+    return a
+
+
+class Oracle:
+    """The C restatement.  Same call shape as the multi-rope API it checks."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(_need(os.path.join(BUILD, "liboracle.so")))
+            L.orc_init.restype = C.c_void_p
+            L.orc_init.argtypes = [C.c_int]
+            L.orc_destroy.argtypes = [C.c_void_p]
+            L.orc_insert_multi.argtypes = [C.c_void_p, C.c_int64, _u8p]
+            L.orc_total.restype = C.c_int64
+            L.orc_total.argtypes = [C.c_void_p]
+            L.orc_counts.argtypes = [C.c_void_p, _i64p]
+            L.orc_text.argtypes = [C.c_void_p, _u8p]
+            L.orc_rank1a.argtypes = [C.c_void_p, C.c_int64, _i64p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, so: int = 0):
+        self.h = self.lib().orc_init(so)
+
+    def insert_multi(self, buf) -> None:
+        a = _as_u8(buf)
+        self.lib().orc_insert_multi(self.h, a.size, a.ctypes.data_as(_u8p))
+
+    def total(self) -> int:
+        return self.lib().orc_total(self.h)
+
+    def counts(self) -> np.ndarray:
+        c = np.zeros(36, dtype=np.int64)
+        self.lib().orc_counts(self.h, c.ctypes.data_as(_i64p))
+        return c.reshape(6, 6)
+
+    def text(self) -> np.ndarray:
+        out = np.empty(self.total(), dtype=np.uint8)
+        self.lib().orc_text(self.h, out.ctypes.data_as(_u8p))
+        return out
+
+    def rank1a(self, x: int) -> np.ndarray:
+        c = np.zeros(6, dtype=np.int64)
+        self.lib().orc_rank1a(self.h, x, c.ctypes.data_as(_i64p))
+        return c
+
+    def close(self):
+        if self.h:
+            self.lib().orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_ITR_FIRST = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
+_ITR_NEXT = C.CFUNCTYPE(C.c_void_p, C.c_void_p)
+
+
+def _itrlib():
+    L = C.CDLL(_need(os.path.join(BUILD, "libitrtext.so")))
+    L.itr_text.restype = C.c_int64
+    L.itr_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u8p, C.c_int64, C.c_int, _i64p, _i64p]
+    L.itr_runs.restype = C.c_int64
+    L.itr_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u8p, _i64p, C.c_int64]
+    return L
+
+
+def decode_index(lib: C.CDLL, mr, total: int, to_free: int = 0, ascii: bool = False):
+    """Decode the index behind ``mr`` (an ``mrope_t*`` of ``lib``) into ``total`` symbols by
+    walking ``lib``'s own mr_itr_first / mr_itr_next_block.  Returns (text, n_blocks, n_runs)."""
+    il = _itrlib()
+    first = C.cast(lib.mr_itr_first, C.c_void_p)
+    nxt = C.cast(lib.mr_itr_next_block, C.c_void_p)
+    out = np.empty(max(total, 1), dtype=np.uint8)
+    nb, nr = C.c_int64(0), C.c_int64(0)
+    n = il.itr_text(mr, first, nxt, to_free, out.ctypes.data_as(_u8p), total, int(ascii), C.byref(nb), C.byref(nr))
+    if n != total:
+        raise AssertionError(f"index decodes to {n} symbols, expected {total}")
+    return out[:total], nb.value, nr.value
+
+
+class RefLib:
+    """The unmodified reference ``mrope.h`` API (``oracle/_ref/libref.so``)."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(_need(os.path.join(REF, "libref.so")))
+            L.mr_init.restype = C.c_void_p
+            L.mr_init.argtypes = [C.c_int, C.c_int, C.c_int]
+            L.mr_destroy.argtypes = [C.c_void_p]
+            L.mr_insert_multi.argtypes = [C.c_void_p, C.c_int64, _u8p, C.c_int]
+            L.mr_insert1.restype = C.c_int64
+            L.mr_insert1.argtypes = [C.c_void_p, _u8p]
+            L.mr_rank2a.argtypes = [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i64p]
+            L.mr_itr_first.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            L.mr_itr_next_block.restype = C.c_void_p
+            L.mr_itr_next_block.argtypes = [C.c_void_p]
+            L.mr_thr_min.restype = C.c_int
+            L.mr_thr_min.argtypes = [C.c_void_p, C.c_int]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, so: int = 0, max_nodes: int = 64, block_len: int = 512):
+        self.h = self.lib().mr_init(max_nodes, block_len, so)
+        self.n_sym = 0
+
+    def insert_multi(self, buf, is_thr: int = 0) -> None:
+        a = _as_u8(buf)
+        self.lib().mr_insert_multi(self.h, a.size, a.ctypes.data_as(_u8p), is_thr)
+        self.n_sym += a.size
+
+    def insert1(self, s) -> None:
+        a = np.ascontiguousarray(s, dtype=np.uint8)
+        assert a[-1] == 0
+        self.lib().mr_insert1(self.h, a.ctypes.data_as(_u8p))
+        self.n_sym += a.size
+
+    def total(self) -> int:
+        return self.n_sym
+
+    def text(self) -> np.ndarray:
+        return decode_index(self.lib(), self.h, self.n_sym)[0]
+
+    def rank2a(self, x: int, y: int):
+        cx = np.zeros(6, dtype=np.int64)
+        cy = np.zeros(6, dtype=np.int64)
+        self.lib().mr_rank2a(self.h, x, y, cx.ctypes.data_as(_i64p), cy.ctypes.data_as(_i64p) if y >= 0 else None)
+        return cx, cy
+
+    def close(self):
+        if self.h:
+            self.lib().mr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def ref_cli(args, stdin_bytes: bytes = b"", timeout: float = 3600.0):
+    """Run the unmodified reference binary; returns (stdout bytes, stderr text)."""
+    exe = _need(os.path.join(REF, "ropebwt2"))
+    r = subprocess.run([exe] + list(args), input=stdin_bytes, capture_output=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"ropebwt2 {args} failed: {r.stderr.decode()[-400:]}")
+    return r.stdout, r.stderr.decode()
+
+
+def ref_hot_path_seconds(stderr_text: str) -> float:
+    """Sum of the reference's own hot-path timer lines
+    ``[M::main_ropebwt2] inserted N symbols in X sec`` (main.c:241,249)."""
+    tot = 0.0
+    for line in stderr_text.splitlines():
+        if "inserted" in line and " sec," in line:
+            tot += float(line.split(" in ")[1].split(" sec")[0])
+    return tot
