@@ -1,0 +1,104 @@
+/*
+ * ropebwt2_b200.h -- C-ABI of the B200 (sm_100a) BCR insertion engine.
+ *
+ * This is the device shim under the reference-compatible host API in mrope.h / rope.h.
+ * Plain C types only: no CUDA, torch or C++ types cross this boundary, so the library
+ * can be bound from C (the reference's own language), ctypes, cgo, JNI, ...
+ *
+ * What each entry point replaces in lh3/ropebwt2 (file:line into the reference):
+ *
+ *   rb2_create / rb2_destroy     mr_init / mr_destroy              mrope.c:14-33
+ *   rb2_insert_multi             the body of mr_insert_multi       mrope.c:258-345
+ *                                incl. mr_insert_multi_aux         mrope.c:184-233
+ *                                rope_insert_run / rope_rank2a     rope.c:114-194
+ *                                rle_insert_cached / rle_rank2a    rle.c:10-89,134-191
+ *   rb2_insert_multi_dev         same, input already resident in HBM (bench "value" leg)
+ *   rb2_rank2a                   mr_rank2a                         mrope.c:70-105
+ *   rb2_counts                   the rope_t::c[6] marginals        rope.h:19, mrope.h:86-116
+ *   rb2_num_blocks/fetch_blocks  rope_itr_first/next_block         rope.c:200-219
+ *   rb2_load_blocks              rope_restore (leaf upload)        rope.c:277-318
+ *
+ * Every function aborts the process with a message on a CUDA failure; there is no CPU
+ * fallback anywhere behind this header.
+ */
+#ifndef ROPEBWT2_B200_H_
+#define ROPEBWT2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB2_SO_IO   0  /* input order                     (MR_SO_IO,   mrope.h:6) */
+#define RB2_SO_RLO  1  /* reverse lexicographical order   (MR_SO_RLO,  mrope.h:7) */
+#define RB2_SO_RCLO 2  /* reverse-complement lex. order   (MR_SO_RCLO, mrope.h:8) */
+
+#define RB2_BLOCK_BYTES 512 /* one leaf block in HBM: [uint16 nbytes][runs...], the rle.h layout (rle.h:36) */
+#define RB2_BLOCK_FILL  494 /* max run bytes per block: block_len - RLE_MIN_SPACE (rope.c:143, rle.h:35) */
+
+typedef struct rb2_engine rb2_engine_t;
+
+/* counters and CUDA-event timings accumulated since the last rb2_reset_stats() */
+typedef struct {
+	int64_t n_strings, n_symbols;       /* inserted strings / symbols (sentinels included) */
+	int64_t n_columns;                  /* BCR columns executed */
+	int64_t n_launches;                 /* kernels launched by this library */
+	int64_t n_merge_launches;           /* launches of the dominant kernel (k_merge_blocks) */
+	int64_t merge_blocks;               /* leaf blocks read by k_merge_blocks, all launches */
+	int64_t merge_bytes_rw;             /* algorithmic HBM bytes of k_merge_blocks: blocks read + written, x512 */
+	int64_t n_records;                  /* (position, symbol, count) insertion records merged */
+	int64_t pool_blocks, pool_capacity; /* leaf blocks in use / allocated */
+	double  ms_total;                   /* device time of whole rb2_insert_multi* calls (CUDA events) */
+	double  ms_h2d;                     /* host->device copy of the batch */
+	double  ms_transpose;               /* string split + column-major transpose */
+	double  ms_members;                 /* symbol fetch, radix partition of the string set */
+	double  ms_groups;                  /* group scan, record emission, rank pre-pass */
+	double  ms_merge;                   /* k_merge_blocks only */
+	double  ms_directory;               /* item planning + directory rebuild */
+} rb2_stats_t;
+
+int  rb2_device_count(void);
+
+/* Create an engine on CUDA device `device` with an empty six-bucket index. */
+rb2_engine_t *rb2_create(int device, int sorting_order);
+void rb2_destroy(rb2_engine_t *e);
+int  rb2_sorting_order(const rb2_engine_t *e);
+
+/*
+ * Insert a batch.  `s` holds `len` bytes of nt6 codes ($=0 A=1 C=2 G=3 T=4 N=5), each string
+ * REVERSED and NUL-terminated, strings concatenated; len > 0 and s[len-1] == 0 (mrope.c:268).
+ * The buffer is only read and may be reused as soon as the call returns (main.c:243).
+ */
+void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s_host);
+void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev);
+
+/* c[b*6+a] = number of symbols a in bucket b (bucket b = symbols followed by b) */
+void rb2_counts(rb2_engine_t *e, int64_t c[36]);
+
+/* cx[a] = #a in BWT[0,x), cy[a] = #a in BWT[0,y) over the concatenated buckets; y < 0 or
+ * cy == NULL skips the second query (mr_rank1a) */
+void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6]);
+
+/* Leaf blocks of one bucket in logical (left-to-right) order. */
+int64_t rb2_num_blocks(rb2_engine_t *e, int bucket);
+/* Copy blocks [first, first+n) of `bucket` to host: dst gets n*512 bytes, cnt (optional)
+ * n*6 per-block symbol counts.  Returns the number of blocks copied. */
+int64_t rb2_fetch_blocks(rb2_engine_t *e, int bucket, int64_t first, int64_t n, uint8_t *dst, int64_t *cnt);
+/* Append n host blocks (512 B each, rle.h layout, every run < 2^19, nbytes <= 494) to the
+ * right end of `bucket`; cnt = n*6 per-block symbol counts.  Used by mr_restore. */
+void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const uint8_t *src, const int64_t *cnt);
+
+void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st);
+void rb2_reset_stats(rb2_engine_t *e);
+/* stream the engine launches on (a cudaStream_t), for callers that time with their own events */
+void *rb2_stream(rb2_engine_t *e);
+/* device scratch helpers for callers that stage inputs in HBM themselves (bench, tests) */
+void *rb2_dev_alloc(rb2_engine_t *e, int64_t bytes);
+void  rb2_dev_free(rb2_engine_t *e, void *p);
+void  rb2_dev_upload(rb2_engine_t *e, void *dst_dev, const void *src_host, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

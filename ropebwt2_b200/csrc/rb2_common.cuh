@@ -1,0 +1,139 @@
+// rb2_common.cuh -- shared device helpers: error handling, warp/CTA scans, and the
+// three-phase (reduce / mid / apply) multi-counter prefix sum every column kernel uses.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define RB2_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	fprintf(stderr, "[ropebwt2_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+	abort(); } } while (0)
+
+#define RB2_FATAL(...) do { fprintf(stderr, "[ropebwt2_b200] fatal: " __VA_ARGS__); fputc('\n', stderr); abort(); } while (0)
+
+#define FULLMASK 0xffffffffu
+
+// device-side error codes (Ctl::err)
+enum { RB2_ERR_NONE = 0, RB2_ERR_POOL = 1, RB2_ERR_RUN8 = 2, RB2_ERR_STAGE = 4, RB2_ERR_ORDER = 8, RB2_ERR_PIECES = 16 };
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v, int lane)
+{
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		T y = __shfl_up_sync(FULLMASK, v, o);
+		if (lane >= o) v += y;
+	}
+	return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+	return v;
+}
+
+// Exclusive scan of K counters across a CTA of NT threads (NT multiple of 32, <= 1024).
+// v[] in: this thread's values; out: exclusive prefix inside the CTA.  tot[]: CTA totals
+// (valid in every thread).  smem must hold K*(NT/32) elements of T.
+template <int K, int NT, typename T>
+__device__ __forceinline__ void cta_excl_scan(T (&v)[K], T (&tot)[K], T *smem)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	constexpr int NW = NT / 32;
+	T incl[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		incl[k] = warp_incl_scan(v[k], lane);
+		if (lane == 31) smem[k * NW + wid] = incl[k];
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		T base = 0, t = 0;
+#pragma unroll
+		for (int w = 0; w < NW; ++w) {
+			T x = smem[k * NW + w];
+			if (w < wid) base += x;
+			t += x;
+		}
+		v[k] = base + incl[k] - v[k];
+		tot[k] = t;
+	}
+	__syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// Three-phase prefix sum over n elements, K counters of type T per element.
+//   F::load(i, v[K])                 produce element i's counters (may recompute)
+//   F::store(i, v[K], pre[K])        consume element i's counters + exclusive prefix
+// scan_reduce -> per-CTA totals; scan_mid -> exclusive scan of the CTA totals (one CTA)
+// and the grand totals; scan_apply -> per-element exclusive prefix.
+// ---------------------------------------------------------------------------------
+#define SCAN_NT 256
+
+template <int K, typename T, class F>
+__global__ void __launch_bounds__(SCAN_NT) scan_reduce(F f, uint64_t n, T *ctaTot)
+{
+	__shared__ T sm[K * (SCAN_NT / 32)];
+	uint64_t i = (uint64_t)blockIdx.x * SCAN_NT + threadIdx.x;
+	T v[K], tot[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] = 0;
+	if (i < n) f.load(i, v);
+	cta_excl_scan<K, SCAN_NT, T>(v, tot, sm);
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) ctaTot[(uint64_t)blockIdx.x * K + k] = tot[k];
+	}
+}
+
+// one CTA of 1024 threads: in-place exclusive scan of ctaTot[nCta][K]; grand[K] = totals
+template <int K, typename T>
+__global__ void __launch_bounds__(1024) scan_mid(T *ctaTot, uint64_t nCta, T *grand)
+{
+	__shared__ T sm[K * 32];
+	const uint64_t per = (nCta + 1023) / 1024;
+	const uint64_t lo = (uint64_t)threadIdx.x * per;
+	const uint64_t hi = lo + per < nCta ? lo + per : nCta;
+	T v[K], tot[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] = 0;
+	for (uint64_t i = lo; i < hi; ++i)
+#pragma unroll
+		for (int k = 0; k < K; ++k) v[k] += ctaTot[i * K + k];
+	cta_excl_scan<K, 1024, T>(v, tot, sm);
+	for (uint64_t i = lo; i < hi; ++i)
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			T x = ctaTot[i * K + k];
+			ctaTot[i * K + k] = v[k];
+			v[k] += x;
+		}
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) grand[k] = tot[k];
+	}
+}
+
+template <int K, typename T, class F>
+__global__ void __launch_bounds__(SCAN_NT) scan_apply(F f, uint64_t n, const T *ctaPre)
+{
+	__shared__ T sm[K * (SCAN_NT / 32)];
+	uint64_t i = (uint64_t)blockIdx.x * SCAN_NT + threadIdx.x;
+	T v[K], own[K], tot[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] = 0;
+	if (i < n) f.load(i, v);
+#pragma unroll
+	for (int k = 0; k < K; ++k) own[k] = v[k];
+	cta_excl_scan<K, SCAN_NT, T>(v, tot, sm);
+	if (i < n) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) v[k] += ctaPre[(uint64_t)blockIdx.x * K + k];
+		f.store(i, own, v);
+	}
+}

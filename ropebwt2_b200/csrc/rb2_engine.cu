@@ -1,0 +1,1380 @@
+// rb2_engine.cu -- B200 (sm_100a) engine for ropebwt2's batched multi-string insertion.
+//
+// What it replaces: mr_insert_multi (reference mrope.c:258-345) and everything below it:
+// mr_insert_multi_aux (mrope.c:184-233), rope_insert_run / rope_rank2a (rope.c:114-194),
+// rle_insert_cached / rle_rank2a (rle.c:10-89, 134-191).  See DESIGN.md for the data layout
+// and the derivation; the short version:
+//
+//  * The BWT lives in HBM as a pool of 512-byte leaf blocks in the reference's own leaf
+//    format ([uint16 nbytes][43+3 coded runs], rle.h:36-75).  A flat directory replaces the
+//    B+-tree: `order` (logical -> physical block), `cumLen` / `cumCnt` (exclusive prefix of
+//    block lengths / per-symbol counts over ALL six buckets, so a directory lookup plus an
+//    in-block decode is a whole-index rank, i.e. occ() including the cross-bucket offsets of
+//    mrope.c:332-340).
+//  * The string set of a batch is a column-major symbol matrix T[column][string] plus two
+//    sorted structures: GROUPS (one per suffix-array interval: start position, interval
+//    size, member range) and MEMBERS (string ids, grouped).  One BCR column =
+//      members : fetch next symbol, 6-way stable partition               (mrope.c:189-190, 303-309)
+//      groups  : per-group symbol histogram -> one insertion RECORD per   (mrope.c:191-224)
+//                (group, symbol) in $,A,C,G,T,N / $,T,G,C,A,N order; every record with a
+//                symbol != $ is also the next column's group
+//      blocks  : k_merge_blocks: one warp per touched leaf block decodes it, merges its
+//                records into the run stream, re-encodes, splits overfull blocks, and returns
+//                rank(a, position) for every record = the next interval start (rope.c:114-148)
+//      directory rebuild (prefix sums).
+//  * No CPU fallback: every failure aborts.
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "rb2_codec.cuh"
+#include "../../include/ropebwt2_b200.h"
+
+#define MEM_TILE    1024   // members per CTA in the fetch / partition kernels (256 threads x 4)
+#define RMAX        448    // max records merged by one work item (bounds the staging buffer)
+#define STAGE_BYTES 4096   // >= 510 + 8*RMAX: old block bytes + <=8 new bytes per record
+#define SPLIT_T     488    // piece size target when a block overflows (pieces are < SPLIT_T+4 <= 494)
+#define MAXPIECES   16
+#define MERGE_WARPS 4
+#define NONE32      0xffffffffu
+#define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
+#define NGC         13     // group-scan counters: has[6], hist[6], nrec
+
+struct Ctl { // device control block (one per engine), mirrored through pinned host memory
+	uint32_t poolUsed, err, nItems, nlogNew;
+	uint32_t blkBkt[8];     // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
+	uint32_t blkBktNew[8];
+	uint32_t gBkt[8], mBkt[8];         // this column: group / member index range per bucket
+	uint32_t gBktNext[8], mBktNext[8]; // next column
+	uint32_t recBkt[8];     // record index range per bucket (this column)
+	uint32_t nrec, Gnext, Mnext, poolCap;
+	int64_t  cpost[8];      // global start position of each bucket AFTER this column's insertions
+	uint32_t memTot[8];     // members per next symbol
+	uint32_t grpTot[16];    // grand totals of the NGC group counters
+};
+
+struct Dir {
+	uint32_t *order;   // [cap]      logical -> physical block id
+	int64_t  *cumLen;  // [cap+1]    symbols in front of logical block i (all buckets)
+	int64_t  *cumCnt;  // [cap+1][6] per-symbol counts in front of logical block i
+	size_t cap;
+};
+
+// =====================================================================================
+// Batch setup: split the NUL-delimited buffer into strings, transpose to column-major
+// =====================================================================================
+
+// 256 threads x 16 bytes: count NUL bytes per 4096-byte tile
+__global__ void __launch_bounds__(256) k_count_nul(const uint8_t *s, int64_t len, uint32_t *tileCnt)
+{
+	__shared__ uint32_t sm[8];
+	int64_t off = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 16;
+	uint32_t c = 0;
+	if (off + 16 <= len) {
+		uint4 v = *reinterpret_cast<const uint4*>(s + off);
+		c = (__popc(__vcmpeq4(v.x, 0)) + __popc(__vcmpeq4(v.y, 0)) + __popc(__vcmpeq4(v.z, 0)) + __popc(__vcmpeq4(v.w, 0))) >> 3;
+	} else for (int64_t i = off; i < len; ++i) c += s[i] == 0;
+	c = warp_sum(c);
+	if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int w = 0; w < 8; ++w) t += sm[w];
+		tileCnt[blockIdx.x] = t;
+	}
+}
+
+// strEnd[k] = byte offset of the k-th NUL
+__global__ void __launch_bounds__(256) k_string_ends(const uint8_t *s, int64_t len, const uint32_t *tilePre, int64_t *strEnd)
+{
+	__shared__ uint32_t sm[8];
+	int64_t off = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 16;
+	uint32_t c = 0;
+	uint8_t b[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { b[i] = off + i < len ? s[off + i] : 1; c += b[i] == 0; }
+	uint32_t v[1] = { c }, tot[1];
+	cta_excl_scan<1, 256, uint32_t>(v, tot, sm);
+	uint32_t k = tilePre[blockIdx.x] + v[0];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) if (b[i] == 0) strEnd[k++] = off + i;
+}
+
+__global__ void k_maxlen(const int64_t *strEnd, uint32_t m, unsigned long long *maxlen)
+{
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long l = 0;
+	if (k < m) l = (unsigned long long)(strEnd[k] - (k ? strEnd[k-1] + 1 : 0));
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(FULLMASK, l, o); l = y > l ? y : l; }
+	if ((threadIdx.x & 31) == 0 && l) atomicMax(maxlen, l);
+}
+
+// T[j*m + k] = j-th symbol of (reversed) string k, including its terminating NUL.
+// 32x32 tiles through shared memory: rows of a tile are strings, columns are symbol
+// indices; reads walk along strings, writes are coalesced along the string index.
+__global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64_t *strEnd, uint32_t m, int64_t ncol, uint8_t *T)
+{
+	__shared__ uint8_t tile[32][33];
+	__shared__ int64_t sStart[32];
+	__shared__ int32_t sLen[32];
+	const uint32_t k0 = blockIdx.x * 32;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 8 rows of 32
+	if (threadIdx.x < 32) {
+		uint32_t k = k0 + threadIdx.x;
+		int64_t st = 0; int32_t ln = -1;
+		if (k < m) { st = k ? strEnd[k-1] + 1 : 0; ln = (int32_t)(strEnd[k] - st); }
+		sStart[threadIdx.x] = st; sLen[threadIdx.x] = ln;
+	}
+	__syncthreads();
+	int32_t maxl = -1;
+	for (int i = 0; i < 32; ++i) maxl = sLen[i] > maxl ? sLen[i] : maxl;
+	for (int64_t j0 = 0; j0 <= maxl; j0 += 32) {
+		for (int r = ty; r < 32; r += 8) { // string r of the tile, symbol j0+tx
+			int64_t j = j0 + tx;
+			tile[r][tx] = j <= sLen[r] ? s[sStart[r] + j] : 0;
+		}
+		__syncthreads();
+		for (int c = ty; c < 32; c += 8) { // column j0+c, string k0+tx
+			int64_t j = j0 + c;
+			if (k0 + tx < m && j <= sLen[tx] && j < ncol) T[j * m + k0 + tx] = tile[tx][c];
+		}
+		__syncthreads();
+	}
+}
+
+// Column 0 state (mrope.c:279-284): sorted modes start with one group [0, n0) holding every
+// string; input order starts with one empty-interval group per string at the end of bucket $.
+__global__ void k_init_state(int sorted, uint32_t m, int64_t n0, int64_t *gL, int64_t *gSize, uint32_t *gOff, uint32_t *sid)
+{
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < m) sid[k] = k;
+	if (sorted) {
+		if (k == 0) { gL[0] = 0; gSize[0] = n0; gOff[0] = 0; gOff[1] = m; }
+	} else {
+		if (k < m) { gL[k] = n0; gSize[k] = 0; gOff[k] = k; }
+		if (k == 0) gOff[m] = m;
+	}
+}
+
+// =====================================================================================
+// Members: fetch the next symbol of every live string; stable 6-way partition
+// =====================================================================================
+
+__global__ void __launch_bounds__(256) k_member_fetch(const uint8_t *Tcol, const uint32_t *sid, uint32_t M, uint8_t *asym, uint32_t *tileTot)
+{
+	__shared__ uint32_t sm[6 * 8];
+	const uint32_t k = blockIdx.x * MEM_TILE + threadIdx.x * 4;
+	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 };
+	uint32_t packed = 0;
+	if (k < M) {
+		uint32_t id[4];
+		if (k + 4 <= M) { uint4 v = *reinterpret_cast<const uint4*>(sid + k); id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w; }
+		else for (int i = 0; i < 4; ++i) id[i] = k + i < M ? sid[k + i] : 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			if (k + i < M) {
+				uint32_t a = Tcol[id[i]];
+				packed |= a << (8 * i);
+#pragma unroll
+				for (int x = 0; x < 6; ++x) c[x] += a == x;
+			}
+		}
+		*reinterpret_cast<uint32_t*>(asym + k) = packed; // asym is padded to a multiple of 4
+	}
+#pragma unroll
+	for (int x = 0; x < 6; ++x) {
+		uint32_t t = warp_sum(c[x]);
+		if ((threadIdx.x & 31) == 0) sm[x * 8 + (threadIdx.x >> 5)] = t;
+	}
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		uint32_t t = 0;
+		for (int w = 0; w < 8; ++w) t += sm[threadIdx.x * 8 + w];
+		tileTot[(size_t)blockIdx.x * 6 + threadIdx.x] = t;
+	}
+}
+
+// dest = start of next bucket a + #earlier members with symbol a (mrope.c:303-309); members
+// whose symbol is the sentinel are finished and dropped (mrope.c:310)
+__global__ void __launch_bounds__(256) k_partition(const uint32_t *sid, const uint8_t *asym, uint32_t M, const uint32_t *tilePre,
+                                                   const Ctl *ctl, uint32_t *sidNext)
+{
+	__shared__ uint32_t sm[6 * 8];
+	const uint32_t k = blockIdx.x * MEM_TILE + threadIdx.x * 4;
+	uint32_t a4 = 0, id[4] = { 0, 0, 0, 0 };
+	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 }, tot[6];
+	if (k < M) {
+		a4 = *reinterpret_cast<const uint32_t*>(asym + k);
+		for (int i = 0; i < 4; ++i) if (k + i < M) {
+			id[i] = sid[k + i];
+			uint32_t a = (a4 >> (8 * i)) & 0xff;
+#pragma unroll
+			for (int x = 0; x < 6; ++x) c[x] += a == x;
+		}
+	}
+	cta_excl_scan<6, 256, uint32_t>(c, tot, sm);
+	if (k < M) {
+		uint32_t base[6];
+#pragma unroll
+		for (int x = 0; x < 6; ++x) base[x] = ctl->mBktNext[x] + tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
+		for (int i = 0; i < 4; ++i) if (k + i < M) {
+			uint32_t a = (a4 >> (8 * i)) & 0xff;
+			uint32_t d = 0;
+#pragma unroll
+			for (int x = 1; x < 6; ++x) if (a == x) d = base[x]++;
+			if (a) sidNext[d] = id[i];
+		}
+	}
+}
+
+// =====================================================================================
+// Rank: whole-index occ(., x) from the flat directory + one warp-decoded block
+// =====================================================================================
+
+// logical block whose range (cumLen[i], cumLen[i+1]] contains x (block 0 for x == 0)
+__device__ __forceinline__ uint32_t find_block(const int64_t *cumLen, uint32_t lo, uint32_t hi, int64_t x)
+{
+	// smallest i in [lo,hi) with cumLen[i+1] >= x; cumLen[hi] >= x is guaranteed by the caller
+	while (lo < hi) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		if (cumLen[mid + 1] >= x) hi = mid; else lo = mid + 1;
+	}
+	return lo;
+}
+
+// occ(a, x) for all six symbols; warp-cooperative, result valid in every lane.
+// scratch: runs[32*17] words + res[6] int64, private to the warp.
+__device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int lane,
+                           uint32_t *runs, int64_t *res, int64_t (&out)[6], uint32_t &err)
+{
+	uint32_t i = find_block(dir.cumLen, 0, nlog - 1, x);
+	if (i >= nlog) i = nlog - 1;
+	const uint32_t xrel = (uint32_t)(x - dir.cumLen[i]);
+	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes;
+	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, runs, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err);
+	const bool mine = xrel > basePos && xrel <= basePos + d.len;
+	if (xrel == 0) { if (lane < 6) res[lane] = dir.cumCnt[(size_t)i * 6 + lane]; }
+	else if (mine) {
+		uint32_t pc[6] = { baseCnt[0], baseCnt[1], baseCnt[2], baseCnt[3], baseCnt[4], baseCnt[5] };
+		uint32_t pos = basePos;
+		const uint32_t *r = runs + lane * RB2_RUNS_STRIDE;
+		for (uint32_t q = 0; q < d.nr && pos < xrel; ++q) {
+			uint32_t l = r[q] >> 3, s = r[q] & 7, take = xrel - pos < l ? xrel - pos : l;
+#pragma unroll
+			for (int a = 0; a < 6; ++a) pc[a] += s == a ? take : 0;
+			pos += l;
+		}
+#pragma unroll
+		for (int a = 0; a < 6; ++a) res[a] = dir.cumCnt[(size_t)i * 6 + a] + pc[a];
+	}
+	__syncwarp();
+#pragma unroll
+	for (int a = 0; a < 6; ++a) out[a] = res[a];
+	__syncwarp();
+}
+
+// sizes6[g][a] = #a in [gL, gL+gSize) for every group with a non-empty interval (rope_rank2a, mrope.c:202)
+__global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir dir, uint32_t nlog, uint32_t G,
+                                                     const int64_t *gL, const int64_t *gSize, int64_t *sizes6, Ctl *ctl)
+{
+	__shared__ uint32_t sRuns[4][32 * RB2_RUNS_STRIDE];
+	__shared__ int64_t sRes[4][6];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t g0 = (blockIdx.x * 4 + wid) * 32;
+	if (g0 >= G) return;
+	const uint32_t g = g0 + lane;
+	const int64_t myL = g < G ? gL[g] : 0, mySz = g < G ? gSize[g] : 0;
+	uint32_t todo = __ballot_sync(FULLMASK, mySz > 0), err = 0;
+	while (todo) {
+		const int src = __ffs(todo) - 1; todo &= todo - 1;
+		const int64_t L = __shfl_sync(FULLMASK, myL, src), sz = __shfl_sync(FULLMASK, mySz, src);
+		int64_t cl[6], cu[6];
+		warp_rank6(pool, dir, nlog, L, lane, sRuns[wid], sRes[wid], cl, err);
+		warp_rank6(pool, dir, nlog, L + sz, lane, sRuns[wid], sRes[wid], cu, err);
+		if (lane < 6) {
+			int64_t v = 0;
+#pragma unroll
+			for (int a = 0; a < 6; ++a) if (lane == a) v = cu[a] - cl[a];
+			sizes6[(size_t)(g0 + src) * 6 + lane] = v;
+		}
+	}
+	if (err) atomicOr(&ctl->err, err);
+}
+
+// API rank (mr_rank2a): one warp, up to two queries
+__global__ void __launch_bounds__(32) k_rank_query(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int64_t y, int64_t *out, Ctl *ctl)
+{
+	__shared__ uint32_t sRuns[32 * RB2_RUNS_STRIDE];
+	__shared__ int64_t sRes[6];
+	const int lane = threadIdx.x;
+	uint32_t err = 0;
+	int64_t c[6];
+	warp_rank6(pool, dir, nlog, x, lane, sRuns, sRes, c, err);
+	if (lane == 0) for (int a = 0; a < 6; ++a) out[a] = c[a];
+	if (y >= 0) {
+		warp_rank6(pool, dir, nlog, y, lane, sRuns, sRes, c, err);
+		if (lane == 0) for (int a = 0; a < 6; ++a) out[6 + a] = c[a];
+	}
+	if (err && lane == 0) atomicOr(&ctl->err, err);
+}
+
+// =====================================================================================
+// Groups: per-group histogram of next symbols, scan, record + next-group emission
+// =====================================================================================
+
+// cooperative #symbol counts of asym[S, E) for one warp; result in every lane
+__device__ __forceinline__ void warp_count_range(const uint8_t *asym, uint32_t S, uint32_t E, int lane, uint32_t (&h)[6])
+{
+#pragma unroll
+	for (int a = 0; a < 6; ++a) h[a] = 0;
+	for (uint32_t k = S + lane; k < E; k += 32) {
+		uint32_t s = asym[k];
+#pragma unroll
+		for (int a = 0; a < 6; ++a) h[a] += s == a;
+	}
+#pragma unroll
+	for (int a = 0; a < 6; ++a) h[a] = warp_sum(h[a]);
+}
+
+// histogram of a big group [S,E): direct count if short, else differences of the sampled
+// global prefix counts (tilePre has one entry per MEM_TILE members plus a terminal one)
+__device__ __forceinline__ void warp_group_hist(const uint8_t *asym, const uint32_t *tilePre, uint32_t S, uint32_t E, int lane, uint32_t (&h)[6])
+{
+	if (E - S <= 4 * MEM_TILE) { warp_count_range(asym, S, E, lane, h); return; }
+	uint32_t hs[6], he[6];
+	const uint32_t ts = S / MEM_TILE, te = E / MEM_TILE;
+	warp_count_range(asym, ts * MEM_TILE, S, lane, hs);
+	warp_count_range(asym, te * MEM_TILE, E, lane, he);
+#pragma unroll
+	for (int a = 0; a < 6; ++a)
+		h[a] = (tilePre[(size_t)te * 6 + a] + he[a]) - (tilePre[(size_t)ts * 6 + a] + hs[a]);
+}
+
+struct GroupArgs {
+	const uint32_t *gOff; const int64_t *gL, *gSize; const int64_t *sizes6; // current column
+	const uint8_t *asym; const uint32_t *tilePre;
+	uint32_t G;
+	uint32_t *ctaTot;        // [nCta][NGC]: totals (MODE 0) / exclusive prefix (MODE 1)
+	int64_t *gSizeNext; uint32_t *gOffNext;
+	int64_t *recP; uint8_t *recSym; uint32_t *recCnt, *recDst;
+	Ctl *ctl;
+};
+
+// MODE 0: reduce (per-CTA totals).  MODE 1: emit.  COMP: RCLO insertion order $,T,G,C,A,N.
+template <int MODE, bool COMP>
+__global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
+{
+	__shared__ uint32_t sm[NGC * 8];
+	const int lane = threadIdx.x & 31;
+	const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+	const bool valid = g < A.G;
+	const uint32_t S = valid ? A.gOff[g] : 0, E = valid ? A.gOff[g + 1] : 0, cnt = E - S;
+	uint32_t h[6] = { 0, 0, 0, 0, 0, 0 };
+	if (valid && cnt <= SMALL_GROUP) {
+		for (uint32_t k = S; k < E; ++k) {
+			uint32_t s = A.asym[k];
+#pragma unroll
+			for (int a = 0; a < 6; ++a) h[a] += s == a;
+		}
+	}
+	uint32_t big = __ballot_sync(FULLMASK, valid && cnt > SMALL_GROUP);
+	while (big) {
+		const int src = __ffs(big) - 1; big &= big - 1;
+		uint32_t hh[6];
+		warp_group_hist(A.asym, A.tilePre, __shfl_sync(FULLMASK, S, src), __shfl_sync(FULLMASK, E, src), lane, hh);
+		if (lane == src) {
+#pragma unroll
+			for (int a = 0; a < 6; ++a) h[a] = hh[a];
+		}
+	}
+	uint32_t v[NGC], tot[NGC];
+	uint32_t nrec = 0;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) {
+		v[a] = h[a] != 0;
+		v[6 + a] = h[a];
+		nrec += (h[a] + RB2_MAXRUN - 1) / RB2_MAXRUN;
+	}
+	v[12] = nrec;
+	cta_excl_scan<NGC, 256, uint32_t>(v, tot, sm);
+	if (MODE == 0) {
+		if (threadIdx.x == 0) {
+#pragma unroll
+			for (int k = 0; k < NGC; ++k) A.ctaTot[(size_t)blockIdx.x * NGC + k] = tot[k];
+		}
+		return;
+	}
+	if (!valid) return;
+#pragma unroll
+	for (int k = 0; k < NGC; ++k) v[k] += A.ctaTot[(size_t)blockIdx.x * NGC + k];
+	const Ctl *ctl = A.ctl;
+	// records of bucket b start at the record prefix of the bucket's first group
+#pragma unroll
+	for (int b = 0; b < 6; ++b) if (g == ctl->gBkt[b]) A.ctl->recBkt[b] = v[12];
+	const int64_t sz = A.gSize[g];
+	const bool nonempty = sz > 0 && A.sizes6 != 0;
+	int64_t P = A.gL[g];
+	uint32_t r = v[12];
+	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
+#pragma unroll
+	for (int slot = 0; slot < 6; ++slot) {
+		const int a = ord[slot];
+		const int64_t sza = nonempty ? A.sizes6[(size_t)g * 6 + a] : 0;
+		if (h[a]) {
+			uint32_t dst = NONE32;
+			if (a > 0) { // a child that continues: it is a group of the next column (bucket a)
+				dst = ctl->gBktNext[a] + v[a];
+				A.gSizeNext[dst] = sza;
+				A.gOffNext[dst] = ctl->mBktNext[a] + v[6 + a];
+			}
+			uint32_t rem = h[a];
+			while (rem) { // counts above the 4-byte run limit become several records at the same position
+				uint32_t c = rem < RB2_MAXRUN ? rem : RB2_MAXRUN;
+				A.recP[r] = P; A.recSym[r] = (uint8_t)a; A.recCnt[r] = c; A.recDst[r] = dst;
+				dst = NONE32; rem -= c; ++r;
+			}
+		}
+		P += sza; // new symbols of slot a go in front of the old a's of the interval (mrope.c:206-218)
+	}
+}
+
+// one thread: derive the next column's bucket ranges from the scan totals
+__global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
+{
+	uint32_t g = 0, m = 0, bad = 0;
+	ctl->gBktNext[0] = 0; ctl->mBktNext[0] = 0;
+	for (int a = 1; a <= 6; ++a) {
+		ctl->gBktNext[a] = g; ctl->mBktNext[a] = m;
+		if (a < 6) { g += ctl->grpTot[a]; m += ctl->grpTot[6 + a]; bad |= ctl->grpTot[6 + a] != ctl->memTot[a]; }
+	}
+	ctl->gBktNext[7] = g; ctl->mBktNext[7] = m;
+	ctl->Gnext = g; ctl->Mnext = m; ctl->nrec = ctl->grpTot[12];
+	for (int b = 0; b < 8; ++b) ctl->recBkt[b] = ctl->grpTot[12];
+	gOffNext[g] = m;
+	if (bad) ctl->err |= RB2_ERR_ORDER;
+}
+
+// =====================================================================================
+// Blocks: plan work items, merge records into leaf blocks, rebuild the directory
+// =====================================================================================
+
+__device__ __forceinline__ int bucket_of(const uint32_t *bkt, uint32_t i)
+{
+	int b = 0;
+#pragma unroll
+	for (int x = 1; x < 6; ++x) b += i >= bkt[x];
+	return b;
+}
+
+// recHi[i] = #records (global index) at positions <= end of logical block i, inside the
+// block's bucket.  A record at position P goes to the block with start < P <= end; P at the
+// very start of a bucket goes to the bucket's first block.
+__global__ void __launch_bounds__(256) k_rec_hi(Dir dir, uint32_t nlog, const Ctl *ctl, const int64_t *recP, uint32_t *recHi)
+{
+	const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= nlog) return;
+	const int b = bucket_of(ctl->blkBkt, i);
+	uint32_t lo = ctl->recBkt[b], hi = ctl->recBkt[b + 1];
+	if (i + 1 != ctl->blkBkt[b + 1]) {
+		const int64_t key = dir.cumLen[i + 1];
+		while (lo < hi) { // first record with P > key
+			uint32_t mid = lo + ((hi - lo) >> 1);
+			if (recP[mid] <= key) lo = mid + 1; else hi = mid;
+		}
+	} else lo = hi;
+	recHi[i] = lo;
+}
+
+struct ItemScan { // K=1: work items per logical block
+	const Ctl *ctl; const uint32_t *recHi; uint32_t nlog;
+	uint32_t *itemOff, *itemBlk; Ctl *ctlw;
+	__device__ uint32_t rec_lo(uint32_t i) const {
+		const int b = bucket_of(ctl->blkBkt, i);
+		return i == ctl->blkBkt[b] ? ctl->recBkt[b] : recHi[i - 1];
+	}
+	__device__ void load(uint64_t i, uint32_t (&v)[1]) const {
+		uint32_t n = recHi[i] - rec_lo((uint32_t)i);
+		v[0] = (n + RMAX - 1) / RMAX;
+	}
+	__device__ void store(uint64_t i, const uint32_t (&own)[1], const uint32_t (&pre)[1]) const {
+		itemOff[i] = pre[0];
+		for (uint32_t s = 0; s < own[0]; ++s) itemBlk[pre[0] + s] = (uint32_t)i;
+		if (i + 1 == nlog) { itemOff[nlog] = pre[0] + own[0]; ctlw->nItems = pre[0] + own[0]; }
+	}
+};
+
+struct MergeArgs {
+	uint8_t *pool; uint32_t *blkCnt; Dir dir; uint32_t nlog;
+	const uint32_t *recHi, *itemOff, *itemBlk;
+	const int64_t *recP; const uint8_t *recSym; const uint32_t *recCnt, *recDst;
+	int64_t *gLNext;
+	uint32_t *itemPieces, *itemFirst, *itemRest;
+	Ctl *ctl;
+};
+
+struct MergeSmem {
+	uint32_t runs[32 * RB2_RUNS_STRIDE];
+	uint8_t  stage[STAGE_BYTES];
+	uint32_t lcnt[32 * 7];          // per-lane running old-symbol counts (lane-private, stride 7)
+	uint32_t pcl[32 * 7];           // per-lane counts of the piece currently being written
+	uint32_t cut[MAXPIECES + 1];
+	uint32_t pcnt[MAXPIECES * 6];
+};
+
+// Sequential merge of one lane's old runs with the records that fall into them.
+// EMIT=false: only count output bytes.  EMIT=true: write bytes into `stage` from offset `o`,
+// note piece cuts / per-piece counts, and deliver rank(a, P) of every record.
+template <bool EMIT>
+__device__ __forceinline__ uint32_t lane_merge(const uint32_t *runs, uint32_t nr, uint32_t pos, uint32_t rlo, uint32_t rhi,
+                                               const MergeArgs &A, int64_t blkStart, uint32_t posLo, uint32_t posHi,
+                                               const int64_t *cumCntBlk, uint32_t *lc, uint32_t o, uint32_t T,
+                                               uint8_t *stage, uint32_t *cut, uint32_t *pcnt, uint32_t *pl)
+{
+	uint32_t psym = 8, plen = 0, r = rlo;
+	uint32_t curPiece = NONE32;
+	const uint32_t o0 = o;
+	uint32_t nextP = r < rhi ? (uint32_t)(A.recP[r] - blkStart) : 0xffffffffu;
+
+	auto flush = [&]() {
+		while (plen) {
+			const uint32_t l = plen < RB2_MAXRUN ? plen : RB2_MAXRUN;
+			const int nb = run_nbytes(l);
+			if (EMIT) {
+				enc_run(stage + o, psym, l);
+				const uint32_t p = (o + nb - 1) / T;
+				if (p && o <= p * T) cut[p] = o;      // this run is the first one of piece p
+				if (p != curPiece) {
+					if (curPiece != NONE32) {
+#pragma unroll
+						for (int a = 0; a < 6; ++a) if (pl[a]) { atomicAdd(&pcnt[curPiece * 6 + a], pl[a]); pl[a] = 0; }
+					}
+					curPiece = p;
+				}
+				pl[psym] += l;
+			}
+			o += nb; plen -= l;
+		}
+	};
+	auto emit = [&](uint32_t s, uint32_t l) {
+		if (l == 0) return;
+		if (s != psym) { flush(); psym = s; }
+		plen += l;
+	};
+	auto emit_old = [&](uint32_t s, uint32_t from, uint32_t to) { // old symbols [from,to), clipped to the item's window
+		const uint32_t a = from > posLo ? from : posLo, b = to < posHi ? to : posHi;
+		if (b > a) emit(s, b - a);
+	};
+	auto do_record = [&]() {
+		const uint32_t a = A.recSym[r];
+		if (EMIT) {
+			const uint32_t dst = A.recDst[r];
+			if (dst != NONE32) A.gLNext[dst] = A.ctl->cpost[a] + cumCntBlk[a] + lc[a];
+		}
+		emit(a, A.recCnt[r]);
+		++r;
+		nextP = r < rhi ? (uint32_t)(A.recP[r] - blkStart) : 0xffffffffu;
+	};
+
+	for (uint32_t q = 0; q < nr; ++q) {
+		const uint32_t s = runs[q] & 7, end = pos + (runs[q] >> 3);
+		uint32_t cur = pos;
+		while (nextP < end) {              // records in front of or inside this run
+			if (nextP > cur) { emit_old(s, cur, nextP); lc[s] += nextP - cur; cur = nextP; }
+			do_record();
+		}
+		emit_old(s, cur, end); lc[s] += end - cur;
+		pos = end;
+	}
+	while (r < rhi) do_record();           // records right behind the lane's last run
+	flush();
+	if (EMIT && curPiece != NONE32) {
+#pragma unroll
+		for (int a = 0; a < 6; ++a) if (pl[a]) { atomicAdd(&pcnt[curPiece * 6 + a], pl[a]); pl[a] = 0; }
+	}
+	return o - o0;
+}
+
+// One warp per work item = (logical block, slice of <= RMAX of its records).
+__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t w = blockIdx.x * MERGE_WARPS + wid;
+	if (w >= A.ctl->nItems) return;
+	MergeSmem &S = reinterpret_cast<MergeSmem*>(smraw)[wid];
+
+	const uint32_t i = A.itemBlk[w];
+	const uint32_t it0 = A.itemOff[i], nIt = A.itemOff[i + 1] - it0, sub = w - it0;
+	const int b = bucket_of(A.ctl->blkBkt, i);
+	const uint32_t recLo = i == A.ctl->blkBkt[b] ? A.ctl->recBkt[b] : A.recHi[i - 1], recHiB = A.recHi[i];
+	const uint32_t r0 = recLo + sub * RMAX, r1 = r0 + RMAX < recHiB ? r0 + RMAX : recHiB;
+	const int64_t blkStart = A.dir.cumLen[i];
+	const uint32_t phys = A.dir.order[i];
+	const int64_t *cumCntBlk = A.dir.cumCnt + (size_t)i * 6;
+
+	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes, err = 0;
+	warp_decode_block(A.pool + (size_t)phys * RB2_BLK, lane, S.runs, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err);
+
+	// the slice of old symbols this item re-emits: [posLo, posHi) relative to the block start
+	const uint32_t posLo = sub == 0 ? 0 : (uint32_t)(A.recP[r0] - blkStart);
+	const uint32_t posHi = sub + 1 == nIt ? blkLen : (uint32_t)(A.recP[r1] - blkStart);
+	// lane owns the records with position in (c_{lane-1}, c_lane], c = end of the lane's runs capped
+	// at posHi; lane 0 also takes position 0.  Lanes that end in front of posLo own nothing (every
+	// record of the item is >= posLo), so a record is always ranked by the lane that contains it.
+	uint32_t c = basePos + d.len;
+	c = c > posHi ? posHi : c;
+	uint32_t lo = r0, hi = r1;
+	{
+		const int64_t key = blkStart + c;
+		while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (A.recP[mid] <= key) lo = mid + 1; else hi = mid; }
+	}
+	const uint32_t rhi = lane == 31 ? r1 : lo; // the last lane sweeps up whatever is left (positions == posHi)
+	uint32_t rlo = __shfl_up_sync(FULLMASK, rhi, 1);
+	if (lane == 0) rlo = r0;
+
+	uint32_t *lc = S.lcnt + lane * 7, *pl = S.pcl + lane * 7;
+	const uint32_t *runs = S.runs + lane * RB2_RUNS_STRIDE;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) { lc[a] = baseCnt[a]; pl[a] = 0; }
+
+	// pass 1: output bytes per lane
+	const uint32_t myBytes = lane_merge<false>(runs, d.nr, basePos, rlo, rhi, A, blkStart, posLo, posHi, cumCntBlk, lc, 0, 1u << 30, S.stage, S.cut, S.pcnt, pl);
+	const uint32_t incl = warp_incl_scan(myBytes, lane);
+	const uint32_t out = __shfl_sync(FULLMASK, incl, 31);
+	if (out > STAGE_BYTES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_STAGE); return; }
+	const uint32_t K = out <= RB2_FILL ? 1 : (out + SPLIT_T - 1) / SPLIT_T;
+	const uint32_t T = K == 1 ? (1u << 30) : (out + K - 1) / K;
+	const bool inplace = nIt == 1;
+	const uint32_t nNew = inplace ? K - 1 : K;
+	uint32_t newBase = 0;
+	if (lane == 0 && nNew) {
+		newBase = atomicAdd(&A.ctl->poolUsed, nNew);
+		if (newBase + nNew > A.ctl->poolCap) { atomicOr(&A.ctl->err, RB2_ERR_POOL); newBase = NONE32; }
+	}
+	newBase = __shfl_sync(FULLMASK, newBase, 0);
+	if (newBase == NONE32) return;
+	if (K > MAXPIECES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_PIECES); return; }
+
+	for (int k = lane; k < MAXPIECES * 6; k += 32) S.pcnt[k] = 0;
+	if (lane <= MAXPIECES) S.cut[lane] = 0;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) { lc[a] = baseCnt[a]; pl[a] = 0; }
+	__syncwarp();
+
+	// pass 2: emit bytes, piece cuts, piece counts, ranks
+	lane_merge<true>(runs, d.nr, basePos, rlo, rhi, A, blkStart, posLo, posHi, cumCntBlk, lc, incl - myBytes, T, S.stage, S.cut, S.pcnt, pl);
+	__syncwarp();
+	if (lane == 0) S.cut[K] = out;
+	__syncwarp();
+
+	// copy the pieces out as leaf blocks: [uint16 nbytes][runs...], zero padded
+	const uint32_t firstPhys = inplace ? phys : newBase;
+	const uint32_t restPhys = inplace ? newBase : newBase + 1;
+	for (uint32_t k = 0; k < K; ++k) {
+		const uint32_t p = k == 0 ? firstPhys : restPhys + (k - 1);
+		const uint32_t st = S.cut[k], n = S.cut[k + 1] - st;
+		uint32_t wv[4];
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			uint32_t x = 0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int bp = lane * 16 + j * 4 + q;
+				uint32_t byte;
+				if (bp < 2) byte = bp == 0 ? (n & 0xff) : (n >> 8);
+				else byte = (uint32_t)(bp - 2) < n ? S.stage[st + bp - 2] : 0;
+				x |= byte << (8 * q);
+			}
+			wv[j] = x;
+		}
+		*(reinterpret_cast<uint4*>(A.pool + (size_t)p * RB2_BLK) + lane) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+		if (lane < 6) A.blkCnt[(size_t)p * 6 + lane] = S.pcnt[k * 6 + lane];
+	}
+	if (lane == 0) { A.itemPieces[w] = K; A.itemFirst[w] = firstPhys; A.itemRest[w] = restPhys; }
+	if (err && lane == 0) atomicOr(&A.ctl->err, err);
+}
+
+struct RebuildScan { // K=1: pieces per old logical block -> new logical order
+	const Ctl *ctl; Ctl *ctlw; uint32_t nlog;
+	const uint32_t *order, *itemOff, *itemPieces, *itemFirst, *itemRest;
+	uint32_t *orderNew;
+	__device__ void load(uint64_t i, uint32_t (&v)[1]) const {
+		uint32_t n = 0;
+		for (uint32_t it = itemOff[i]; it < itemOff[i + 1]; ++it) n += itemPieces[it];
+		v[0] = n ? n : 1;
+	}
+	__device__ void store(uint64_t i, const uint32_t (&own)[1], const uint32_t (&pre)[1]) const {
+		uint32_t o = pre[0];
+		if (itemOff[i] == itemOff[i + 1]) orderNew[o++] = order[i];
+		else for (uint32_t it = itemOff[i]; it < itemOff[i + 1]; ++it) {
+			orderNew[o++] = itemFirst[it];
+			for (uint32_t k = 1; k < itemPieces[it]; ++k) orderNew[o++] = itemRest[it] + (k - 1);
+		}
+#pragma unroll
+		for (int b = 0; b < 6; ++b) if (i == ctl->blkBkt[b]) ctlw->blkBktNew[b] = pre[0];
+		if (i + 1 == nlog) { ctlw->nlogNew = pre[0] + own[0]; ctlw->blkBktNew[6] = pre[0] + own[0]; ctlw->blkBktNew[7] = pre[0] + own[0]; }
+	}
+};
+
+struct DirScan { // K=7 (int64): per-symbol counts + length of every logical block -> cumCnt / cumLen
+	const uint32_t *order, *blkCnt; uint32_t nlog;
+	int64_t *cumLen, *cumCnt;
+	__device__ void load(uint64_t i, int64_t (&v)[7]) const {
+		const uint32_t *c = blkCnt + (size_t)order[i] * 6;
+		int64_t t = 0;
+#pragma unroll
+		for (int a = 0; a < 6; ++a) { v[a] = c[a]; t += c[a]; }
+		v[6] = t;
+	}
+	__device__ void store(uint64_t i, const int64_t (&own)[7], const int64_t (&pre)[7]) const {
+#pragma unroll
+		for (int a = 0; a < 6; ++a) cumCnt[i * 6 + a] = pre[a];
+		cumLen[i] = pre[6];
+		if (i + 1 == nlog) {
+#pragma unroll
+			for (int a = 0; a < 6; ++a) cumCnt[(i + 1) * 6 + a] = pre[a] + own[a];
+			cumLen[i + 1] = pre[6] + own[6];
+		}
+	}
+};
+
+// export: gather logical blocks [first, first+n) of the index into a contiguous staging area
+__global__ void k_gather_blocks(const uint8_t *pool, const uint32_t *order, const uint32_t *blkCnt, uint32_t first, uint32_t n,
+                                uint8_t *dst, int64_t *cnt)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t k = t >> 5, lane = t & 31;
+	if (k >= n) return;
+	const uint32_t p = order[first + k];
+	reinterpret_cast<uint4*>(dst + (size_t)k * RB2_BLK)[lane] = reinterpret_cast<const uint4*>(pool + (size_t)p * RB2_BLK)[lane];
+	if (cnt && lane < 6) cnt[(size_t)k * 6 + lane] = blkCnt[(size_t)p * 6 + lane];
+}
+
+// import: place n staged blocks at physical ids base.. and append them to the order array
+__global__ void k_scatter_blocks(uint8_t *pool, uint32_t *blkCnt, uint32_t base, uint32_t n, const uint8_t *src, const int64_t *cnt)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t k = t >> 5, lane = t & 31;
+	if (k >= n) return;
+	reinterpret_cast<uint4*>(pool + (size_t)(base + k) * RB2_BLK)[lane] = reinterpret_cast<const uint4*>(src + (size_t)k * RB2_BLK)[lane];
+	if (lane < 6) blkCnt[(size_t)(base + k) * 6 + lane] = (uint32_t)cnt[(size_t)k * 6 + lane];
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t n, uint32_t v0, uint32_t step)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = v0 + i * step;
+}
+
+// =====================================================================================
+// Host side
+// =====================================================================================
+
+template <typename T> struct DevBuf {
+	T *p = 0; size_t cap = 0;
+	void need(size_t n) {
+		if (n <= cap) return;
+		if (p) RB2_CUDA(cudaFree(p));
+		cap = n + n / 8 + 64;
+		RB2_CUDA(cudaMalloc(&p, cap * sizeof(T)));
+	}
+	void release() { if (p) RB2_CUDA(cudaFree(p)); p = 0; cap = 0; }
+};
+
+enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_N };
+
+struct rb2_engine {
+	int dev, so;
+	cudaStream_t st;
+	// leaf block pool + directory
+	uint8_t *pool; uint32_t *blkCnt; uint32_t poolCap;
+	Dir dir[2]; int cur;
+	uint32_t nlog; uint32_t blkBkt[8];
+	int64_t tot[6][6]; int64_t bktLen[6];
+	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
+	int64_t *dRankOut, *hRankOut;
+	// batch scratch
+	DevBuf<uint8_t> sbuf, T, asym, recSym, stage;
+	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
+	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recCnt, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, scanCta;
+	DevBuf<int64_t> scanCta64;
+	unsigned long long *dMaxLen;
+	// stats
+	rb2_stats_t stats;
+	int64_t lastP; int lastBkt; // single-string batches: where the sentinel went
+	cudaEvent_t ev[PH_N][2], evTot[2];
+};
+
+static void dir_alloc(Dir &d, size_t cap)
+{
+	d.cap = cap;
+	RB2_CUDA(cudaMalloc(&d.order, cap * sizeof(uint32_t)));
+	RB2_CUDA(cudaMalloc(&d.cumLen, (cap + 1) * sizeof(int64_t)));
+	RB2_CUDA(cudaMalloc(&d.cumCnt, (cap + 1) * 6 * sizeof(int64_t)));
+}
+static void dir_free(Dir &d)
+{
+	if (d.order) { RB2_CUDA(cudaFree(d.order)); RB2_CUDA(cudaFree(d.cumLen)); RB2_CUDA(cudaFree(d.cumCnt)); }
+	d.order = 0; d.cumLen = 0; d.cumCnt = 0; d.cap = 0;
+}
+
+static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+#define LAUNCH(e, kernel, grid, block, smem, ...) do { \
+	kernel<<<(grid), (block), (smem), (e)->st>>>(__VA_ARGS__); ++(e)->stats.n_launches; \
+	cudaError_t le_ = cudaGetLastError(); if (le_ != cudaSuccess) RB2_FATAL("launch of %s failed: %s", #kernel, cudaGetErrorString(le_)); } while (0)
+
+// three-phase scan driver over n elements
+template <int K, typename T, class F>
+static void run_scan(rb2_engine *e, F f, uint64_t n, DevBuf<T> &cta, T *grandDev)
+{
+	if (n == 0) return;
+	uint32_t nCta = cdiv(n, SCAN_NT);
+	cta.need((size_t)nCta * K + K);
+	LAUNCH(e, (scan_reduce<K, T, F>), nCta, SCAN_NT, 0, f, n, cta.p);
+	LAUNCH(e, (scan_mid<K, T>), 1, 1024, 0, cta.p, (uint64_t)nCta, grandDev ? grandDev : cta.p + (size_t)nCta * K);
+	LAUNCH(e, (scan_apply<K, T, F>), nCta, SCAN_NT, 0, f, n, cta.p);
+}
+
+static void ctl_pull(rb2_engine *e)
+{
+	RB2_CUDA(cudaMemcpyAsync(e->hctl, e->dctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	if (e->hctl->err) RB2_FATAL("device error flags 0x%x (1=block pool exhausted, 2=8-byte run in pool, 4=staging overflow, 8=scan mismatch, 16=too many pieces)", e->hctl->err);
+}
+static void ctl_push(rb2_engine *e)
+{
+	RB2_CUDA(cudaMemcpyAsync(e->dctl, e->hctl, sizeof(Ctl), cudaMemcpyHostToDevice, e->st));
+}
+
+// rebuild cumLen/cumCnt of the current directory from blkCnt + order
+static void rebuild_directory(rb2_engine *e)
+{
+	Dir &d = e->dir[e->cur];
+	DirScan f = { d.order, e->blkCnt, e->nlog, d.cumLen, d.cumCnt };
+	run_scan<7, int64_t, DirScan>(e, f, e->nlog, e->scanCta64, (int64_t*)0);
+}
+
+// refresh host mirrors of per-bucket totals from the directory
+static void pull_totals(rb2_engine *e)
+{
+	Dir &d = e->dir[e->cur];
+	std::vector<int64_t> c(7 * 6);
+	for (int b = 0; b <= 6; ++b)
+		RB2_CUDA(cudaMemcpyAsync(&c[b * 6], d.cumCnt + (size_t)e->blkBkt[b] * 6, 48, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	for (int b = 0; b < 6; ++b) {
+		e->bktLen[b] = 0;
+		for (int a = 0; a < 6; ++a) { e->tot[b][a] = c[(b + 1) * 6 + a] - c[b * 6 + a]; e->bktLen[b] += e->tot[b][a]; }
+	}
+}
+
+static void pool_reserve(rb2_engine *e, uint64_t blocks)
+{
+	if (blocks <= e->poolCap) return;
+	uint64_t cap = std::max<uint64_t>(blocks, (uint64_t)e->poolCap + e->poolCap / 2);
+	if (cap > 0xfffffff0ull) RB2_FATAL("block pool would exceed 2^32 blocks");
+	size_t freeB = 0, totB = 0;
+	RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+	if (cap * (RB2_BLK + 24ull) > freeB) {
+		cap = blocks;
+		if (cap * (RB2_BLK + 24ull) > freeB) RB2_FATAL("out of HBM: need %llu leaf blocks (%.1f GB), %.1f GB free", (unsigned long long)cap, cap * 536e-9, freeB * 1e-9);
+	}
+	uint8_t *np; uint32_t *nc;
+	RB2_CUDA(cudaMalloc(&np, cap * RB2_BLK));
+	RB2_CUDA(cudaMalloc(&nc, cap * 6 * sizeof(uint32_t)));
+	uint32_t used = e->hctl->poolUsed;
+	if (e->pool) {
+		RB2_CUDA(cudaMemcpyAsync(np, e->pool, (size_t)used * RB2_BLK, cudaMemcpyDeviceToDevice, e->st));
+		RB2_CUDA(cudaMemcpyAsync(nc, e->blkCnt, (size_t)used * 24, cudaMemcpyDeviceToDevice, e->st));
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+		RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt));
+	}
+	e->pool = np; e->blkCnt = nc; e->poolCap = (uint32_t)cap;
+}
+
+static void dir_reserve(rb2_engine *e, size_t blocks)
+{
+	for (int k = 0; k < 2; ++k) {
+		Dir &d = e->dir[k];
+		if (blocks <= d.cap) continue;
+		Dir nd; dir_alloc(nd, blocks + blocks / 4 + 1024);
+		if (k == e->cur && e->nlog) {
+			RB2_CUDA(cudaMemcpyAsync(nd.order, d.order, (size_t)e->nlog * 4, cudaMemcpyDeviceToDevice, e->st));
+			RB2_CUDA(cudaMemcpyAsync(nd.cumLen, d.cumLen, ((size_t)e->nlog + 1) * 8, cudaMemcpyDeviceToDevice, e->st));
+			RB2_CUDA(cudaMemcpyAsync(nd.cumCnt, d.cumCnt, ((size_t)e->nlog + 1) * 48, cudaMemcpyDeviceToDevice, e->st));
+			RB2_CUDA(cudaStreamSynchronize(e->st));
+		}
+		dir_free(d);
+		d = nd;
+	}
+}
+
+extern "C" int rb2_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
+{
+	if (sorting_order < 0 || sorting_order > 2) RB2_FATAL("sorting order must be 0, 1 or 2 (mrope.c:18)");
+	int n = rb2_device_count();
+	if (n <= 0) RB2_FATAL("no CUDA device visible: this library has no CPU path");
+	if (device < 0 || device >= n) RB2_FATAL("device %d out of range (0..%d)", device, n - 1);
+	RB2_CUDA(cudaSetDevice(device));
+	rb2_engine *e = new rb2_engine();
+	memset(&e->stats, 0, sizeof(e->stats));
+	e->dev = device; e->so = sorting_order;
+	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
+	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
+	RB2_CUDA(cudaMalloc(&e->dRankOut, 12 * sizeof(int64_t)));
+	RB2_CUDA(cudaMallocHost(&e->hRankOut, 12 * sizeof(int64_t)));
+	RB2_CUDA(cudaMalloc(&e->dMaxLen, sizeof(unsigned long long)));
+	memset(e->hctl, 0, sizeof(Ctl));
+	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) RB2_CUDA(cudaEventCreate(&e->ev[p][k]));
+	for (int k = 0; k < 2; ++k) RB2_CUDA(cudaEventCreate(&e->evTot[k]));
+	e->pool = 0; e->blkCnt = 0; e->poolCap = 0;
+	memset(e->dir, 0, sizeof(e->dir)); e->cur = 0;
+	RB2_CUDA(cudaFuncSetAttribute(k_merge_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(MergeSmem))));
+	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
+	pool_reserve(e, 1024);
+	dir_reserve(e, 1024);
+	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
+	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
+	LAUNCH(e, k_fill_u32, 1, 32, 0, e->dir[0].order, 6u, 0u, 1u);
+	e->nlog = 6;
+	for (int b = 0; b < 8; ++b) e->blkBkt[b] = b < 6 ? b : 6;
+	e->hctl->poolUsed = 6; e->hctl->poolCap = e->poolCap;
+	ctl_push(e);
+	rebuild_directory(e);
+	pull_totals(e);
+	return e;
+}
+
+extern "C" void rb2_destroy(rb2_engine_t *e)
+{
+	if (!e) return;
+	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
+	dir_free(e->dir[0]); dir_free(e->dir[1]);
+	e->sbuf.release(); e->T.release(); e->asym.release(); e->recSym.release(); e->stage.release();
+	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
+	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
+	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recCnt.release(); e->recDst.release(); e->recHi.release();
+	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release();
+	e->scanCta.release(); e->scanCta64.release();
+	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
+	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
+	RB2_CUDA(cudaFree(e->dMaxLen));
+	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
+	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);
+	RB2_CUDA(cudaStreamDestroy(e->st));
+	delete e;
+}
+
+extern "C" int rb2_sorting_order(const rb2_engine_t *e) { return e->so; }
+
+static inline void ph_begin(rb2_engine *e, int p) { RB2_CUDA(cudaEventRecord(e->ev[p][0], e->st)); }
+static inline void ph_end(rb2_engine *e, int p) { RB2_CUDA(cudaEventRecord(e->ev[p][1], e->st)); }
+static void ph_collect(rb2_engine *e, uint32_t mask)
+{
+	double *acc[PH_N] = { &e->stats.ms_h2d, &e->stats.ms_transpose, &e->stats.ms_members, &e->stats.ms_groups, &e->stats.ms_merge,
+	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members };
+	for (int p = 0; p < PH_N; ++p) if (mask >> p & 1) {
+		float ms = 0;
+		RB2_CUDA(cudaEventElapsedTime(&ms, e->ev[p][0], e->ev[p][1]));
+		*acc[p] += ms;
+	}
+}
+
+// Merge `nrec` insertion records (sorted by position; per-bucket ranges in dctl->recBkt) into
+// the leaf blocks and rebuild the directory.  The device control block must already hold
+// blkBkt / recBkt / cpost for this step; the host mirror e->hctl must be current.
+// gLNext[recDst[r]] receives cpost[sym] + occ(sym, position) for every record with a target.
+static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
+{
+	Ctl *h = e->hctl;
+	// ---- plan items, make room --------------------------------------------------
+	ph_begin(e, PH_DIR);
+	e->recHi.need(e->nlog);
+	e->itemOff.need((size_t)e->nlog + 1);
+	const uint64_t maxItems = (uint64_t)std::min<uint64_t>(e->nlog, nrec) + nrec / RMAX + 1;
+	e->itemBlk.need(maxItems); e->itemPieces.need(maxItems); e->itemFirst.need(maxItems); e->itemRest.need(maxItems);
+	// worst case every touched block splits and every record adds 8 bytes
+	const uint64_t needBlocks = (uint64_t)h->poolUsed + maxItems * 21 / 10 + (uint64_t)nrec / 60 + 64;
+	if (needBlocks > e->poolCap) { pool_reserve(e, needBlocks); h->poolCap = e->poolCap; ctl_push(e); }
+	dir_reserve(e, needBlocks);
+	Dir &dc = e->dir[e->cur], &dnx = e->dir[e->cur ^ 1];
+	LAUNCH(e, k_rec_hi, cdiv(e->nlog, 256), 256, 0, dc, e->nlog, e->dctl, e->recP.p, e->recHi.p);
+	ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemBlk.p, e->dctl };
+	run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0);
+	ph_end(e, PH_DIR);
+
+	// ---- merge -----------------------------------------------------------------
+	ph_begin(e, PH_MERGE);
+	MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
+	                 e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, gLNext,
+	                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->dctl };
+	LAUNCH(e, k_merge_blocks, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(MergeSmem), ma);
+	ph_end(e, PH_MERGE);
+	++e->stats.n_merge_launches;
+
+	// ---- new logical order + directory --------------------------------------------
+	ph_begin(e, PH_DIR2);
+	const uint32_t usedBefore = h->poolUsed;
+	RebuildScan rs = { e->dctl, e->dctl, e->nlog, dc.order, e->itemOff.p, e->itemPieces.p, e->itemFirst.p, e->itemRest.p, dnx.order };
+	run_scan<1, uint32_t, RebuildScan>(e, rs, e->nlog, e->scanCta, (uint32_t*)0);
+	ctl_pull(e);
+	const uint32_t nItems = h->nItems;
+	e->nlog = h->nlogNew;
+	for (int b = 0; b < 8; ++b) e->blkBkt[b] = h->blkBktNew[b];
+	e->cur ^= 1;
+	rebuild_directory(e);
+	ph_end(e, PH_DIR2);
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	ph_collect(e, (1u << PH_MERGE) | (1u << PH_DIR) | (1u << PH_DIR2));
+	e->stats.merge_blocks += nItems;
+	// every item reads one leaf block and writes it back, plus the freshly allocated pieces
+	e->stats.merge_bytes_rw += ((int64_t)nItems * 2 + (int64_t)(h->poolUsed - usedBefore)) * RB2_BLK;
+
+}
+
+// One sub-batch whose strings already sit in device memory at `s` (len bytes, ends with NUL).
+static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
+{
+	const int sorted = e->so != RB2_SO_IO;
+	// ---- split into strings, transpose -------------------------------------------------
+	ph_begin(e, PH_TRANSPOSE);
+	const uint32_t nT = cdiv(len, 4096);
+	e->tileA.need((size_t)nT + 2);
+	LAUNCH(e, k_count_nul, nT, 256, 0, s, len, e->tileA.p);
+	uint32_t *dTot = e->tileA.p + nT; // grand total lands behind the tile array
+	LAUNCH(e, (scan_mid<1, uint32_t>), 1, 1024, 0, e->tileA.p, (uint64_t)nT, dTot);
+	uint32_t m = 0;
+	RB2_CUDA(cudaMemcpyAsync(&m, dTot, 4, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	if (m == 0) RB2_FATAL("batch holds no terminated string");
+	e->strEnd.need(m);
+	LAUNCH(e, k_string_ends, nT, 256, 0, s, len, e->tileA.p, e->strEnd.p);
+	RB2_CUDA(cudaMemsetAsync(e->dMaxLen, 0, 8, e->st));
+	LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, m, e->dMaxLen);
+	unsigned long long maxlen = 0;
+	RB2_CUDA(cudaMemcpyAsync(&maxlen, e->dMaxLen, 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	const int64_t ncol = (int64_t)maxlen + 1;
+	{
+		size_t freeB = 0, totB = 0;
+		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+		if ((size_t)ncol * m > e->T.cap && (size_t)ncol * m > freeB + e->T.cap)
+			RB2_FATAL("column-major symbol matrix (%lld columns x %u strings) does not fit in HBM", (long long)ncol, m);
+	}
+	e->T.need((size_t)ncol * m);
+	LAUNCH(e, k_transpose, cdiv(m, 32), 256, 0, s, e->strEnd.p, m, ncol, e->T.p);
+	ph_end(e, PH_TRANSPOSE);
+
+	// ---- state for column 0 (mrope.c:279-285) -------------------------------------------
+	for (int k = 0; k < 2; ++k) { e->gL[k].need(m); e->gSize[k].need(m); e->gOff[k].need((size_t)m + 1); e->sid[k].need((size_t)m + 4); }
+	e->asym.need((size_t)m + 8);
+	const size_t recCap = (size_t)m + m / RB2_MAXRUN + 64;
+	e->recP.need(recCap); e->recSym.need(recCap); e->recCnt.need(recCap); e->recDst.need(recCap);
+	const int64_t n0 = e->bktLen[0];
+	const bool useSizes = sorted && n0 > 0;
+	if (useSizes) e->sizes6.need((size_t)m * 6);
+	int cs = 0; // current state buffer
+	LAUNCH(e, k_init_state, cdiv(m, 256), 256, 0, sorted, m, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
+	uint32_t G = sorted ? 1 : m, M = m;
+	uint32_t gBkt[8], mBkt[8];
+	for (int b = 0; b < 8; ++b) { gBkt[b] = b == 0 ? 0 : G; mBkt[b] = b == 0 ? 0 : M; }
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	ph_collect(e, 1u << PH_TRANSPOSE);
+
+	for (int64_t col = 0; M > 0; ++col) {
+		if (col >= ncol) RB2_FATAL("internal: live strings beyond the last column");
+		Dir &d = e->dir[e->cur];
+		Ctl *h = e->hctl;
+		// control block for this column
+		for (int b = 0; b < 8; ++b) { h->gBkt[b] = gBkt[b]; h->mBkt[b] = mBkt[b]; h->blkBkt[b] = e->blkBkt[b]; }
+		{ // bucket starts after this column: every member of bucket b inserts one symbol into it
+			int64_t acc = 0;
+			for (int b = 0; b < 6; ++b) { h->cpost[b] = acc; acc += e->bktLen[b] + (mBkt[b + 1] - mBkt[b]); }
+			h->cpost[6] = h->cpost[7] = acc;
+		}
+		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0;
+		ctl_push(e);
+
+		// ---- members: next symbol + tile histograms ---------------------------------
+		ph_begin(e, PH_MEMBERS);
+		const uint32_t nTile = cdiv(M, MEM_TILE);
+		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
+		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
+		LAUNCH(e, k_member_fetch, nTile, 256, 0, e->T.p + (size_t)col * m, e->sid[cs].p, M, e->asym.p, e->tileB.p);
+		LAUNCH(e, (scan_mid<6, uint32_t>), 1, 1024, 0, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot);
+		ph_end(e, PH_MEMBERS);
+
+		// ---- groups: interval sizes, histograms, records ------------------------------
+		ph_begin(e, PH_GROUPS);
+		if (useSizes)
+			LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+		const uint32_t nGC = cdiv(G, 256);
+		e->grpCta.need((size_t)nGC * NGC + NGC);
+		GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
+		                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, e->dctl };
+		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
+		else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
+		LAUNCH(e, (scan_mid<NGC, uint32_t>), 1, 1024, 0, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot);
+		LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p);
+		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
+		else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
+		ph_end(e, PH_GROUPS);
+
+		ph_begin(e, PH_MEMBERS2);
+		LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[cs ^ 1].p);
+		ph_end(e, PH_MEMBERS2);
+		ctl_pull(e);
+		ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2));
+		const uint32_t nrec = h->nrec;
+
+		if (m == 1) { // remember where the string's sentinel goes (mr_insert1's return value)
+			RB2_CUDA(cudaMemcpyAsync(&e->lastP, e->recP.p, 8, cudaMemcpyDeviceToHost, e->st));
+			RB2_CUDA(cudaStreamSynchronize(e->st));
+			e->lastBkt = 0;
+			for (int b = 0; b < 6; ++b) if (gBkt[b + 1] > gBkt[b]) e->lastBkt = b;
+		}
+		apply_records(e, nrec, e->gL[cs ^ 1].p);
+		e->stats.n_records += nrec;
+		++e->stats.n_columns;
+
+		// ---- advance to the next column ---------------------------------------------
+		for (int b = 0; b < 6; ++b) e->bktLen[b] += mBkt[b + 1] - mBkt[b];
+		for (int b = 0; b < 8; ++b) { gBkt[b] = h->gBktNext[b]; mBkt[b] = h->mBktNext[b]; }
+		G = h->Gnext; M = h->Mnext;
+		cs ^= 1;
+	}
+	pull_totals(e);
+	e->stats.n_strings += m;
+	e->stats.n_symbols += len;
+	e->stats.pool_blocks = e->hctl->poolUsed;
+	e->stats.pool_capacity = e->poolCap;
+}
+
+// sub-batching: the text output is independent of how a batch is cut, so
+// huge inputs are processed as several device batches to bound the per-batch working set.
+#define RB2_MAX_BATCH_BYTES (24ll << 30)
+
+extern "C" void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev)
+{
+	if (len <= 0) RB2_FATAL("mr_insert_multi: empty batch (mrope.c:268)");
+	RB2_CUDA(cudaSetDevice(e->dev));
+	if (((uintptr_t)s_dev & 15) != 0) RB2_FATAL("device batch must be 16-byte aligned");
+	if (len > RB2_MAX_BATCH_BYTES) RB2_FATAL("device-resident batches are limited to %lld bytes; use the host entry point", (long long)RB2_MAX_BATCH_BYTES);
+	RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
+	insert_device_batch(e, len, s_dev);
+	RB2_CUDA(cudaEventRecord(e->evTot[1], e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	float ms = 0; RB2_CUDA(cudaEventElapsedTime(&ms, e->evTot[0], e->evTot[1]));
+	e->stats.ms_total += ms;
+}
+
+extern "C" void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s)
+{
+	if (len <= 0 || s[len - 1] != 0) RB2_FATAL("mr_insert_multi: batch must be non-empty and end with NUL (mrope.c:268)");
+	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
+	int64_t off = 0;
+	while (off < len) {
+		int64_t n = len - off;
+		if (n > RB2_MAX_BATCH_BYTES) { // cut behind the last NUL inside the window
+			n = RB2_MAX_BATCH_BYTES;
+			while (n > 0 && s[off + n - 1] != 0) --n;
+			if (n == 0) RB2_FATAL("a single string longer than %lld bytes is not supported", (long long)RB2_MAX_BATCH_BYTES);
+		}
+		e->sbuf.need((size_t)n + 16);
+		ph_begin(e, PH_H2D);
+		RB2_CUDA(cudaMemcpyAsync(e->sbuf.p, s + off, (size_t)n, cudaMemcpyHostToDevice, e->st));
+		ph_end(e, PH_H2D);
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+		ph_collect(e, 1u << PH_H2D);
+		insert_device_batch(e, n, e->sbuf.p);
+		off += n;
+	}
+	RB2_CUDA(cudaEventRecord(e->evTot[1], e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	float ms = 0; RB2_CUDA(cudaEventElapsedTime(&ms, e->evTot[0], e->evTot[1]));
+	e->stats.ms_total += ms;
+}
+
+extern "C" void rb2_counts(rb2_engine_t *e, int64_t c[36])
+{
+	for (int b = 0; b < 6; ++b) for (int a = 0; a < 6; ++a) c[b * 6 + a] = e->tot[b][a];
+}
+
+extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6])
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	int64_t total = 0;
+	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
+	if (x < 0 || x > total || y > total) RB2_FATAL("rank position out of range");
+	if (!cy) y = -1;
+	LAUNCH(e, k_rank_query, 1, 32, 0, e->pool, e->dir[e->cur], e->nlog, x, y, e->dRankOut, e->dctl);
+	RB2_CUDA(cudaMemcpyAsync(e->hRankOut, e->dRankOut, 12 * 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	for (int a = 0; a < 6; ++a) { cx[a] = e->hRankOut[a]; if (y >= 0) cy[a] = e->hRankOut[6 + a]; }
+}
+
+extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)
+{
+	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
+	return (int64_t)e->blkBkt[bucket + 1] - e->blkBkt[bucket];
+}
+
+extern "C" int64_t rb2_fetch_blocks(rb2_engine_t *e, int bucket, int64_t first, int64_t n, uint8_t *dst, int64_t *cnt)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	int64_t nb = rb2_num_blocks(e, bucket);
+	if (first < 0 || first > nb) RB2_FATAL("block index out of range");
+	if (n > nb - first) n = nb - first;
+	if (n <= 0) return 0;
+	e->stage.need((size_t)n * RB2_BLK);
+	if (cnt) e->stageCnt.need((size_t)n * 6);
+	LAUNCH(e, k_gather_blocks, cdiv((uint64_t)n * 32, 256), 256, 0, e->pool, e->dir[e->cur].order, e->blkCnt,
+	       (uint32_t)(e->blkBkt[bucket] + first), (uint32_t)n, e->stage.p, cnt ? e->stageCnt.p : (int64_t*)0);
+	RB2_CUDA(cudaMemcpyAsync(dst, e->stage.p, (size_t)n * RB2_BLK, cudaMemcpyDeviceToHost, e->st));
+	if (cnt) RB2_CUDA(cudaMemcpyAsync(cnt, e->stageCnt.p, (size_t)n * 48, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	return n;
+}
+
+extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const uint8_t *src, const int64_t *cnt)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
+	if (n <= 0) return;
+	// the bucket's blocks are [blkBkt[b], blkBkt[b+1]); new blocks are inserted at its right end.
+	// An initially empty bucket consists of one empty block, which is replaced.
+	const uint32_t used = e->hctl->poolUsed;
+	pool_reserve(e, (uint64_t)used + n + 64);
+	dir_reserve(e, (size_t)e->nlog + n + 64);
+	e->stage.need((size_t)n * RB2_BLK);
+	e->stageCnt.need((size_t)n * 6);
+	RB2_CUDA(cudaMemcpyAsync(e->stage.p, src, (size_t)n * RB2_BLK, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(e->stageCnt.p, cnt, (size_t)n * 48, cudaMemcpyHostToDevice, e->st));
+	LAUNCH(e, k_scatter_blocks, cdiv((uint64_t)n * 32, 256), 256, 0, e->pool, e->blkCnt, used, (uint32_t)n, e->stage.p, e->stageCnt.p);
+	// splice into the logical order (host side: restore is not on the hot path)
+	std::vector<uint32_t> ord(e->nlog);
+	RB2_CUDA(cudaMemcpyAsync(ord.data(), e->dir[e->cur].order, (size_t)e->nlog * 4, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	const bool replaceEmpty = e->bktLen[bucket] == 0 && e->blkBkt[bucket + 1] - e->blkBkt[bucket] == 1;
+	std::vector<uint32_t> nw;
+	nw.reserve(e->nlog + n);
+	const uint32_t cutAt = e->blkBkt[bucket + 1];
+	for (uint32_t i = 0; i < cutAt - (replaceEmpty ? 1 : 0); ++i) nw.push_back(ord[i]);
+	for (int64_t k = 0; k < n; ++k) nw.push_back(used + (uint32_t)k);
+	for (uint32_t i = cutAt; i < e->nlog; ++i) nw.push_back(ord[i]);
+	const uint32_t delta = (uint32_t)n - (replaceEmpty ? 1 : 0);
+	for (int b = bucket + 1; b < 8; ++b) e->blkBkt[b] += delta;
+	e->nlog = (uint32_t)nw.size();
+	RB2_CUDA(cudaMemcpyAsync(e->dir[e->cur].order, nw.data(), nw.size() * 4, cudaMemcpyHostToDevice, e->st));
+	e->hctl->poolUsed = used + (uint32_t)n;
+	e->hctl->poolCap = e->poolCap;
+	ctl_push(e);
+	rebuild_directory(e);
+	pull_totals(e);
+	e->stats.pool_blocks = e->hctl->poolUsed;
+	e->stats.pool_capacity = e->poolCap;
+}
+
+extern "C" void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st) { *st = e->stats; }
+extern "C" void rb2_reset_stats(rb2_engine_t *e)
+{
+	int64_t pb = e->stats.pool_blocks, pc = e->stats.pool_capacity;
+	memset(&e->stats, 0, sizeof(e->stats));
+	e->stats.pool_blocks = pb; e->stats.pool_capacity = pc;
+}
+extern "C" void *rb2_stream(rb2_engine_t *e) { return (void*)e->st; }
+extern "C" void *rb2_dev_alloc(rb2_engine_t *e, int64_t bytes)
+{
+	void *p = 0;
+	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_CUDA(cudaMalloc(&p, (size_t)bytes + 16));
+	return p;
+}
+extern "C" void rb2_dev_free(rb2_engine_t *e, void *p) { RB2_CUDA(cudaSetDevice(e->dev)); RB2_CUDA(cudaFree(p)); }
+extern "C" void rb2_dev_upload(rb2_engine_t *e, void *dst, const void *src, int64_t bytes)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+}
+
+// ---- single-run and bucket-local entry points behind rope.h ---------------------------------
+
+// global position of the start of bucket b
+static int64_t bucket_start(const rb2_engine *e, int b)
+{
+	int64_t s = 0;
+	for (int x = 0; x < b; ++x) s += e->bktLen[x];
+	return s;
+}
+
+// rope_insert_run (rope.c:114-148): insert rl copies of a behind the first x symbols of
+// `bucket`; returns the bucket-local rank(a, x) before the insertion.
+extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a, int64_t rl)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	if (bucket < 0 || bucket > 5 || a < 0 || a > 5 || rl <= 0) RB2_FATAL("rb2_insert_run: bad argument");
+	if (x < 0 || x > e->bktLen[bucket]) RB2_FATAL("rb2_insert_run: position out of range");
+	const uint32_t k = (uint32_t)((rl + RB2_MAXRUN - 1) / RB2_MAXRUN);
+	e->recP.need(k); e->recSym.need(k); e->recCnt.need(k); e->recDst.need(k);
+	std::vector<int64_t> P(k, bucket_start(e, bucket) + x);
+	std::vector<uint8_t> S(k, (uint8_t)a);
+	std::vector<uint32_t> C(k, RB2_MAXRUN), D(k, NONE32);
+	C[k - 1] = (uint32_t)(rl - (int64_t)(k - 1) * RB2_MAXRUN);
+	D[0] = 0;
+	RB2_CUDA(cudaMemcpyAsync(e->recP.p, P.data(), k * 8, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(e->recSym.p, S.data(), k, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(e->recCnt.p, C.data(), k * 4, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(e->recDst.p, D.data(), k * 4, cudaMemcpyHostToDevice, e->st));
+	Ctl *h = e->hctl;
+	for (int b = 0; b < 8; ++b) { h->blkBkt[b] = e->blkBkt[b]; h->recBkt[b] = b <= bucket ? 0 : k; h->cpost[b] = 0; }
+	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0;
+	ctl_push(e);
+	apply_records(e, k, e->dRankOut);
+	RB2_CUDA(cudaMemcpyAsync(e->hRankOut, e->dRankOut, 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	int64_t z = e->hRankOut[0];
+	for (int b = 0; b < bucket; ++b) z -= e->tot[b][a];
+	pull_totals(e);
+	e->stats.pool_blocks = e->hctl->poolUsed; e->stats.pool_capacity = e->poolCap;
+	return z;
+}
+
+// rope_rank2a (rope.c:179-194) on one bucket: counts inside the bucket only
+extern "C" void rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6])
+{
+	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
+	if (x < 0 || x > e->bktLen[bucket] || y > e->bktLen[bucket]) RB2_FATAL("rope_rank2a: position out of range");
+	const int64_t s = bucket_start(e, bucket);
+	int64_t tmp[6];
+	rb2_rank2a(e, s + x, y >= 0 && cy ? s + y : -1, cx, cy ? cy : tmp);
+	for (int a = 0; a < 6; ++a) {
+		int64_t pre = 0;
+		for (int b = 0; b < bucket; ++b) pre += e->tot[b][a];
+		cx[a] -= pre;
+		if (y >= 0 && cy) cy[a] -= pre;
+	}
+}
+
+// mr_insert1's return value (mrope.c:67): the rank of the sentinel of the string that was
+// inserted last as a single-string batch, local to the bucket it went into.
+extern "C" int64_t rb2_last_sentinel_rank(rb2_engine_t *e)
+{
+	int64_t cx[6];
+	rb2_rank2a(e, e->lastP, -1, cx, 0);
+	int64_t z = cx[0];
+	for (int b = 0; b < e->lastBkt; ++b) z -= e->tot[b][0];
+	return z;
+}
