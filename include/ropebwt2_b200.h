@@ -64,6 +64,8 @@ int  rb2_device_count(void);
 rb2_engine_t *rb2_create(int device, int sorting_order);
 void rb2_destroy(rb2_engine_t *e);
 int  rb2_sorting_order(const rb2_engine_t *e);
+/* Empty the index (six empty buckets, as after rb2_create) but keep all HBM allocations. */
+void rb2_reset(rb2_engine_t *e);
 
 /*
  * Insert a batch.  `s` holds `len` bytes of nt6 codes ($=0 A=1 C=2 G=3 T=4 N=5), each string
@@ -97,6 +99,14 @@ void *rb2_stream(rb2_engine_t *e);
 void *rb2_dev_alloc(rb2_engine_t *e, int64_t bytes);
 void  rb2_dev_free(rb2_engine_t *e, void *p);
 void  rb2_dev_upload(rb2_engine_t *e, void *dst_dev, const void *src_host, int64_t bytes);
+/* pinned host memory for batches handed to rb2_insert_multi / mr_insert_multi (faster H2D) */
+void *rb2_host_alloc(int64_t bytes);
+void  rb2_host_free(void *p);
+/* rope.h back ends: one run into one bucket (rope_insert_run, rope.c:114-148) and bucket-local
+ * rank (rope_rank2a, rope.c:179-194); mr_insert1's return value (mrope.c:67) */
+int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a, int64_t rl);
+void    rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6]);
+int64_t rb2_last_sentinel_rank(rb2_engine_t *e);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,8 @@ RLE_SYMBOLS = ["rle_count", "rle_print"]
 RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_destroy", "rb2_sorting_order", "rb2_insert_multi",
                "rb2_insert_multi_dev", "rb2_counts", "rb2_rank2a", "rb2_num_blocks", "rb2_fetch_blocks",
                "rb2_load_blocks", "rb2_get_stats", "rb2_reset_stats", "rb2_stream", "rb2_dev_alloc",
-               "rb2_dev_free", "rb2_dev_upload"]
+               "rb2_dev_free", "rb2_dev_upload", "rb2_reset", "rb2_host_alloc", "rb2_host_free", "rb2_insert_run",
+               "rb2_bucket_rank2a", "rb2_last_sentinel_rank"]
 
 
 class Stats(C.Structure):
@@ -98,6 +99,15 @@ def load(rebuild: bool = False) -> C.CDLL:
     L.rb2_dev_alloc.argtypes = [C.c_void_p, C.c_int64]
     L.rb2_dev_free.argtypes = [C.c_void_p, C.c_void_p]
     L.rb2_dev_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.rb2_reset.argtypes = [C.c_void_p]
+    L.rb2_host_alloc.restype = C.c_void_p
+    L.rb2_host_alloc.argtypes = [C.c_int64]
+    L.rb2_host_free.argtypes = [C.c_void_p]
+    L.rb2_insert_run.restype = C.c_int64
+    L.rb2_insert_run.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64]
+    L.rb2_bucket_rank2a.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _i64p, _i64p]
+    L.rb2_last_sentinel_rank.restype = C.c_int64
+    L.rb2_last_sentinel_rank.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -233,6 +243,12 @@ class Engine:
 
     def reset_stats(self) -> None:
         self.L.rb2_reset_stats(self.h)
+
+    def reset(self) -> None:
+        self.L.rb2_reset(self.h)
+
+    def total(self) -> int:
+        return int(self.counts().sum())
 
     def fetch_all_blocks(self):
         """All leaf blocks, buckets 0..5 in order -> (uint8 [n,512], int64 [n,6])."""

@@ -41,6 +41,7 @@
 
 struct Ctl { // device control block (one per engine), mirrored through pinned host memory
 	uint32_t poolUsed, err, nItems, nlogNew;
+	uint32_t overflow, failBase, pad0, pad1; // pool exhausted during k_merge_blocks: first block id that did not fit
 	uint32_t blkBkt[8];     // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
 	uint32_t blkBktNew[8];
 	uint32_t gBkt[8], mBkt[8];         // this column: group / member index range per bucket
@@ -601,6 +602,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t w = blockIdx.x * MERGE_WARPS + wid;
 	if (w >= A.ctl->nItems) return;
+	if (A.itemPieces[w] != 0) return; // already merged by an earlier launch (retry after pool growth)
 	MergeSmem &S = reinterpret_cast<MergeSmem*>(smraw)[wid];
 
 	const uint32_t i = A.itemBlk[w];
@@ -647,13 +649,15 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
 	const bool inplace = nIt == 1;
 	const uint32_t nNew = inplace ? K - 1 : K;
 	uint32_t newBase = 0;
+	if (K > MAXPIECES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_PIECES); return; }
 	if (lane == 0 && nNew) {
+		// Nothing has been written yet, so running out of pool is recoverable: note the first id
+		// that did not fit and leave the item untouched; the host grows the pool and relaunches.
 		newBase = atomicAdd(&A.ctl->poolUsed, nNew);
-		if (newBase + nNew > A.ctl->poolCap) { atomicOr(&A.ctl->err, RB2_ERR_POOL); newBase = NONE32; }
+		if (newBase + nNew > A.ctl->poolCap) { atomicMin(&A.ctl->failBase, newBase); A.ctl->overflow = 1; newBase = NONE32; }
 	}
 	newBase = __shfl_sync(FULLMASK, newBase, 0);
 	if (newBase == NONE32) return;
-	if (K > MAXPIECES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_PIECES); return; }
 
 	for (int k = lane; k < MAXPIECES * 6; k += 32) S.pcnt[k] = 0;
 	if (lane <= MAXPIECES) S.cut[lane] = 0;
@@ -818,11 +822,22 @@ static void dir_free(Dir &d)
 	d.order = 0; d.cumLen = 0; d.cumCnt = 0; d.cap = 0;
 }
 
+#include <chrono>
+static int rb2_trace_on(void) { static int v = -1; if (v < 0) { const char *s = getenv("RB2_TRACE"); v = s && *s && *s != '0'; } return v; }
+struct TraceT {
+	rb2_engine *e; const char *name; std::chrono::steady_clock::time_point t0;
+	TraceT(rb2_engine *e_, const char *n);
+	~TraceT();
+};
+
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 #define LAUNCH(e, kernel, grid, block, smem, ...) do { \
 	kernel<<<(grid), (block), (smem), (e)->st>>>(__VA_ARGS__); ++(e)->stats.n_launches; \
 	cudaError_t le_ = cudaGetLastError(); if (le_ != cudaSuccess) RB2_FATAL("launch of %s failed: %s", #kernel, cudaGetErrorString(le_)); } while (0)
+
+TraceT::TraceT(rb2_engine *e_, const char *n) : e(e_), name(n) { if (rb2_trace_on()) { cudaStreamSynchronize(e->st); t0 = std::chrono::steady_clock::now(); } }
+TraceT::~TraceT() { if (rb2_trace_on()) { cudaStreamSynchronize(e->st); double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); fprintf(stderr, "[trace] %-14s %9.1f us\n", name, us); } }
 
 // three-phase scan driver over n elements
 template <int K, typename T, class F>
@@ -869,21 +884,24 @@ static void pull_totals(rb2_engine *e)
 	}
 }
 
-static void pool_reserve(rb2_engine *e, uint64_t blocks)
+// Grow everything that is sized by the number of leaf blocks: the pool, the per-block counts,
+// both directory buffers and the per-block planning arrays.  Allocation is slow (tens of ms),
+// so callers reserve generously once per batch; the merge kernel tolerates running out (retry).
+static void reserve_blocks(rb2_engine *e, uint64_t blocks)
 {
 	if (blocks <= e->poolCap) return;
-	uint64_t cap = std::max<uint64_t>(blocks, (uint64_t)e->poolCap + e->poolCap / 2);
-	if (cap > 0xfffffff0ull) RB2_FATAL("block pool would exceed 2^32 blocks");
+	if (blocks > 0xfffffff0ull) RB2_FATAL("block pool would exceed 2^32 blocks");
+	const uint64_t perBlock = RB2_BLK + 24 + 2 * 60 + 8;
 	size_t freeB = 0, totB = 0;
+	RB2_CUDA(cudaStreamSynchronize(e->st));
 	RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-	if (cap * (RB2_BLK + 24ull) > freeB) {
-		cap = blocks;
-		if (cap * (RB2_BLK + 24ull) > freeB) RB2_FATAL("out of HBM: need %llu leaf blocks (%.1f GB), %.1f GB free", (unsigned long long)cap, cap * 536e-9, freeB * 1e-9);
-	}
+	if (blocks * perBlock > freeB)
+		RB2_FATAL("out of HBM: need %llu leaf blocks (%.1f GB), %.1f GB free", (unsigned long long)blocks, blocks * perBlock * 1e-9, freeB * 1e-9);
+	const uint64_t cap = blocks;
 	uint8_t *np; uint32_t *nc;
 	RB2_CUDA(cudaMalloc(&np, cap * RB2_BLK));
 	RB2_CUDA(cudaMalloc(&nc, cap * 6 * sizeof(uint32_t)));
-	uint32_t used = e->hctl->poolUsed;
+	const uint32_t used = e->hctl->poolUsed;
 	if (e->pool) {
 		RB2_CUDA(cudaMemcpyAsync(np, e->pool, (size_t)used * RB2_BLK, cudaMemcpyDeviceToDevice, e->st));
 		RB2_CUDA(cudaMemcpyAsync(nc, e->blkCnt, (size_t)used * 24, cudaMemcpyDeviceToDevice, e->st));
@@ -891,15 +909,10 @@ static void pool_reserve(rb2_engine *e, uint64_t blocks)
 		RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt));
 	}
 	e->pool = np; e->blkCnt = nc; e->poolCap = (uint32_t)cap;
-}
-
-static void dir_reserve(rb2_engine *e, size_t blocks)
-{
 	for (int k = 0; k < 2; ++k) {
 		Dir &d = e->dir[k];
-		if (blocks <= d.cap) continue;
-		Dir nd; dir_alloc(nd, blocks + blocks / 4 + 1024);
-		if (k == e->cur && e->nlog) {
+		Dir nd; dir_alloc(nd, cap);
+		if (k == e->cur && e->nlog && d.order) {
 			RB2_CUDA(cudaMemcpyAsync(nd.order, d.order, (size_t)e->nlog * 4, cudaMemcpyDeviceToDevice, e->st));
 			RB2_CUDA(cudaMemcpyAsync(nd.cumLen, d.cumLen, ((size_t)e->nlog + 1) * 8, cudaMemcpyDeviceToDevice, e->st));
 			RB2_CUDA(cudaMemcpyAsync(nd.cumCnt, d.cumCnt, ((size_t)e->nlog + 1) * 48, cudaMemcpyDeviceToDevice, e->st));
@@ -908,6 +921,13 @@ static void dir_reserve(rb2_engine *e, size_t blocks)
 		dir_free(d);
 		d = nd;
 	}
+	e->recHi.need(cap); e->itemOff.need(cap + 1);
+	e->hctl->poolCap = e->poolCap;
+}
+
+static void reserve_items(rb2_engine *e, uint64_t n)
+{
+	e->itemBlk.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n);
 }
 
 extern "C" int rb2_device_count(void)
@@ -940,8 +960,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	memset(e->dir, 0, sizeof(e->dir)); e->cur = 0;
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(MergeSmem))));
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
-	pool_reserve(e, 1024);
-	dir_reserve(e, 1024);
+	reserve_blocks(e, 4096);
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
 	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
 	LAUNCH(e, k_fill_u32, 1, 32, 0, e->dir[0].order, 6u, 0u, 1u);
@@ -953,6 +972,30 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	pull_totals(e);
 	return e;
 }
+
+// Empty the index but keep every allocation (bench steps and tests reuse one engine).
+extern "C" void rb2_reset(rb2_engine_t *e)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
+	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
+	LAUNCH(e, k_fill_u32, 1, 32, 0, e->dir[e->cur].order, 6u, 0u, 1u);
+	e->nlog = 6;
+	for (int b = 0; b < 8; ++b) e->blkBkt[b] = b < 6 ? b : 6;
+	e->hctl->poolUsed = 6; e->hctl->poolCap = e->poolCap; e->hctl->err = 0;
+	ctl_push(e);
+	rebuild_directory(e);
+	pull_totals(e);
+	e->stats.pool_blocks = 6;
+}
+
+extern "C" void *rb2_host_alloc(int64_t bytes)
+{
+	void *p = 0;
+	RB2_CUDA(cudaMallocHost(&p, (size_t)bytes));
+	return p;
+}
+extern "C" void rb2_host_free(void *p) { RB2_CUDA(cudaFreeHost(p)); }
 
 extern "C" void rb2_destroy(rb2_engine_t *e)
 {
@@ -998,38 +1041,47 @@ static void ph_collect(rb2_engine *e, uint32_t mask)
 static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 {
 	Ctl *h = e->hctl;
-	// ---- plan items, make room --------------------------------------------------
+	// ---- plan work items -----------------------------------------------------------
 	ph_begin(e, PH_DIR);
-	e->recHi.need(e->nlog);
-	e->itemOff.need((size_t)e->nlog + 1);
 	const uint64_t maxItems = (uint64_t)std::min<uint64_t>(e->nlog, nrec) + nrec / RMAX + 1;
-	e->itemBlk.need(maxItems); e->itemPieces.need(maxItems); e->itemFirst.need(maxItems); e->itemRest.need(maxItems);
-	// worst case every touched block splits and every record adds 8 bytes
-	const uint64_t needBlocks = (uint64_t)h->poolUsed + maxItems * 21 / 10 + (uint64_t)nrec / 60 + 64;
-	if (needBlocks > e->poolCap) { pool_reserve(e, needBlocks); h->poolCap = e->poolCap; ctl_push(e); }
-	dir_reserve(e, needBlocks);
-	Dir &dc = e->dir[e->cur], &dnx = e->dir[e->cur ^ 1];
-	LAUNCH(e, k_rec_hi, cdiv(e->nlog, 256), 256, 0, dc, e->nlog, e->dctl, e->recP.p, e->recHi.p);
-	ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemBlk.p, e->dctl };
-	run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0);
+	reserve_items(e, maxItems);                    // no-op when the batch-level reservation holds
+	if ((uint64_t)h->poolUsed + 1024 > e->poolCap) { // keep a little slack so most columns never retry
+		reserve_blocks(e, (uint64_t)e->poolCap + e->poolCap / 2 + 4096);
+		ctl_push(e);
+	}
+	{
+		Dir &dc = e->dir[e->cur];
+		LAUNCH(e, k_rec_hi, cdiv(e->nlog, 256), 256, 0, dc, e->nlog, e->dctl, e->recP.p, e->recHi.p);
+		ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemBlk.p, e->dctl };
+		run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0);
+		RB2_CUDA(cudaMemsetAsync(e->itemPieces.p, 0, maxItems * 4, e->st)); // 0 = not merged yet
+	}
 	ph_end(e, PH_DIR);
-
-	// ---- merge -----------------------------------------------------------------
-	ph_begin(e, PH_MERGE);
-	MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
-	                 e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, gLNext,
-	                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->dctl };
-	LAUNCH(e, k_merge_blocks, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(MergeSmem), ma);
-	ph_end(e, PH_MERGE);
-	++e->stats.n_merge_launches;
-
-	// ---- new logical order + directory --------------------------------------------
-	ph_begin(e, PH_DIR2);
 	const uint32_t usedBefore = h->poolUsed;
-	RebuildScan rs = { e->dctl, e->dctl, e->nlog, dc.order, e->itemOff.p, e->itemPieces.p, e->itemFirst.p, e->itemRest.p, dnx.order };
-	run_scan<1, uint32_t, RebuildScan>(e, rs, e->nlog, e->scanCta, (uint32_t*)0);
-	ctl_pull(e);
-	const uint32_t nItems = h->nItems;
+	uint32_t nItems = 0;
+	for (int attempt = 0;; ++attempt) {
+		Dir &dc = e->dir[e->cur], &dnx = e->dir[e->cur ^ 1];
+		// ---- merge -----------------------------------------------------------------
+		if (attempt == 0) ph_begin(e, PH_MERGE);
+		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
+		                 e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, gLNext,
+		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->dctl };
+		LAUNCH(e, k_merge_blocks, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(MergeSmem), ma);
+		if (attempt == 0) ph_end(e, PH_MERGE);
+		++e->stats.n_merge_launches;
+		// ---- new logical order ----------------------------------------------------------
+		if (attempt == 0) ph_begin(e, PH_DIR2);
+		RebuildScan rs = { e->dctl, e->dctl, e->nlog, dc.order, e->itemOff.p, e->itemPieces.p, e->itemFirst.p, e->itemRest.p, dnx.order };
+		run_scan<1, uint32_t, RebuildScan>(e, rs, e->nlog, e->scanCta, (uint32_t*)0);
+		ctl_pull(e);
+		nItems = h->nItems;
+		if (!h->overflow) break;
+		// pool ran out: the items that did not fit are untouched.  Grow and run them again.
+		if (attempt > 8) RB2_FATAL("block pool growth did not converge");
+		h->poolUsed = h->failBase; h->overflow = 0; h->failBase = NONE32;
+		reserve_blocks(e, (uint64_t)e->poolCap + e->poolCap / 2 + maxItems / 4 + 4096);
+		ctl_push(e);
+	}
 	e->nlog = h->nlogNew;
 	for (int b = 0; b < 8; ++b) e->blkBkt[b] = h->blkBktNew[b];
 	e->cur ^= 1;
@@ -1040,7 +1092,6 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 	e->stats.merge_blocks += nItems;
 	// every item reads one leaf block and writes it back, plus the freshly allocated pieces
 	e->stats.merge_bytes_rw += ((int64_t)nItems * 2 + (int64_t)(h->poolUsed - usedBefore)) * RB2_BLK;
-
 }
 
 // One sub-batch whose strings already sit in device memory at `s` (len bytes, ends with NUL).
@@ -1081,6 +1132,10 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	e->asym.need((size_t)m + 8);
 	const size_t recCap = (size_t)m + m / RB2_MAXRUN + 64;
 	e->recP.need(recCap); e->recSym.need(recCap); e->recCnt.need(recCap); e->recDst.need(recCap);
+	// Reserve leaf blocks for the whole batch up front (2 bytes of pool per new symbol covers random
+	// data at B+-tree fill plus blocks retired by multi-item merges); more is added on demand.
+	reserve_blocks(e, (uint64_t)e->hctl->poolUsed + (uint64_t)len * 2 / RB2_FILL + 4096);
+	reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
 	const int64_t n0 = e->bktLen[0];
 	const bool useSizes = sorted && n0 > 0;
 	if (useSizes) e->sizes6.need((size_t)m * 6);
@@ -1103,7 +1158,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			for (int b = 0; b < 6; ++b) { h->cpost[b] = acc; acc += e->bktLen[b] + (mBkt[b + 1] - mBkt[b]); }
 			h->cpost[6] = h->cpost[7] = acc;
 		}
-		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0;
+		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32;
 		ctl_push(e);
 
 		// ---- members: next symbol + tile histograms ---------------------------------
@@ -1256,8 +1311,7 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 	// the bucket's blocks are [blkBkt[b], blkBkt[b+1]); new blocks are inserted at its right end.
 	// An initially empty bucket consists of one empty block, which is replaced.
 	const uint32_t used = e->hctl->poolUsed;
-	pool_reserve(e, (uint64_t)used + n + 64);
-	dir_reserve(e, (size_t)e->nlog + n + 64);
+	reserve_blocks(e, (uint64_t)used + n + 4096);
 	e->stage.need((size_t)n * RB2_BLK);
 	e->stageCnt.need((size_t)n * 6);
 	RB2_CUDA(cudaMemcpyAsync(e->stage.p, src, (size_t)n * RB2_BLK, cudaMemcpyHostToDevice, e->st));
@@ -1340,8 +1394,9 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	RB2_CUDA(cudaMemcpyAsync(e->recDst.p, D.data(), k * 4, cudaMemcpyHostToDevice, e->st));
 	Ctl *h = e->hctl;
 	for (int b = 0; b < 8; ++b) { h->blkBkt[b] = e->blkBkt[b]; h->recBkt[b] = b <= bucket ? 0 : k; h->cpost[b] = 0; }
-	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0;
+	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32;
 	ctl_push(e);
+	reserve_items(e, (uint64_t)k + 2);
 	apply_records(e, k, e->dRankOut);
 	RB2_CUDA(cudaMemcpyAsync(e->hRankOut, e->dRankOut, 8, cudaMemcpyDeviceToHost, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));

@@ -45,6 +45,29 @@ def genome_reads(n: int, length: int, seed: int, coverage: float = 30.0,
     return np.ascontiguousarray(r)
 
 
+def varlen_reads(n: int, max_len: int, seed: int, min_len: int = 0):
+    """Variable-length reads (list of 1-D arrays) with some N's and two duplicated strings."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(min_len, max_len + 1))
+        out.append(rng.integers(1, 6 if rng.random() < 0.2 else 5, size=ln).astype(np.uint8))
+    out += [out[0].copy(), out[len(out) // 2].copy()]
+    return out
+
+
+def from_spec(gen: dict):
+    """Reads from a fixture spec: {"kind": "U"|"G"|"V", "n", "L", "seed", ...} (tests/golden)."""
+    k = gen["kind"]
+    if k == "U":
+        return uniform_reads(gen["n"], gen["L"], gen["seed"], gen.get("n_frac", 0.0))
+    if k == "G":
+        return genome_reads(gen["n"], gen["L"], gen["seed"], gen.get("coverage", 30.0), gen.get("err", 0.01))
+    if k == "V":
+        return varlen_reads(gen["n"], gen["L"], gen["seed"], gen.get("lmin", 0))
+    raise ValueError(k)
+
+
 def revcomp(reads: np.ndarray) -> np.ndarray:
     """Reverse complement of fixed-length nt6 reads (A<->T, C<->G; $ and N unchanged)."""
     r = reads[:, ::-1].copy()
