@@ -24,6 +24,10 @@
 #define RB2_FILL 494
 #define RB2_MAXRUN ((1u << 19) - 1)
 #define RB2_RUNS_STRIDE 17  // per-lane stride (words) of the decoded-run scratch: odd => conflict-free
+// decoded run word: byte offset inside the lane's 16 bytes (4 bits) | length (19 bits) | symbol (3 bits)
+#define RUN_SYM(r) ((r) & 7u)
+#define RUN_LEN(r) (((r) >> 3) & 0x7ffffu)
+#define RUN_OFF(r) ((r) >> 22)
 
 struct LaneDec {
 	uint32_t nr;     // runs starting in this lane's 16 bytes
@@ -37,20 +41,22 @@ __device__ __forceinline__ uint32_t win_byte(const uint32_t (&W)[5], int i)
 	return (W[i >> 2] >> ((i & 3) * 8)) & 0xffu;
 }
 
-// Decode the runs starting in this lane's bytes into runs[0..nr) as (len << 3 | sym).
-// `runs` points at this lane's private slice (stride RB2_RUNS_STRIDE words).
+// Decode the runs starting in this lane's bytes into runs[0..nr) as (byteoff << 22 | len << 3 | sym).
+// `runs` points at this lane's private slice (stride RB2_RUNS_STRIDE words); `lcs` is a lane-private
+// scratch of 6 shared-memory words used to accumulate the per-symbol counts (indexing registers by
+// a run-time symbol would cost a 6-way select per run).
 __device__ __forceinline__ void decode_lane(const uint4 &own, uint32_t next0, int lane, uint32_t nbytes,
-                                            uint32_t *runs, LaneDec &d, uint32_t &err)
+                                            uint32_t *runs, uint32_t *lcs, LaneDec &d, uint32_t &err)
 {
 	const uint32_t W[5] = { own.x, own.y, own.z, own.w, next0 };
 	uint32_t nr = 0, tot = 0;
-	uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
-	const int base = lane * 16;
+	const int lim = (int)nbytes + 2 - lane * 16; // byte i of this lane is a run byte iff i < lim (and i >= 2 in lane 0)
+#pragma unroll
+	for (int a = 0; a < 6; ++a) lcs[a] = 0;
 #pragma unroll
 	for (int i = 0; i < 16; ++i) {
 		const uint32_t b = win_byte(W, i);
-		const int pos = base + i;
-		const bool start = pos >= 2 && pos < 2 + (int)nbytes && (b & 0xC0u) != 0x80u;
+		const bool start = (i >= 2 || lane > 0) && i < lim && (b & 0xC0u) != 0x80u;
 		if (start) {
 			uint32_t l;
 			if (b < 0x80u) l = b >> 3;
@@ -61,14 +67,14 @@ __device__ __forceinline__ void decode_lane(const uint4 &own, uint32_t next0, in
 				  | ((win_byte(W, i + 2) & 0x3fu) << 6) | (win_byte(W, i + 3) & 0x3fu);
 			}
 			const uint32_t s = b & 7u;
-			runs[nr++] = (l << 3) | s;
+			runs[nr++] = ((uint32_t)i << 22) | (l << 3) | s;
 			tot += l;
-			c0 += s == 0 ? l : 0; c1 += s == 1 ? l : 0; c2 += s == 2 ? l : 0;
-			c3 += s == 3 ? l : 0; c4 += s == 4 ? l : 0; c5 += s == 5 ? l : 0;
+			lcs[s] += l;
 		}
 	}
 	d.nr = nr; d.len = tot;
-	d.c[0] = c0; d.c[1] = c1; d.c[2] = c2; d.c[3] = c3; d.c[4] = c4; d.c[5] = c5;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) d.c[a] = lcs[a];
 }
 
 // Whole-warp decode of one block.  On return, for this lane:
@@ -76,24 +82,36 @@ __device__ __forceinline__ void decode_lane(const uint4 &own, uint32_t next0, in
 //   basePos  symbols in front of the lane's first run (exclusive scan of d.len)
 //   baseCnt  per-symbol counts in front of the lane (exclusive scan of d.c)
 //   blkLen   symbols in the block, blkCnt[6] per-symbol totals (same in all lanes)
-__device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, uint32_t *runsWarp,
+// cntScratch: 32 x 7 shared-memory words (lane-private slices).
+__device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, uint32_t *runsWarp, uint32_t *cntScratch,
                                                   LaneDec &d, uint32_t &basePos, uint32_t (&baseCnt)[6],
-                                                  uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err)
+                                                  uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err, uint4 &own)
 {
 	// plain (coherent) load: k_merge_blocks rewrites the same block in place later on
-	const uint4 own = *(reinterpret_cast<const uint4*>(blk) + lane);
+	own = *(reinterpret_cast<const uint4*>(blk) + lane);
 	nbytes = __shfl_sync(FULLMASK, own.x, 0) & 0xffffu;
 	uint32_t next0 = __shfl_down_sync(FULLMASK, own.x, 1);
 	if (lane == 31) next0 = 0;
-	decode_lane(own, next0, lane, nbytes, runsWarp + lane * RB2_RUNS_STRIDE, d, err);
+	decode_lane(own, next0, lane, nbytes, runsWarp + lane * RB2_RUNS_STRIDE, cntScratch + lane * 7, d, err);
 	uint32_t incl = warp_incl_scan(d.len, lane);
 	basePos = incl - d.len;
 	blkLen = __shfl_sync(FULLMASK, incl, 31);
+	if (blkLen < 65536u) { // every count fits 16 bits: scan two symbols per word
 #pragma unroll
-	for (int a = 0; a < 6; ++a) {
-		uint32_t x = warp_incl_scan(d.c[a], lane);
-		baseCnt[a] = x - d.c[a];
-		blkCnt[a] = __shfl_sync(FULLMASK, x, 31);
+		for (int a = 0; a < 6; a += 2) {
+			const uint32_t v = d.c[a] | (d.c[a + 1] << 16);
+			const uint32_t x = warp_incl_scan(v, lane);
+			const uint32_t ex = x - v, t = __shfl_sync(FULLMASK, x, 31);
+			baseCnt[a] = ex & 0xffffu; baseCnt[a + 1] = ex >> 16;
+			blkCnt[a] = t & 0xffffu; blkCnt[a + 1] = t >> 16;
+		}
+	} else {
+#pragma unroll
+		for (int a = 0; a < 6; ++a) {
+			uint32_t x = warp_incl_scan(d.c[a], lane);
+			baseCnt[a] = x - d.c[a];
+			blkCnt[a] = __shfl_sync(FULLMASK, x, 31);
+		}
 	}
 	__syncwarp();
 }

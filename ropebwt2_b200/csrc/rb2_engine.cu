@@ -30,8 +30,8 @@
 #include "../../include/ropebwt2_b200.h"
 
 #define MEM_TILE    1024   // members per CTA in the fetch / partition kernels (256 threads x 4)
-#define RMAX        448    // max records merged by one work item (bounds the staging buffer)
-#define STAGE_BYTES 4096   // >= 510 + 8*RMAX: old block bytes + <=8 new bytes per record
+#define RMAX        256    // max records merged by one work item (bounds the staging buffer)
+#define STAGE_BYTES 2560   // >= 510 + 8*RMAX: old block bytes + <=8 new bytes per record
 #define SPLIT_T     488    // piece size target when a block overflows (pieces are < SPLIT_T+4 <= 494)
 #define MAXPIECES   16
 #define MERGE_WARPS 4
@@ -246,13 +246,13 @@ __device__ __forceinline__ uint32_t find_block(const int64_t *cumLen, uint32_t l
 // occ(a, x) for all six symbols; warp-cooperative, result valid in every lane.
 // scratch: runs[32*17] words + res[6] int64, private to the warp.
 __device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int lane,
-                           uint32_t *runs, int64_t *res, int64_t (&out)[6], uint32_t &err)
+                           uint32_t *runs, uint32_t *cntScratch, int64_t *res, int64_t (&out)[6], uint32_t &err)
 {
 	uint32_t i = find_block(dir.cumLen, 0, nlog - 1, x);
 	if (i >= nlog) i = nlog - 1;
 	const uint32_t xrel = (uint32_t)(x - dir.cumLen[i]);
-	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes;
-	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, runs, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err);
+	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes; uint4 own;
+	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, runs, cntScratch, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err, own);
 	const bool mine = xrel > basePos && xrel <= basePos + d.len;
 	if (xrel == 0) { if (lane < 6) res[lane] = dir.cumCnt[(size_t)i * 6 + lane]; }
 	else if (mine) {
@@ -260,7 +260,7 @@ __device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t 
 		uint32_t pos = basePos;
 		const uint32_t *r = runs + lane * RB2_RUNS_STRIDE;
 		for (uint32_t q = 0; q < d.nr && pos < xrel; ++q) {
-			uint32_t l = r[q] >> 3, s = r[q] & 7, take = xrel - pos < l ? xrel - pos : l;
+			uint32_t l = RUN_LEN(r[q]), s = RUN_SYM(r[q]), take = xrel - pos < l ? xrel - pos : l;
 #pragma unroll
 			for (int a = 0; a < 6; ++a) pc[a] += s == a ? take : 0;
 			pos += l;
@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir di
                                                      const int64_t *gL, const int64_t *gSize, int64_t *sizes6, Ctl *ctl)
 {
 	__shared__ uint32_t sRuns[4][32 * RB2_RUNS_STRIDE];
+	__shared__ uint32_t sCnt[4][32 * 7];
 	__shared__ int64_t sRes[4][6];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t g0 = (blockIdx.x * 4 + wid) * 32;
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir di
 		const int src = __ffs(todo) - 1; todo &= todo - 1;
 		const int64_t L = __shfl_sync(FULLMASK, myL, src), sz = __shfl_sync(FULLMASK, mySz, src);
 		int64_t cl[6], cu[6];
-		warp_rank6(pool, dir, nlog, L, lane, sRuns[wid], sRes[wid], cl, err);
-		warp_rank6(pool, dir, nlog, L + sz, lane, sRuns[wid], sRes[wid], cu, err);
+		warp_rank6(pool, dir, nlog, L, lane, sRuns[wid], sCnt[wid], sRes[wid], cl, err);
+		warp_rank6(pool, dir, nlog, L + sz, lane, sRuns[wid], sCnt[wid], sRes[wid], cu, err);
 		if (lane < 6) {
 			int64_t v = 0;
 #pragma unroll
@@ -306,14 +307,15 @@ __global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir di
 __global__ void __launch_bounds__(32) k_rank_query(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int64_t y, int64_t *out, Ctl *ctl)
 {
 	__shared__ uint32_t sRuns[32 * RB2_RUNS_STRIDE];
+	__shared__ uint32_t sCnt[32 * 7];
 	__shared__ int64_t sRes[6];
 	const int lane = threadIdx.x;
 	uint32_t err = 0;
 	int64_t c[6];
-	warp_rank6(pool, dir, nlog, x, lane, sRuns, sRes, c, err);
+	warp_rank6(pool, dir, nlog, x, lane, sRuns, sCnt, sRes, c, err);
 	if (lane == 0) for (int a = 0; a < 6; ++a) out[a] = c[a];
 	if (y >= 0) {
-		warp_rank6(pool, dir, nlog, y, lane, sRuns, sRes, c, err);
+		warp_rank6(pool, dir, nlog, y, lane, sRuns, sCnt, sRes, c, err);
 		if (lane == 0) for (int a = 0; a < 6; ++a) out[6 + a] = c[a];
 	}
 	if (err && lane == 0) atomicOr(&ctl->err, err);
@@ -513,13 +515,28 @@ struct MergeArgs {
 	Ctl *ctl;
 };
 
-struct MergeSmem {
-	uint32_t runs[32 * RB2_RUNS_STRIDE];
-	uint8_t  stage[STAGE_BYTES];
+#define FAST_MAXREC 32  // records per item the edit-based fast path handles (one per lane)
+
+struct GenScratch {                 // general path
 	uint32_t lcnt[32 * 7];          // per-lane running old-symbol counts (lane-private, stride 7)
 	uint32_t pcl[32 * 7];           // per-lane counts of the piece currently being written
 	uint32_t cut[MAXPIECES + 1];
 	uint32_t pcnt[MAXPIECES * 6];
+};
+struct FastScratch {                // edit-based fast path
+	uint32_t laneBase[32 * 7];      // per-lane exclusive per-symbol counts
+	uint32_t laneEnd[32], laneNr[32], laneRunPre[32];
+	uint32_t eStart[FAST_MAXREC + 1], eEnd[FAST_MAXREC + 1], eNew[FAST_MAXREC + 1], eBuf[FAST_MAXREC + 1];
+	int32_t  eCum[FAST_MAXREC + 2];   // exclusive prefix of (new - old) byte deltas
+	uint32_t oStart[FAST_MAXREC + 1]; // edit start in the output image
+	uint32_t cntAdd[8];               // symbols added by the item's records
+};
+#define IMG_OFF  512   // fast path: the input block image sits at stage[512, 1024)
+#define EBUF_OFF 2048  // fast path: replacement bytes of the edits, 16 per record, at stage[2048, 2560)
+struct alignas(16) MergeSmem {
+	uint32_t runs[32 * RB2_RUNS_STRIDE];
+	uint8_t  stage[STAGE_BYTES];    // general: output run bytes; fast: input image + replacement bytes
+	union { GenScratch g; FastScratch f; } u;
 };
 
 // Sequential merge of one lane's old runs with the records that fall into them.
@@ -577,7 +594,7 @@ __device__ __forceinline__ uint32_t lane_merge(const uint32_t *runs, uint32_t nr
 	};
 
 	for (uint32_t q = 0; q < nr; ++q) {
-		const uint32_t s = runs[q] & 7, end = pos + (runs[q] >> 3);
+		const uint32_t s = RUN_SYM(runs[q]), end = pos + RUN_LEN(runs[q]);
 		uint32_t cur = pos;
 		while (nextP < end) {              // records in front of or inside this run
 			if (nextP > cur) { emit_old(s, cur, nextP); lc[s] += nextP - cur; cur = nextP; }
@@ -595,35 +612,42 @@ __device__ __forceinline__ uint32_t lane_merge(const uint32_t *runs, uint32_t nr
 	return o - o0;
 }
 
-// One warp per work item = (logical block, slice of <= RMAX of its records).
-__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
+// Everything a warp knows about its work item after the common prologue.
+struct ItemCtx {
+	uint32_t w, i, phys, nIt, sub, r0, r1;
+	int64_t blkStart;
+	const int64_t *cumCntBlk;
+	LaneDec d;
+	uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes;
+	uint4 own;
+};
+
+// Allocate nNew fresh leaf blocks for one item (lane 0 asks, everybody gets the answer).
+// Returns NONE32 when the pool is exhausted; nothing has been written at that point, so the
+// host can grow the pool and run the item again.
+__device__ __forceinline__ uint32_t alloc_blocks(const MergeArgs &A, int lane, uint32_t nNew)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t w = blockIdx.x * MERGE_WARPS + wid;
-	if (w >= A.ctl->nItems) return;
-	if (A.itemPieces[w] != 0) return; // already merged by an earlier launch (retry after pool growth)
-	MergeSmem &S = reinterpret_cast<MergeSmem*>(smraw)[wid];
+	uint32_t base = 0;
+	if (lane == 0 && nNew) {
+		base = atomicAdd(&A.ctl->poolUsed, nNew);
+		if (base + nNew > A.ctl->poolCap) { atomicMin(&A.ctl->failBase, base); A.ctl->overflow = 1; base = NONE32; }
+	}
+	return __shfl_sync(FULLMASK, base, 0);
+}
 
-	const uint32_t i = A.itemBlk[w];
-	const uint32_t it0 = A.itemOff[i], nIt = A.itemOff[i + 1] - it0, sub = w - it0;
-	const int b = bucket_of(A.ctl->blkBkt, i);
-	const uint32_t recLo = i == A.ctl->blkBkt[b] ? A.ctl->recBkt[b] : A.recHi[i - 1], recHiB = A.recHi[i];
-	const uint32_t r0 = recLo + sub * RMAX, r1 = r0 + RMAX < recHiB ? r0 + RMAX : recHiB;
-	const int64_t blkStart = A.dir.cumLen[i];
-	const uint32_t phys = A.dir.order[i];
-	const int64_t *cumCntBlk = A.dir.cumCnt + (size_t)i * 6;
-
-	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes, err = 0;
-	warp_decode_block(A.pool + (size_t)phys * RB2_BLK, lane, S.runs, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err);
-
+// ---- general path: any number of records, sub-items, empty blocks ---------------------------
+__device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, int lane, const ItemCtx &C)
+{
+	GenScratch &G = S.u.g;
+	const uint32_t r0 = C.r0, r1 = C.r1;
+	const int64_t blkStart = C.blkStart;
 	// the slice of old symbols this item re-emits: [posLo, posHi) relative to the block start
-	const uint32_t posLo = sub == 0 ? 0 : (uint32_t)(A.recP[r0] - blkStart);
-	const uint32_t posHi = sub + 1 == nIt ? blkLen : (uint32_t)(A.recP[r1] - blkStart);
+	const uint32_t posLo = C.sub == 0 ? 0 : (uint32_t)(A.recP[r0] - blkStart);
+	const uint32_t posHi = C.sub + 1 == C.nIt ? C.blkLen : (uint32_t)(A.recP[r1] - blkStart);
 	// lane owns the records with position in (c_{lane-1}, c_lane], c = end of the lane's runs capped
 	// at posHi; lane 0 also takes position 0.  Lanes that end in front of posLo own nothing (every
 	// record of the item is >= posLo), so a record is always ranked by the lane that contains it.
-	uint32_t c = basePos + d.len;
+	uint32_t c = C.basePos + C.d.len;
 	c = c > posHi ? posHi : c;
 	uint32_t lo = r0, hi = r1;
 	{
@@ -634,49 +658,42 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
 	uint32_t rlo = __shfl_up_sync(FULLMASK, rhi, 1);
 	if (lane == 0) rlo = r0;
 
-	uint32_t *lc = S.lcnt + lane * 7, *pl = S.pcl + lane * 7;
+	uint32_t *lc = G.lcnt + lane * 7, *pl = G.pcl + lane * 7;
 	const uint32_t *runs = S.runs + lane * RB2_RUNS_STRIDE;
 #pragma unroll
-	for (int a = 0; a < 6; ++a) { lc[a] = baseCnt[a]; pl[a] = 0; }
+	for (int a = 0; a < 6; ++a) { lc[a] = C.baseCnt[a]; pl[a] = 0; }
 
 	// pass 1: output bytes per lane
-	const uint32_t myBytes = lane_merge<false>(runs, d.nr, basePos, rlo, rhi, A, blkStart, posLo, posHi, cumCntBlk, lc, 0, 1u << 30, S.stage, S.cut, S.pcnt, pl);
+	const uint32_t myBytes = lane_merge<false>(runs, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, 0, 1u << 30, S.stage, G.cut, G.pcnt, pl);
 	const uint32_t incl = warp_incl_scan(myBytes, lane);
 	const uint32_t out = __shfl_sync(FULLMASK, incl, 31);
 	if (out > STAGE_BYTES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_STAGE); return; }
 	const uint32_t K = out <= RB2_FILL ? 1 : (out + SPLIT_T - 1) / SPLIT_T;
 	const uint32_t T = K == 1 ? (1u << 30) : (out + K - 1) / K;
-	const bool inplace = nIt == 1;
+	const bool inplace = C.nIt == 1;
 	const uint32_t nNew = inplace ? K - 1 : K;
-	uint32_t newBase = 0;
 	if (K > MAXPIECES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_PIECES); return; }
-	if (lane == 0 && nNew) {
-		// Nothing has been written yet, so running out of pool is recoverable: note the first id
-		// that did not fit and leave the item untouched; the host grows the pool and relaunches.
-		newBase = atomicAdd(&A.ctl->poolUsed, nNew);
-		if (newBase + nNew > A.ctl->poolCap) { atomicMin(&A.ctl->failBase, newBase); A.ctl->overflow = 1; newBase = NONE32; }
-	}
-	newBase = __shfl_sync(FULLMASK, newBase, 0);
+	const uint32_t newBase = alloc_blocks(A, lane, nNew);
 	if (newBase == NONE32) return;
 
-	for (int k = lane; k < MAXPIECES * 6; k += 32) S.pcnt[k] = 0;
-	if (lane <= MAXPIECES) S.cut[lane] = 0;
+	for (int k = lane; k < MAXPIECES * 6; k += 32) G.pcnt[k] = 0;
+	if (lane <= MAXPIECES) G.cut[lane] = 0;
 #pragma unroll
-	for (int a = 0; a < 6; ++a) { lc[a] = baseCnt[a]; pl[a] = 0; }
+	for (int a = 0; a < 6; ++a) { lc[a] = C.baseCnt[a]; pl[a] = 0; }
 	__syncwarp();
 
 	// pass 2: emit bytes, piece cuts, piece counts, ranks
-	lane_merge<true>(runs, d.nr, basePos, rlo, rhi, A, blkStart, posLo, posHi, cumCntBlk, lc, incl - myBytes, T, S.stage, S.cut, S.pcnt, pl);
+	lane_merge<true>(runs, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, incl - myBytes, T, S.stage, G.cut, G.pcnt, pl);
 	__syncwarp();
-	if (lane == 0) S.cut[K] = out;
+	if (lane == 0) G.cut[K] = out;
 	__syncwarp();
 
 	// copy the pieces out as leaf blocks: [uint16 nbytes][runs...], zero padded
-	const uint32_t firstPhys = inplace ? phys : newBase;
+	const uint32_t firstPhys = inplace ? C.phys : newBase;
 	const uint32_t restPhys = inplace ? newBase : newBase + 1;
 	for (uint32_t k = 0; k < K; ++k) {
 		const uint32_t p = k == 0 ? firstPhys : restPhys + (k - 1);
-		const uint32_t st = S.cut[k], n = S.cut[k + 1] - st;
+		const uint32_t st = G.cut[k], n = G.cut[k + 1] - st;
 		uint32_t wv[4];
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
@@ -692,10 +709,258 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
 			wv[j] = x;
 		}
 		*(reinterpret_cast<uint4*>(A.pool + (size_t)p * RB2_BLK) + lane) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-		if (lane < 6) A.blkCnt[(size_t)p * 6 + lane] = S.pcnt[k * 6 + lane];
+		if (lane < 6) A.blkCnt[(size_t)p * 6 + lane] = G.pcnt[k * 6 + lane];
 	}
-	if (lane == 0) { A.itemPieces[w] = K; A.itemFirst[w] = firstPhys; A.itemRest[w] = restPhys; }
+	if (lane == 0) { A.itemPieces[C.w] = K; A.itemFirst[C.w] = firstPhys; A.itemRest[C.w] = restPhys; }
+}
+
+// ---- fast path: one item per block, <= 32 records, non-empty block ---------------------------
+// Only the runs a record touches are re-encoded.  Lane j locates record j (target lane by binary
+// search over the per-lane end positions, then a walk over that lane's <= 16 decoded runs), which
+// also yields rank(a, P).  Records whose touched runs overlap form a group; the group's first lane
+// re-encodes that short span with the records merged in ("edit": old byte range -> new bytes).
+// The output block image is then assembled by pulling: every lane fetches its 16 output bytes
+// either verbatim from the shifted input image or from the edits' replacement bytes.
+// Returns false (no side effects besides idempotent rank writes) if it cannot place a split.
+__device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int lane, const ItemCtx &C)
+{
+	FastScratch &F = S.u.f;
+	const uint32_t nrec = C.r1 - C.r0, nbytes = C.nbytes;
+	F.laneEnd[lane] = C.basePos + C.d.len;
+	F.laneNr[lane] = C.d.nr;
+	const uint32_t runIncl = warp_incl_scan(C.d.nr, lane);
+	F.laneRunPre[lane] = runIncl - C.d.nr;
+	const uint32_t nRuns = __shfl_sync(FULLMASK, runIncl, 31);
+#pragma unroll
+	for (int a = 0; a < 6; ++a) F.laneBase[lane * 7 + a] = C.baseCnt[a];
+	reinterpret_cast<uint4*>(S.stage + IMG_OFF)[lane] = C.own; // input block image, byte-addressable
+	if (lane < 8) F.cntAdd[lane] = 0;
+	__syncwarp();
+
+	// ---- locate record `lane` ----------------------------------------------------------
+	const bool act = (uint32_t)lane < nrec;
+	uint32_t P = 0, a = 0, cnt = 0, t = 0, q = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
+	if (act) {
+		const uint32_t r = C.r0 + lane;
+		P = (uint32_t)(A.recP[r] - C.blkStart); a = A.recSym[r]; cnt = A.recCnt[r];
+		uint32_t lo = 0, hi = 31;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.laneEnd[mid] >= P) hi = mid; else lo = mid + 1; }
+		t = lo;
+		pos = t ? F.laneEnd[t - 1] : 0;
+		uint32_t ca = F.laneBase[t * 7 + a];
+		const uint32_t *rr = S.runs + t * RB2_RUNS_STRIDE;
+		const uint32_t nrt = F.laneNr[t];
+		for (q = 0;; ++q) { // run that contains symbol P-1 (the first run for P == 0)
+			const uint32_t rw = rr[q];
+			len = RUN_LEN(rw); sym = RUN_SYM(rw);
+			if (pos + len >= P || q + 1 >= nrt) break;
+			ca += sym == a ? len : 0;
+			pos += len;
+		}
+		off = P - pos;
+		const uint32_t dst = A.recDst[r];
+		if (dst != NONE32) A.gLNext[dst] = A.ctl->cpost[a] + C.cumCntBlk[a] + ca + (sym == a ? off : 0);
+		atomicAdd(&F.cntAdd[a], cnt);
+		s = F.laneRunPre[t] + q;                                   // global index of that run
+		e = s + ((off == len && s + 1 < nRuns) ? 1 : 0);           // at a run boundary the next run may absorb the record
+	}
+	// ---- group records whose touched runs overlap ----------------------------------------------
+	const uint32_t ePrev = __shfl_up_sync(FULLMASK, e, 1);
+	const bool head = act && (lane == 0 || s > ePrev);
+	const uint32_t H = __ballot_sync(FULLMASK, head);
+	const uint32_t ng = __popc(H);
+	const uint32_t above = lane == 31 ? 0u : (H & ~((2u << lane) - 1u));
+	const uint32_t gend = above ? (uint32_t)(__ffs(above) - 1) : nrec;  // one past the group's last record
+	const uint32_t eLast = __shfl_sync(FULLMASK, e, (gend - 1) & 31);
+	const uint32_t k = __popc(H & ((1u << lane) - 1u));
+	// ---- group heads re-encode their span ------------------------------------------------
+	if (head) {
+		uint8_t *ob = S.stage + EBUF_OFF + lane * 16;
+		uint32_t o = 0, psym = 8, plen = 0;
+		uint32_t rr_ = C.r0 + lane;
+		const uint32_t rend = C.r0 + gend;
+		uint32_t nextP = P, na = a, nc = cnt;
+		uint32_t tt = t, qq = q, p0 = pos;
+		const uint32_t oldStart = tt * 16 + RUN_OFF(S.runs[tt * RB2_RUNS_STRIDE + qq]);
+		auto flush = [&]() {
+			while (plen) {
+				const uint32_t l = plen < RB2_MAXRUN ? plen : RB2_MAXRUN;
+				o += enc_run(ob + o, psym, l);
+				plen -= l;
+			}
+		};
+		auto emit = [&](uint32_t sy, uint32_t l) {
+			if (l == 0) return;
+			if (sy != psym) { flush(); psym = sy; }
+			plen += l;
+		};
+		auto next_rec = [&]() {
+			++rr_;
+			if (rr_ < rend) { nextP = (uint32_t)(A.recP[rr_] - C.blkStart); na = A.recSym[rr_]; nc = A.recCnt[rr_]; }
+		};
+		for (uint32_t g = s; g <= eLast; ++g) {
+			const uint32_t rw = S.runs[tt * RB2_RUNS_STRIDE + qq];
+			const uint32_t sy = RUN_SYM(rw), end = p0 + RUN_LEN(rw);
+			uint32_t cur = p0;
+			while (rr_ < rend && nextP < end) {
+				if (nextP > cur) { emit(sy, nextP - cur); cur = nextP; }
+				emit(na, nc);
+				next_rec();
+			}
+			emit(sy, end - cur);
+			p0 = end;
+			if (++qq >= F.laneNr[tt]) { qq = 0; do { ++tt; } while (tt < 32 && F.laneNr[tt] == 0); }
+		}
+		while (rr_ < rend) { emit(na, nc); next_rec(); }
+		flush();
+		F.eStart[k] = oldStart;
+		F.eEnd[k] = tt < 32 ? tt * 16 + RUN_OFF(S.runs[tt * RB2_RUNS_STRIDE + qq]) : 2 + nbytes;
+		F.eNew[k] = o;
+		F.eBuf[k] = lane * 16;
+	}
+	__syncwarp();
+	// ---- output geometry ---------------------------------------------------------------
+	int32_t delta = 0;
+	if ((uint32_t)lane < ng) delta = (int32_t)F.eNew[lane] - (int32_t)(F.eEnd[lane] - F.eStart[lane]);
+	const int32_t dIncl = warp_incl_scan(delta, lane);
+	if ((uint32_t)lane < ng) { F.eCum[lane] = dIncl - delta; F.oStart[lane] = F.eStart[lane] + (dIncl - delta); }
+	const int32_t totalDelta = __shfl_sync(FULLMASK, dIncl, 31);
+	if (lane == 0) F.eCum[ng] = totalDelta;
+	__syncwarp();
+	const uint32_t outEnd = 2 + nbytes + totalDelta;   // end of the output image (header included)
+	const uint32_t outBytes = outEnd - 2;
+	uint32_t K = 1, cutImg = outEnd, cutLane = 32;
+	if (outBytes > RB2_FILL) {
+		// split in two at the first run of some lane (never inside an edited span)
+		K = 2;
+		uint32_t score = 0xffffffffu;
+		if (C.d.nr) {
+			const uint32_t bpF = lane * 16 + RUN_OFF(S.runs[lane * RB2_RUNS_STRIDE]);
+			uint32_t kk = 0;
+			while (kk < ng && F.eStart[kk] <= bpF) ++kk;
+			const bool inside = kk && bpF < F.eEnd[kk - 1];
+			const uint32_t cand = bpF + F.eCum[kk];
+			if (!inside && cand > 2 && cand - 2 <= RB2_FILL && outEnd - cand <= RB2_FILL && cand < outEnd) {
+				const uint32_t mid = 2 + outBytes / 2;
+				score = ((cand > mid ? cand - mid : mid - cand) << 5) | lane;
+				cutImg = cand;
+			}
+		}
+		uint32_t best = score;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(FULLMASK, best, o); best = y < best ? y : best; }
+		if (best == 0xffffffffu) return false;
+		cutLane = best & 31;
+		cutImg = __shfl_sync(FULLMASK, cutImg, cutLane);
+	}
+	const uint32_t newBase = alloc_blocks(A, lane, K - 1);
+	if (newBase == NONE32) return true; // pool exhausted: item stays unmerged, the host retries
+
+	// ---- new per-block symbol counts ------------------------------------------------------
+	if (K == 1) {
+		if (lane < 6) {
+			uint32_t v = 0;
+#pragma unroll
+			for (int x = 0; x < 6; ++x) if (lane == x) v = C.blkCnt[x];
+			A.blkCnt[(size_t)C.phys * 6 + lane] = v + F.cntAdd[lane];
+		}
+	} else {
+		const uint32_t cutPos = __shfl_sync(FULLMASK, C.basePos, cutLane);
+		uint32_t v0 = 0, v1 = 0;
+#pragma unroll
+		for (int x = 0; x < 6; ++x) {
+			const uint32_t mine = act && a == (uint32_t)x ? cnt : 0;
+			const uint32_t add0 = warp_sum(act && P < cutPos ? mine : 0u);
+			const uint32_t before = __shfl_sync(FULLMASK, C.baseCnt[x], cutLane);
+			if (lane == x) { v0 = before + add0; v1 = C.blkCnt[x] - before + F.cntAdd[x] - add0; }
+		}
+		if (lane < 6) { A.blkCnt[(size_t)C.phys * 6 + lane] = v0; A.blkCnt[(size_t)newBase * 6 + lane] = v1; }
+	}
+	// ---- assemble the output image(s) by pulling 16 bytes per lane -----------------------------
+	// The output is a sequence of segments: verbatim stretches of the input image (shifted by the
+	// byte deltas of the edits in front) and the edits' replacement bytes.  Both live in S.stage,
+	// so a segment is "16 bytes from stage[window - shift]", masked to the bytes it covers.
+	auto fetch16 = [&](uint32_t srcByte, uint32_t (&x)[4]) {
+		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.stage) + (srcByte >> 2);
+		const uint32_t sh = (srcByte & 3) * 8;
+		const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+		x[0] = __funnelshift_r(a0, a1, sh); x[1] = __funnelshift_r(a1, a2, sh);
+		x[2] = __funnelshift_r(a2, a3, sh); x[3] = __funnelshift_r(a3, a4, sh);
+	};
+	auto pull16 = [&](uint32_t base, uint32_t end, uint32_t hdr) -> uint4 {
+		// image bytes [base, base+16) clipped to `end`; lane 0's first two bytes become the header
+		uint32_t wv[4] = { 0, 0, 0, 0 };
+		const uint32_t stop = base + 16 < end ? base + 16 : end;
+		if (base < stop) {
+			uint32_t kk = 0; // #edits whose output start is <= base
+			{ uint32_t lo = 0, hi = ng; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.oStart[mid] <= base) lo = mid + 1; else hi = mid; } kk = lo; }
+			uint32_t pos = base;
+			while (pos < stop) {
+				uint32_t segEnd, src;
+				const uint32_t newEnd = kk ? F.oStart[kk - 1] + F.eNew[kk - 1] : 0;
+				if (kk && pos < newEnd) { // inside the replacement bytes of edit kk-1
+					segEnd = newEnd;
+					src = EBUF_OFF + F.eBuf[kk - 1] + base - F.oStart[kk - 1];
+				} else {                  // verbatim input up to the next edit
+					segEnd = kk < ng ? F.oStart[kk] : 0xffffffffu;
+					if (segEnd <= pos) { ++kk; continue; }
+					src = IMG_OFF + base - (uint32_t)F.eCum[kk];
+				}
+				if (segEnd > stop) segEnd = stop;
+				uint32_t x[4];
+				fetch16(src, x);
+				if (pos == base && segEnd == base + 16) { wv[0] = x[0]; wv[1] = x[1]; wv[2] = x[2]; wv[3] = x[3]; }
+				else { // keep bytes [pos-base, segEnd-base) of the window
+					const uint32_t lo = pos - base, hi = segEnd - base; // 0 <= lo < hi <= 16
+					const uint64_t geLo0 = lo >= 8 ? 0ull : (~0ull << (lo * 8)), geLo1 = lo > 8 ? (~0ull << ((lo - 8) * 8)) : ~0ull;
+					const uint64_t ltHi0 = hi >= 8 ? ~0ull : ~(~0ull << (hi * 8)), ltHi1 = hi >= 16 ? ~0ull : (hi > 8 ? ~(~0ull << ((hi - 8) * 8)) : 0ull);
+					const uint64_t m0 = geLo0 & ltHi0, m1 = geLo1 & ltHi1;
+					wv[0] |= x[0] & (uint32_t)m0; wv[1] |= x[1] & (uint32_t)(m0 >> 32);
+					wv[2] |= x[2] & (uint32_t)m1; wv[3] |= x[3] & (uint32_t)(m1 >> 32);
+				}
+				pos = segEnd;
+			}
+		}
+		if (lane == 0) wv[0] = (wv[0] & 0xffff0000u) | hdr;
+		return make_uint4(wv[0], wv[1], wv[2], wv[3]);
+	};
+	const uint32_t end0 = K == 1 ? outEnd : cutImg;
+	const uint4 v0 = pull16(lane * 16, end0, end0 - 2);
+	uint4 v1 = make_uint4(0, 0, 0, 0);
+	if (K == 2) v1 = pull16(cutImg - 2 + lane * 16, outEnd, outEnd - cutImg);
+	*(reinterpret_cast<uint4*>(A.pool + (size_t)C.phys * RB2_BLK) + lane) = v0;
+	if (K == 2) *(reinterpret_cast<uint4*>(A.pool + (size_t)newBase * RB2_BLK) + lane) = v1;
+	if (lane == 0) { A.itemPieces[C.w] = K; A.itemFirst[C.w] = C.phys; A.itemRest[C.w] = newBase; }
+	return true;
+}
+
+// One warp per work item = (logical block, slice of <= RMAX of its records).
+__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	ItemCtx C;
+	C.w = blockIdx.x * MERGE_WARPS + wid;
+	if (C.w >= A.ctl->nItems) return;
+	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
+	MergeSmem &S = reinterpret_cast<MergeSmem*>(smraw)[wid];
+
+	C.i = A.itemBlk[C.w];
+	const uint32_t it0 = A.itemOff[C.i];
+	C.nIt = A.itemOff[C.i + 1] - it0; C.sub = C.w - it0;
+	const int b = bucket_of(A.ctl->blkBkt, C.i);
+	const uint32_t recLo = C.i == A.ctl->blkBkt[b] ? A.ctl->recBkt[b] : A.recHi[C.i - 1], recHiB = A.recHi[C.i];
+	C.r0 = recLo + C.sub * RMAX; C.r1 = C.r0 + RMAX < recHiB ? C.r0 + RMAX : recHiB;
+	C.blkStart = A.dir.cumLen[C.i];
+	C.phys = A.dir.order[C.i];
+	C.cumCntBlk = A.dir.cumCnt + (size_t)C.i * 6;
+	uint32_t err = 0;
+	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.runs, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own);
 	if (err && lane == 0) atomicOr(&A.ctl->err, err);
+
+	bool done = false;
+	if (C.nIt == 1 && C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C);
+	if (!done) merge_general(A, S, lane, C);
 }
 
 struct RebuildScan { // K=1: pieces per old logical block -> new logical order
