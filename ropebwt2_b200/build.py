@@ -9,8 +9,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OUT = os.path.join(PKG, "_build")
+OUT = os.environ.get("RB2_BUILD_DIR", os.path.join(PKG, "_build"))
 LIB = os.path.join(OUT, "libropebwt2_b200.so")
+EXTRA = os.environ.get("RB2_NVCC_EXTRA", "").split()
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -40,7 +41,7 @@ def build(force: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     cc = os.environ.get("CC", "gcc")
     with open(os.path.join(OUT, "build.log"), "w") as log:
-        _run([nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "rb2_engine.cu"), "-o", os.path.join(OUT, "rb2_engine.o")], log)
+        _run([nvcc] + NVCC_FLAGS + EXTRA + ["-c", os.path.join(CSRC, "rb2_engine.cu"), "-o", os.path.join(OUT, "rb2_engine.o")], log)
         _run([cc, "-O2", "-g", "-Wall", "-fPIC", "-c", os.path.join(CSRC, "mrope_b200.c"), "-o", os.path.join(OUT, "mrope_b200.o")], log)
         _run([nvcc, "-shared", "-o", LIB, os.path.join(OUT, "rb2_engine.o"), os.path.join(OUT, "mrope_b200.o"),
               "-cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64"], log)

@@ -23,17 +23,30 @@
 #define RB2_BLK 512
 #define RB2_FILL 494
 #define RB2_MAXRUN ((1u << 19) - 1)
-#define RB2_RUNS_STRIDE 17  // per-lane stride (words) of the decoded-run scratch: odd => conflict-free
-// decoded run word: byte offset inside the lane's 16 bytes (4 bits) | length (19 bits) | symbol (3 bits)
-#define RUN_SYM(r) ((r) & 7u)
-#define RUN_LEN(r) (((r) >> 3) & 0x7ffffu)
-#define RUN_OFF(r) ((r) >> 22)
+// One warp decodes one block.  Lane i owns bytes [16i, 16i+16) (one 128-bit load) and accounts for
+// the runs that START in its bytes.  The block image is kept in shared memory (`img`, 512 + 16
+// bytes, the 16 extra bytes zero) so that individual runs can be parsed on demand.
+#define RB2_IMG_BYTES (RB2_BLK + 16)
 
 struct LaneDec {
 	uint32_t nr;     // runs starting in this lane's 16 bytes
 	uint32_t len;    // symbols in those runs
+	uint32_t fb;     // byte offset (0..15) of the first run start in the lane, 16 if none
 	uint32_t c[6];   // per-symbol counts of those runs
 };
+
+// parse the run whose first byte is img[bp]: symbol, length, encoded size
+__device__ __forceinline__ void parse_run(const uint8_t *img, uint32_t bp, uint32_t &sym, uint32_t &len, uint32_t &nb)
+{
+	const uint32_t b = img[bp];
+	sym = b & 7u;
+	if (b < 0x80u) { len = b >> 3; nb = 1; }
+	else if (b < 0xE0u) { len = ((b & 0x18u) << 3) | (img[bp + 1] & 0x3fu); nb = 2; }
+	else {
+		len = ((b & 0x08u) << 15) | ((img[bp + 1] & 0x3fu) << 12) | ((img[bp + 2] & 0x3fu) << 6) | (img[bp + 3] & 0x3fu);
+		nb = 4;
+	}
+}
 
 // byte i (0..19) of the 20-byte window {own 16 bytes, first word of the next lane}
 __device__ __forceinline__ uint32_t win_byte(const uint32_t (&W)[5], int i)
@@ -41,15 +54,13 @@ __device__ __forceinline__ uint32_t win_byte(const uint32_t (&W)[5], int i)
 	return (W[i >> 2] >> ((i & 3) * 8)) & 0xffu;
 }
 
-// Decode the runs starting in this lane's bytes into runs[0..nr) as (byteoff << 22 | len << 3 | sym).
-// `runs` points at this lane's private slice (stride RB2_RUNS_STRIDE words); `lcs` is a lane-private
-// scratch of 6 shared-memory words used to accumulate the per-symbol counts (indexing registers by
-// a run-time symbol would cost a 6-way select per run).
-__device__ __forceinline__ void decode_lane(const uint4 &own, uint32_t next0, int lane, uint32_t nbytes,
-                                            uint32_t *runs, uint32_t *lcs, LaneDec &d, uint32_t &err)
+// Byte-serial accounting of one lane (any mix of 1/2/4-byte runs).  `lcs` = 6 lane-private
+// shared-memory words (indexing registers by a run-time symbol would cost a 6-way select per run).
+__device__ __forceinline__ void decode_lane_serial(const uint4 &own, uint32_t next0, int lane, uint32_t nbytes,
+                                                   uint32_t *lcs, LaneDec &d, uint32_t &err)
 {
 	const uint32_t W[5] = { own.x, own.y, own.z, own.w, next0 };
-	uint32_t nr = 0, tot = 0;
+	uint32_t nr = 0, tot = 0, fb = 16;
 	const int lim = (int)nbytes + 2 - lane * 16; // byte i of this lane is a run byte iff i < lim (and i >= 2 in lane 0)
 #pragma unroll
 	for (int a = 0; a < 6; ++a) lcs[a] = 0;
@@ -66,33 +77,79 @@ __device__ __forceinline__ void decode_lane(const uint4 &own, uint32_t next0, in
 				l = ((b & 0x08u) << 15) | ((win_byte(W, i + 1) & 0x3fu) << 12)
 				  | ((win_byte(W, i + 2) & 0x3fu) << 6) | (win_byte(W, i + 3) & 0x3fu);
 			}
-			const uint32_t s = b & 7u;
-			runs[nr++] = ((uint32_t)i << 22) | (l << 3) | s;
-			tot += l;
-			lcs[s] += l;
+			if (nr == 0) fb = i;
+			++nr; tot += l;
+			lcs[b & 7u] += l;
 		}
 	}
-	d.nr = nr; d.len = tot;
+	d.nr = nr; d.len = tot; d.fb = fb;
 #pragma unroll
 	for (int a = 0; a < 6; ++a) d.c[a] = lcs[a];
 }
 
+// SIMD accounting of a lane whose run bytes are all 1-byte runs (every byte < 0x80; bytes behind
+// the block's last run are zero by invariant and count as nothing).  Per 4 bytes: lengths =
+// (w >> 3) & 0x0f.., the four symbols become a PRMT selector, and for each symbol x a one-hot byte
+// table looked up through PRMT gives 0/1 weights for a 4-way dot product (DP4A) with the lengths.
+__device__ __forceinline__ void decode_lane_simd(const uint4 &own, int lane, uint32_t nbytes, LaneDec &d)
+{
+	uint32_t w[4] = { own.x, own.y, own.z, own.w };
+	if (lane == 0) w[0] &= 0xffff0000u; // the 2-byte header is not run data
+	const int lim = (int)nbytes + 2 - lane * 16;
+	const int hi = lim < 0 ? 0 : (lim > 16 ? 16 : lim), lo = lane == 0 ? 2 : 0;
+	if (hi < 16) { // the one lane holding the end of the data: ignore whatever sits behind it
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int keep = hi - 4 * j;
+			w[j] = keep >= 4 ? w[j] : (keep <= 0 ? 0u : w[j] & ((1u << (8 * keep)) - 1u));
+		}
+	}
+	d.nr = hi > lo ? hi - lo : 0;
+	d.fb = hi > lo ? lo : 16;
+	uint32_t tot = 0, c[6] = { 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const uint32_t lens = (w[j] >> 3) & 0x0f0f0f0fu;
+		const uint32_t sy = w[j] & 0x07070707u;
+		const uint32_t t = sy | (sy >> 4);
+		const uint32_t sel = (t & 0xffu) | ((t >> 8) & 0xff00u);
+		tot = __dp4a(lens, 0x01010101u, tot);
+		c[0] = __dp4a(lens, __byte_perm(0x00000001u, 0u, sel), c[0]);
+		c[1] = __dp4a(lens, __byte_perm(0x00000100u, 0u, sel), c[1]);
+		c[2] = __dp4a(lens, __byte_perm(0x00010000u, 0u, sel), c[2]);
+		c[3] = __dp4a(lens, __byte_perm(0x01000000u, 0u, sel), c[3]);
+		c[4] = __dp4a(lens, __byte_perm(0u, 0x00000001u, sel), c[4]);
+		c[5] = __dp4a(lens, __byte_perm(0u, 0x00000100u, sel), c[5]);
+	}
+	d.len = tot;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) d.c[a] = c[a];
+}
+
 // Whole-warp decode of one block.  On return, for this lane:
-//   d        runs starting in the lane
+//   d        accounting of the runs starting in the lane
 //   basePos  symbols in front of the lane's first run (exclusive scan of d.len)
 //   baseCnt  per-symbol counts in front of the lane (exclusive scan of d.c)
 //   blkLen   symbols in the block, blkCnt[6] per-symbol totals (same in all lanes)
-// cntScratch: 32 x 7 shared-memory words (lane-private slices).
-__device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, uint32_t *runsWarp, uint32_t *cntScratch,
+// img: RB2_IMG_BYTES of shared memory receiving the block image; cntScratch: 32 x 7 words.
+__device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, uint8_t *img, uint32_t *cntScratch,
                                                   LaneDec &d, uint32_t &basePos, uint32_t (&baseCnt)[6],
                                                   uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err, uint4 &own)
 {
 	// plain (coherent) load: k_merge_blocks rewrites the same block in place later on
 	own = *(reinterpret_cast<const uint4*>(blk) + lane);
+	reinterpret_cast<uint4*>(img)[lane] = own;
+	if (lane == 0) reinterpret_cast<uint4*>(img)[32] = make_uint4(0, 0, 0, 0);
 	nbytes = __shfl_sync(FULLMASK, own.x, 0) & 0xffffu;
 	uint32_t next0 = __shfl_down_sync(FULLMASK, own.x, 1);
 	if (lane == 31) next0 = 0;
-	decode_lane(own, next0, lane, nbytes, runsWarp + lane * RB2_RUNS_STRIDE, cntScratch + lane * 7, d, err);
+	// a lane is "pure" if none of its run bytes has the top bit set (no multi-byte run touches it)
+	uint32_t any = own.x | own.y | own.z | own.w;
+	if (lane == 0) any = (own.x & 0xffff0000u) | own.y | own.z | own.w;
+	const int lim = (int)nbytes + 2 - lane * 16;
+	const bool pure = (any & 0x80808080u) == 0 || lim <= 0;
+	if (pure) decode_lane_simd(own, lane, nbytes, d);
+	else decode_lane_serial(own, next0, lane, nbytes, cntScratch + lane * 7, d, err);
 	uint32_t incl = warp_incl_scan(d.len, lane);
 	basePos = incl - d.len;
 	blkLen = __shfl_sync(FULLMASK, incl, 31);

@@ -119,6 +119,52 @@ __global__ void __launch_bounds__(1024) scan_mid(T *ctaTot, uint64_t nCta, T *gr
 	}
 }
 
+// Two-level variant of scan_mid for long arrays (one CTA would serialise ~n/1024 rows per thread):
+// mid_reduce sums chunks of MID_ROWS rows, scan_mid scans the chunk sums, mid_apply scans inside
+// each chunk.  Rows are K consecutive counters.
+#define MID_ROWS 1024
+template <int K, typename T>
+__global__ void __launch_bounds__(256) mid_reduce(const T *rows, uint64_t n, T *chunkTot)
+{
+	__shared__ T sm[K * 8];
+	const uint64_t r0 = (uint64_t)blockIdx.x * MID_ROWS + threadIdx.x * 4;
+	T v[K], tot[K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] = 0;
+	for (int j = 0; j < 4; ++j) if (r0 + j < n) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) v[k] += rows[(r0 + j) * K + k];
+	}
+	cta_excl_scan<K, 256, T>(v, tot, sm);
+	if (threadIdx.x == 0) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) chunkTot[(uint64_t)blockIdx.x * K + k] = tot[k];
+	}
+}
+
+template <int K, typename T>
+__global__ void __launch_bounds__(256) mid_apply(T *rows, uint64_t n, const T *chunkPre)
+{
+	__shared__ T sm[K * 8];
+	const uint64_t r0 = (uint64_t)blockIdx.x * MID_ROWS + threadIdx.x * 4;
+	T v[K], tot[K], own[4][K];
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) { own[j][k] = r0 + j < n ? rows[(r0 + j) * K + k] : 0; v[k] += own[j][k]; }
+	}
+	cta_excl_scan<K, 256, T>(v, tot, sm);
+#pragma unroll
+	for (int k = 0; k < K; ++k) v[k] += chunkPre[(uint64_t)blockIdx.x * K + k];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) if (r0 + j < n) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) { rows[(r0 + j) * K + k] = v[k]; v[k] += own[j][k]; }
+	}
+}
+
 template <int K, typename T, class F>
 __global__ void __launch_bounds__(SCAN_NT) scan_apply(F f, uint64_t n, const T *ctaPre)
 {

@@ -34,7 +34,12 @@
 #define STAGE_BYTES 2560   // >= 510 + 8*RMAX: old block bytes + <=8 new bytes per record
 #define SPLIT_T     488    // piece size target when a block overflows (pieces are < SPLIT_T+4 <= 494)
 #define MAXPIECES   16
+#ifndef MERGE_WARPS
 #define MERGE_WARPS 4
+#endif
+#ifndef MERGE_MINCTA
+#define MERGE_MINCTA 8
+#endif
 #define NONE32      0xffffffffu
 #define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
 #define NGC         13     // group-scan counters: has[6], hist[6], nrec
@@ -244,26 +249,27 @@ __device__ __forceinline__ uint32_t find_block(const int64_t *cumLen, uint32_t l
 }
 
 // occ(a, x) for all six symbols; warp-cooperative, result valid in every lane.
-// scratch: runs[32*17] words + res[6] int64, private to the warp.
+// scratch: img[RB2_IMG_BYTES], cnt[32*7] words, res[6] int64 -- private to the warp.
 __device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int lane,
-                           uint32_t *runs, uint32_t *cntScratch, int64_t *res, int64_t (&out)[6], uint32_t &err)
+                           uint8_t *img, uint32_t *cntScratch, int64_t *res, int64_t (&out)[6], uint32_t &err)
 {
 	uint32_t i = find_block(dir.cumLen, 0, nlog - 1, x);
 	if (i >= nlog) i = nlog - 1;
 	const uint32_t xrel = (uint32_t)(x - dir.cumLen[i]);
 	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes; uint4 own;
-	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, runs, cntScratch, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err, own);
+	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, img, cntScratch, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err, own);
 	const bool mine = xrel > basePos && xrel <= basePos + d.len;
 	if (xrel == 0) { if (lane < 6) res[lane] = dir.cumCnt[(size_t)i * 6 + lane]; }
 	else if (mine) {
 		uint32_t pc[6] = { baseCnt[0], baseCnt[1], baseCnt[2], baseCnt[3], baseCnt[4], baseCnt[5] };
-		uint32_t pos = basePos;
-		const uint32_t *r = runs + lane * RB2_RUNS_STRIDE;
+		uint32_t pos = basePos, bp = lane * 16 + d.fb;
 		for (uint32_t q = 0; q < d.nr && pos < xrel; ++q) {
-			uint32_t l = RUN_LEN(r[q]), s = RUN_SYM(r[q]), take = xrel - pos < l ? xrel - pos : l;
+			uint32_t l, s, nb;
+			parse_run(img, bp, s, l, nb);
+			const uint32_t take = xrel - pos < l ? xrel - pos : l;
 #pragma unroll
 			for (int a = 0; a < 6; ++a) pc[a] += s == a ? take : 0;
-			pos += l;
+			pos += l; bp += nb;
 		}
 #pragma unroll
 		for (int a = 0; a < 6; ++a) res[a] = dir.cumCnt[(size_t)i * 6 + a] + pc[a];
@@ -278,7 +284,7 @@ __device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t 
 __global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir dir, uint32_t nlog, uint32_t G,
                                                      const int64_t *gL, const int64_t *gSize, int64_t *sizes6, Ctl *ctl)
 {
-	__shared__ uint32_t sRuns[4][32 * RB2_RUNS_STRIDE];
+	__shared__ __align__(16) uint8_t sRuns[4][RB2_IMG_BYTES];
 	__shared__ uint32_t sCnt[4][32 * 7];
 	__shared__ int64_t sRes[4][6];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(128) k_rank_groups(const uint8_t *pool, Dir di
 // API rank (mr_rank2a): one warp, up to two queries
 __global__ void __launch_bounds__(32) k_rank_query(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t x, int64_t y, int64_t *out, Ctl *ctl)
 {
-	__shared__ uint32_t sRuns[32 * RB2_RUNS_STRIDE];
+	__shared__ __align__(16) uint8_t sRuns[RB2_IMG_BYTES];
 	__shared__ uint32_t sCnt[32 * 7];
 	__shared__ int64_t sRes[6];
 	const int lane = threadIdx.x;
@@ -399,7 +405,23 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 		nrec += (h[a] + RB2_MAXRUN - 1) / RB2_MAXRUN;
 	}
 	v[12] = nrec;
-	cta_excl_scan<NGC, 256, uint32_t>(v, tot, sm);
+	// All 13 counters of a CTA of small groups fit 16-bit fields (256 threads x <= 32 members), so
+	// three 64-bit scans replace thirteen 32-bit ones; a CTA holding a big group takes the wide path.
+	__shared__ uint64_t sm64[3 * 8];
+	const int anyBig = __syncthreads_or(valid && cnt > SMALL_GROUP);
+	if (!anyBig) {
+		uint64_t pk[3], pt[3];
+		pk[0] = (uint64_t)v[0] | (uint64_t)v[1] << 10 | (uint64_t)v[2] << 20 | (uint64_t)v[3] << 30 | (uint64_t)v[4] << 40 | (uint64_t)v[5] << 50;
+		pk[1] = (uint64_t)v[6] | (uint64_t)v[7] << 16 | (uint64_t)v[8] << 32 | (uint64_t)v[9] << 48;
+		pk[2] = (uint64_t)v[10] | (uint64_t)v[11] << 16 | (uint64_t)v[12] << 32;
+		cta_excl_scan<3, 256, uint64_t>(pk, pt, sm64);
+#pragma unroll
+		for (int a = 0; a < 6; ++a) { v[a] = (uint32_t)(pk[0] >> (10 * a)) & 0x3ffu; tot[a] = (uint32_t)(pt[0] >> (10 * a)) & 0x3ffu; }
+#pragma unroll
+		for (int a = 0; a < 4; ++a) { v[6 + a] = (uint32_t)(pk[1] >> (16 * a)) & 0xffffu; tot[6 + a] = (uint32_t)(pt[1] >> (16 * a)) & 0xffffu; }
+#pragma unroll
+		for (int a = 0; a < 3; ++a) { v[10 + a] = (uint32_t)(pk[2] >> (16 * a)) & 0xffffu; tot[10 + a] = (uint32_t)(pt[2] >> (16 * a)) & 0xffffu; }
+	} else cta_excl_scan<NGC, 256, uint32_t>(v, tot, sm);
 	if (MODE == 0) {
 		if (threadIdx.x == 0) {
 #pragma unroll
@@ -525,17 +547,16 @@ struct GenScratch {                 // general path
 };
 struct FastScratch {                // edit-based fast path
 	uint32_t laneBase[32 * 7];      // per-lane exclusive per-symbol counts
-	uint32_t laneEnd[32], laneNr[32], laneRunPre[32];
+	uint32_t laneEnd[32], laneNr[32], laneRunPre[32], laneFb[32];
 	uint32_t eStart[FAST_MAXREC + 1], eEnd[FAST_MAXREC + 1], eNew[FAST_MAXREC + 1], eBuf[FAST_MAXREC + 1];
 	int32_t  eCum[FAST_MAXREC + 2];   // exclusive prefix of (new - old) byte deltas
-	uint32_t oStart[FAST_MAXREC + 1]; // edit start in the output image
 	uint32_t cntAdd[8];               // symbols added by the item's records
 };
-#define IMG_OFF  512   // fast path: the input block image sits at stage[512, 1024)
-#define EBUF_OFF 2048  // fast path: replacement bytes of the edits, 16 per record, at stage[2048, 2560)
+#define OUT_OFF  0     // fast path: the output block image is assembled at stage[0, 1024)
+#define EBUF_OFF 1536  // fast path: replacement bytes of the edits, 16 per record, at stage[1536, 2048)
 struct alignas(16) MergeSmem {
-	uint32_t runs[32 * RB2_RUNS_STRIDE];
-	uint8_t  stage[STAGE_BYTES];    // general: output run bytes; fast: input image + replacement bytes
+	uint8_t  img[RB2_IMG_BYTES];    // the input block, byte-addressable (+16 zero bytes)
+	uint8_t  stage[STAGE_BYTES];    // general: output run bytes; fast: output image + replacement bytes
 	union { GenScratch g; FastScratch f; } u;
 };
 
@@ -543,7 +564,7 @@ struct alignas(16) MergeSmem {
 // EMIT=false: only count output bytes.  EMIT=true: write bytes into `stage` from offset `o`,
 // note piece cuts / per-piece counts, and deliver rank(a, P) of every record.
 template <bool EMIT>
-__device__ __forceinline__ uint32_t lane_merge(const uint32_t *runs, uint32_t nr, uint32_t pos, uint32_t rlo, uint32_t rhi,
+__device__ __forceinline__ uint32_t lane_merge(const uint8_t *img, uint32_t bp, uint32_t nr, uint32_t pos, uint32_t rlo, uint32_t rhi,
                                                const MergeArgs &A, int64_t blkStart, uint32_t posLo, uint32_t posHi,
                                                const int64_t *cumCntBlk, uint32_t *lc, uint32_t o, uint32_t T,
                                                uint8_t *stage, uint32_t *cut, uint32_t *pcnt, uint32_t *pl)
@@ -594,7 +615,10 @@ __device__ __forceinline__ uint32_t lane_merge(const uint32_t *runs, uint32_t nr
 	};
 
 	for (uint32_t q = 0; q < nr; ++q) {
-		const uint32_t s = RUN_SYM(runs[q]), end = pos + RUN_LEN(runs[q]);
+		uint32_t s, rl, nb;
+		parse_run(img, bp, s, rl, nb);
+		bp += nb;
+		const uint32_t end = pos + rl;
 		uint32_t cur = pos;
 		while (nextP < end) {              // records in front of or inside this run
 			if (nextP > cur) { emit_old(s, cur, nextP); lc[s] += nextP - cur; cur = nextP; }
@@ -659,12 +683,12 @@ __device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, 
 	if (lane == 0) rlo = r0;
 
 	uint32_t *lc = G.lcnt + lane * 7, *pl = G.pcl + lane * 7;
-	const uint32_t *runs = S.runs + lane * RB2_RUNS_STRIDE;
+	const uint32_t bp0 = lane * 16 + C.d.fb;
 #pragma unroll
 	for (int a = 0; a < 6; ++a) { lc[a] = C.baseCnt[a]; pl[a] = 0; }
 
 	// pass 1: output bytes per lane
-	const uint32_t myBytes = lane_merge<false>(runs, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, 0, 1u << 30, S.stage, G.cut, G.pcnt, pl);
+	const uint32_t myBytes = lane_merge<false>(S.img, bp0, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, 0, 1u << 30, S.stage, G.cut, G.pcnt, pl);
 	const uint32_t incl = warp_incl_scan(myBytes, lane);
 	const uint32_t out = __shfl_sync(FULLMASK, incl, 31);
 	if (out > STAGE_BYTES) { if (lane == 0) atomicOr(&A.ctl->err, RB2_ERR_STAGE); return; }
@@ -683,7 +707,7 @@ __device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, 
 	__syncwarp();
 
 	// pass 2: emit bytes, piece cuts, piece counts, ranks
-	lane_merge<true>(runs, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, incl - myBytes, T, S.stage, G.cut, G.pcnt, pl);
+	lane_merge<true>(S.img, bp0, C.d.nr, C.basePos, rlo, rhi, A, blkStart, posLo, posHi, C.cumCntBlk, lc, incl - myBytes, T, S.stage, G.cut, G.pcnt, pl);
 	__syncwarp();
 	if (lane == 0) G.cut[K] = out;
 	__syncwarp();
@@ -716,46 +740,48 @@ __device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, 
 
 // ---- fast path: one item per block, <= 32 records, non-empty block ---------------------------
 // Only the runs a record touches are re-encoded.  Lane j locates record j (target lane by binary
-// search over the per-lane end positions, then a walk over that lane's <= 16 decoded runs), which
-// also yields rank(a, P).  Records whose touched runs overlap form a group; the group's first lane
-// re-encodes that short span with the records merged in ("edit": old byte range -> new bytes).
-// The output block image is then assembled by pulling: every lane fetches its 16 output bytes
-// either verbatim from the shifted input image or from the edits' replacement bytes.
-// Returns false (no side effects besides idempotent rank writes) if it cannot place a split.
+// search over the per-lane end positions, then a walk over that lane's <= 16 runs, parsed from the
+// shared-memory block image), which also yields rank(a, P).  Records whose touched runs overlap
+// form a group; the group's first lane re-encodes that short span with the records merged in (an
+// "edit": old byte range -> replacement bytes).  The output image is assembled by pushing: every
+// lane stores its 16 input bytes at their shifted position (bytes inside an edited span are
+// dropped), the group heads store their replacement bytes, then each lane reads back 16 aligned
+// bytes.  Returns false (no side effects besides idempotent rank writes) if it cannot place a split.
 __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int lane, const ItemCtx &C)
 {
 	FastScratch &F = S.u.f;
-	const uint32_t nrec = C.r1 - C.r0, nbytes = C.nbytes;
+	const uint8_t *img = S.img;
+	const uint32_t nrec = C.r1 - C.r0, nbytes = C.nbytes, endBp = 2 + nbytes;
 	F.laneEnd[lane] = C.basePos + C.d.len;
 	F.laneNr[lane] = C.d.nr;
+	F.laneFb[lane] = C.d.fb;
 	const uint32_t runIncl = warp_incl_scan(C.d.nr, lane);
 	F.laneRunPre[lane] = runIncl - C.d.nr;
 	const uint32_t nRuns = __shfl_sync(FULLMASK, runIncl, 31);
 #pragma unroll
 	for (int a = 0; a < 6; ++a) F.laneBase[lane * 7 + a] = C.baseCnt[a];
-	reinterpret_cast<uint4*>(S.stage + IMG_OFF)[lane] = C.own; // input block image, byte-addressable
 	if (lane < 8) F.cntAdd[lane] = 0;
 	__syncwarp();
 
 	// ---- locate record `lane` ----------------------------------------------------------
 	const bool act = (uint32_t)lane < nrec;
-	uint32_t P = 0, a = 0, cnt = 0, t = 0, q = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
+	uint32_t P = 0, a = 0, cnt = 0, bpq = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
 	if (act) {
 		const uint32_t r = C.r0 + lane;
 		P = (uint32_t)(A.recP[r] - C.blkStart); a = A.recSym[r]; cnt = A.recCnt[r];
 		uint32_t lo = 0, hi = 31;
 		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.laneEnd[mid] >= P) hi = mid; else lo = mid + 1; }
-		t = lo;
+		const uint32_t t = lo;
 		pos = t ? F.laneEnd[t - 1] : 0;
 		uint32_t ca = F.laneBase[t * 7 + a];
-		const uint32_t *rr = S.runs + t * RB2_RUNS_STRIDE;
 		const uint32_t nrt = F.laneNr[t];
-		for (q = 0;; ++q) { // run that contains symbol P-1 (the first run for P == 0)
-			const uint32_t rw = rr[q];
-			len = RUN_LEN(rw); sym = RUN_SYM(rw);
+		uint32_t q = 0, nb;
+		bpq = t * 16 + F.laneFb[t];
+		for (;; ++q) { // run that contains symbol P-1 (the first run for P == 0)
+			parse_run(img, bpq, sym, len, nb);
 			if (pos + len >= P || q + 1 >= nrt) break;
 			ca += sym == a ? len : 0;
-			pos += len;
+			pos += len; bpq += nb;
 		}
 		off = P - pos;
 		const uint32_t dst = A.recDst[r];
@@ -780,8 +806,7 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 		uint32_t rr_ = C.r0 + lane;
 		const uint32_t rend = C.r0 + gend;
 		uint32_t nextP = P, na = a, nc = cnt;
-		uint32_t tt = t, qq = q, p0 = pos;
-		const uint32_t oldStart = tt * 16 + RUN_OFF(S.runs[tt * RB2_RUNS_STRIDE + qq]);
+		uint32_t bp = bpq, p0 = pos;
 		auto flush = [&]() {
 			while (plen) {
 				const uint32_t l = plen < RB2_MAXRUN ? plen : RB2_MAXRUN;
@@ -799,8 +824,10 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 			if (rr_ < rend) { nextP = (uint32_t)(A.recP[rr_] - C.blkStart); na = A.recSym[rr_]; nc = A.recCnt[rr_]; }
 		};
 		for (uint32_t g = s; g <= eLast; ++g) {
-			const uint32_t rw = S.runs[tt * RB2_RUNS_STRIDE + qq];
-			const uint32_t sy = RUN_SYM(rw), end = p0 + RUN_LEN(rw);
+			uint32_t sy, rl, nb;
+			parse_run(img, bp, sy, rl, nb);
+			bp += nb;
+			const uint32_t end = p0 + rl;
 			uint32_t cur = p0;
 			while (rr_ < rend && nextP < end) {
 				if (nextP > cur) { emit(sy, nextP - cur); cur = nextP; }
@@ -809,34 +836,39 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 			}
 			emit(sy, end - cur);
 			p0 = end;
-			if (++qq >= F.laneNr[tt]) { qq = 0; do { ++tt; } while (tt < 32 && F.laneNr[tt] == 0); }
 		}
 		while (rr_ < rend) { emit(na, nc); next_rec(); }
 		flush();
-		F.eStart[k] = oldStart;
-		F.eEnd[k] = tt < 32 ? tt * 16 + RUN_OFF(S.runs[tt * RB2_RUNS_STRIDE + qq]) : 2 + nbytes;
+		F.eStart[k] = bpq;   // the span's first byte ...
+		F.eEnd[k] = bp;      // ... and one past its last byte in the input image
 		F.eNew[k] = o;
-		F.eBuf[k] = lane * 16;
+		F.eBuf[k] = EBUF_OFF + lane * 16;
 	}
 	__syncwarp();
 	// ---- output geometry ---------------------------------------------------------------
 	int32_t delta = 0;
 	if ((uint32_t)lane < ng) delta = (int32_t)F.eNew[lane] - (int32_t)(F.eEnd[lane] - F.eStart[lane]);
 	const int32_t dIncl = warp_incl_scan(delta, lane);
-	if ((uint32_t)lane < ng) { F.eCum[lane] = dIncl - delta; F.oStart[lane] = F.eStart[lane] + (dIncl - delta); }
+	if ((uint32_t)lane < ng) F.eCum[lane] = dIncl - delta;
 	const int32_t totalDelta = __shfl_sync(FULLMASK, dIncl, 31);
 	if (lane == 0) F.eCum[ng] = totalDelta;
 	__syncwarp();
-	const uint32_t outEnd = 2 + nbytes + totalDelta;   // end of the output image (header included)
+	const uint32_t outEnd = endBp + totalDelta;   // end of the output image (header included)
 	const uint32_t outBytes = outEnd - 2;
+	// edits in front of this lane's input window, and whether the window is one verbatim stretch
+	const uint32_t bp0 = lane * 16;
+	uint32_t kA = 0;
+	{ uint32_t lo = 0, hi = ng; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.eStart[mid] <= bp0) lo = mid + 1; else hi = mid; } kA = lo; }
+	const bool insideFirst = kA && bp0 < F.eEnd[kA - 1];
+	const bool simple = !insideFirst && (kA >= ng || F.eStart[kA] >= bp0 + 16);
 	uint32_t K = 1, cutImg = outEnd, cutLane = 32;
 	if (outBytes > RB2_FILL) {
 		// split in two at the first run of some lane (never inside an edited span)
 		K = 2;
 		uint32_t score = 0xffffffffu;
 		if (C.d.nr) {
-			const uint32_t bpF = lane * 16 + RUN_OFF(S.runs[lane * RB2_RUNS_STRIDE]);
-			uint32_t kk = 0;
+			const uint32_t bpF = bp0 + C.d.fb;
+			uint32_t kk = kA;
 			while (kk < ng && F.eStart[kk] <= bpF) ++kk;
 			const bool inside = kk && bpF < F.eEnd[kk - 1];
 			const uint32_t cand = bpF + F.eCum[kk];
@@ -876,66 +908,74 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 		}
 		if (lane < 6) { A.blkCnt[(size_t)C.phys * 6 + lane] = v0; A.blkCnt[(size_t)newBase * 6 + lane] = v1; }
 	}
-	// ---- assemble the output image(s) by pulling 16 bytes per lane -----------------------------
-	// The output is a sequence of segments: verbatim stretches of the input image (shifted by the
-	// byte deltas of the edits in front) and the edits' replacement bytes.  Both live in S.stage,
-	// so a segment is "16 bytes from stage[window - shift]", masked to the bytes it covers.
-	auto fetch16 = [&](uint32_t srcByte, uint32_t (&x)[4]) {
-		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.stage) + (srcByte >> 2);
-		const uint32_t sh = (srcByte & 3) * 8;
-		const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
-		x[0] = __funnelshift_r(a0, a1, sh); x[1] = __funnelshift_r(a1, a2, sh);
-		x[2] = __funnelshift_r(a2, a3, sh); x[3] = __funnelshift_r(a3, a4, sh);
-	};
-	auto pull16 = [&](uint32_t base, uint32_t end, uint32_t hdr) -> uint4 {
-		// image bytes [base, base+16) clipped to `end`; lane 0's first two bytes become the header
-		uint32_t wv[4] = { 0, 0, 0, 0 };
-		const uint32_t stop = base + 16 < end ? base + 16 : end;
-		if (base < stop) {
-			uint32_t kk = 0; // #edits whose output start is <= base
-			{ uint32_t lo = 0, hi = ng; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.oStart[mid] <= base) lo = mid + 1; else hi = mid; } kk = lo; }
-			uint32_t pos = base;
-			while (pos < stop) {
-				uint32_t segEnd, src;
-				const uint32_t newEnd = kk ? F.oStart[kk - 1] + F.eNew[kk - 1] : 0;
-				if (kk && pos < newEnd) { // inside the replacement bytes of edit kk-1
-					segEnd = newEnd;
-					src = EBUF_OFF + F.eBuf[kk - 1] + base - F.oStart[kk - 1];
-				} else {                  // verbatim input up to the next edit
-					segEnd = kk < ng ? F.oStart[kk] : 0xffffffffu;
-					if (segEnd <= pos) { ++kk; continue; }
-					src = IMG_OFF + base - (uint32_t)F.eCum[kk];
+	// ---- assemble the output image: push input bytes and replacement bytes to their place ----------
+	uint8_t *out = S.stage + OUT_OFF;
+	{
+		const uint32_t w4[4] = { C.own.x, C.own.y, C.own.z, C.own.w };
+		if (simple) {
+			const uint32_t d0 = bp0 + (uint32_t)F.eCum[kA];
+#pragma unroll
+			for (int i = 0; i < 16; ++i) out[d0 + i] = (uint8_t)(w4[i >> 2] >> ((i & 3) * 8));
+		} else {
+			// walk the window with the current edit's bounds cached in registers
+			uint32_t kk = kA;
+			uint32_t curEnd = kk ? F.eEnd[kk - 1] : 0;                  // bytes below this belong to an edited span
+			uint32_t nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;  // first byte of the next edited span
+			uint32_t cum = (uint32_t)F.eCum[kk];
+#pragma unroll
+			for (int i = 0; i < 16; ++i) {
+				const uint32_t bp = bp0 + i;
+				if (bp >= nextStart) { // distinct starts: at most one edit begins per byte
+					++kk;
+					curEnd = F.eEnd[kk - 1];
+					nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;
+					cum = (uint32_t)F.eCum[kk];
 				}
-				if (segEnd > stop) segEnd = stop;
-				uint32_t x[4];
-				fetch16(src, x);
-				if (pos == base && segEnd == base + 16) { wv[0] = x[0]; wv[1] = x[1]; wv[2] = x[2]; wv[3] = x[3]; }
-				else { // keep bytes [pos-base, segEnd-base) of the window
-					const uint32_t lo = pos - base, hi = segEnd - base; // 0 <= lo < hi <= 16
-					const uint64_t geLo0 = lo >= 8 ? 0ull : (~0ull << (lo * 8)), geLo1 = lo > 8 ? (~0ull << ((lo - 8) * 8)) : ~0ull;
-					const uint64_t ltHi0 = hi >= 8 ? ~0ull : ~(~0ull << (hi * 8)), ltHi1 = hi >= 16 ? ~0ull : (hi > 8 ? ~(~0ull << ((hi - 8) * 8)) : 0ull);
-					const uint64_t m0 = geLo0 & ltHi0, m1 = geLo1 & ltHi1;
-					wv[0] |= x[0] & (uint32_t)m0; wv[1] |= x[1] & (uint32_t)(m0 >> 32);
-					wv[2] |= x[2] & (uint32_t)m1; wv[3] |= x[3] & (uint32_t)(m1 >> 32);
-				}
-				pos = segEnd;
+				if (bp >= curEnd) out[bp + cum] = (uint8_t)(w4[i >> 2] >> ((i & 3) * 8));
 			}
 		}
-		if (lane == 0) wv[0] = (wv[0] & 0xffff0000u) | hdr;
+		if (head) { // my group's replacement bytes
+			const uint32_t d0 = F.eStart[k] + (uint32_t)F.eCum[k], n = F.eNew[k];
+			const uint8_t *src = S.stage + EBUF_OFF + lane * 16;
+			for (uint32_t i = 0; i < n; ++i) out[d0 + i] = src[i];
+		}
+	}
+	// The zero bytes behind the input's last run were pushed too, so the image is zero up to byte
+	// 512 + totalDelta; only a shrinking block leaves a few stale bytes in front of byte 512.
+	if (totalDelta < 0 && lane == 31) for (int32_t i = totalDelta; i < 0; ++i) out[RB2_BLK + i] = 0;
+	__syncwarp();
+	auto tail_mask = [&](uint4 v, uint32_t base, uint32_t end) -> uint4 { // zero the bytes at image index >= end
+		if (base + 16 <= end) return v;
+		uint32_t wv[4] = { v.x, v.y, v.z, v.w };
+		const uint32_t keep = end > base ? end - base : 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const uint32_t kb = keep > (uint32_t)j * 4 ? keep - j * 4 : 0;
+			wv[j] = kb >= 4 ? wv[j] : (kb ? wv[j] & ((1u << (kb * 8)) - 1u) : 0u);
+		}
 		return make_uint4(wv[0], wv[1], wv[2], wv[3]);
 	};
 	const uint32_t end0 = K == 1 ? outEnd : cutImg;
-	const uint4 v0 = pull16(lane * 16, end0, end0 - 2);
-	uint4 v1 = make_uint4(0, 0, 0, 0);
-	if (K == 2) v1 = pull16(cutImg - 2 + lane * 16, outEnd, outEnd - cutImg);
+	uint4 v0 = reinterpret_cast<const uint4*>(out)[lane];
+	if (K == 2) v0 = tail_mask(v0, bp0, end0);
+	if (lane == 0) v0.x = (v0.x & 0xffff0000u) | (end0 - 2);
 	*(reinterpret_cast<uint4*>(A.pool + (size_t)C.phys * RB2_BLK) + lane) = v0;
-	if (K == 2) *(reinterpret_cast<uint4*>(A.pool + (size_t)newBase * RB2_BLK) + lane) = v1;
+	if (K == 2) { // second piece: image bytes [cutImg, outEnd) behind a fresh header
+		const uint32_t src = OUT_OFF + cutImg - 2 + bp0;
+		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.stage) + (src >> 2);
+		const uint32_t sh = (src & 3) * 8;
+		const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4];
+		uint4 v1 = make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh));
+		v1 = tail_mask(v1, cutImg - 2 + bp0, outEnd);
+		if (lane == 0) v1.x = (v1.x & 0xffff0000u) | (outEnd - cutImg);
+		*(reinterpret_cast<uint4*>(A.pool + (size_t)newBase * RB2_BLK) + lane) = v1;
+	}
 	if (lane == 0) { A.itemPieces[C.w] = K; A.itemFirst[C.w] = C.phys; A.itemRest[C.w] = newBase; }
 	return true;
 }
 
 // One warp per work item = (logical block, slice of <= RMAX of its records).
-__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
+__global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_blocks(MergeArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -955,7 +995,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_blocks(MergeArgs A)
 	C.phys = A.dir.order[C.i];
 	C.cumCntBlk = A.dir.cumCnt + (size_t)C.i * 6;
 	uint32_t err = 0;
-	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.runs, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own);
+	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.img, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own);
 	if (err && lane == 0) atomicOr(&A.ctl->err, err);
 
 	bool done = false;
@@ -1066,7 +1106,8 @@ struct rb2_engine {
 	DevBuf<uint8_t> sbuf, T, asym, recSym, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
 	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recCnt, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, scanCta;
-	DevBuf<int64_t> scanCta64;
+	DevBuf<int64_t> scanCta64, midTmp64;
+	DevBuf<uint32_t> midTmp;
 	unsigned long long *dMaxLen;
 	// stats
 	rb2_stats_t stats;
@@ -1104,15 +1145,27 @@ static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b -
 TraceT::TraceT(rb2_engine *e_, const char *n) : e(e_), name(n) { if (rb2_trace_on()) { cudaStreamSynchronize(e->st); t0 = std::chrono::steady_clock::now(); } }
 TraceT::~TraceT() { if (rb2_trace_on()) { cudaStreamSynchronize(e->st); double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); fprintf(stderr, "[trace] %-14s %9.1f us\n", name, us); } }
 
+// exclusive scan of rows[n][K] in place + grand totals; hierarchical above 4096 rows
+template <int K, typename T>
+static void run_mid(rb2_engine *e, T *rows, uint64_t n, T *grandDev, DevBuf<T> &tmp)
+{
+	if (n <= 4096) { LAUNCH(e, (scan_mid<K, T>), 1, 1024, 0, rows, n, grandDev); return; }
+	const uint32_t nChunk = cdiv(n, MID_ROWS);
+	tmp.need((size_t)nChunk * K + K);
+	LAUNCH(e, (mid_reduce<K, T>), nChunk, 256, 0, rows, n, tmp.p);
+	LAUNCH(e, (scan_mid<K, T>), 1, 1024, 0, tmp.p, (uint64_t)nChunk, grandDev);
+	LAUNCH(e, (mid_apply<K, T>), nChunk, 256, 0, rows, n, tmp.p);
+}
+
 // three-phase scan driver over n elements
 template <int K, typename T, class F>
-static void run_scan(rb2_engine *e, F f, uint64_t n, DevBuf<T> &cta, T *grandDev)
+static void run_scan(rb2_engine *e, F f, uint64_t n, DevBuf<T> &cta, T *grandDev, DevBuf<T> &tmp)
 {
 	if (n == 0) return;
 	uint32_t nCta = cdiv(n, SCAN_NT);
 	cta.need((size_t)nCta * K + K);
 	LAUNCH(e, (scan_reduce<K, T, F>), nCta, SCAN_NT, 0, f, n, cta.p);
-	LAUNCH(e, (scan_mid<K, T>), 1, 1024, 0, cta.p, (uint64_t)nCta, grandDev ? grandDev : cta.p + (size_t)nCta * K);
+	run_mid<K, T>(e, cta.p, nCta, grandDev ? grandDev : cta.p + (size_t)nCta * K, tmp);
 	LAUNCH(e, (scan_apply<K, T, F>), nCta, SCAN_NT, 0, f, n, cta.p);
 }
 
@@ -1132,7 +1185,7 @@ static void rebuild_directory(rb2_engine *e)
 {
 	Dir &d = e->dir[e->cur];
 	DirScan f = { d.order, e->blkCnt, e->nlog, d.cumLen, d.cumCnt };
-	run_scan<7, int64_t, DirScan>(e, f, e->nlog, e->scanCta64, (int64_t*)0);
+	run_scan<7, int64_t, DirScan>(e, f, e->nlog, e->scanCta64, (int64_t*)0, e->midTmp64);
 }
 
 // refresh host mirrors of per-bucket totals from the directory
@@ -1274,7 +1327,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recCnt.release(); e->recDst.release(); e->recHi.release();
 	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release();
-	e->scanCta.release(); e->scanCta64.release();
+	e->scanCta.release(); e->scanCta64.release(); e->midTmp.release(); e->midTmp64.release();
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
@@ -1318,7 +1371,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		Dir &dc = e->dir[e->cur];
 		LAUNCH(e, k_rec_hi, cdiv(e->nlog, 256), 256, 0, dc, e->nlog, e->dctl, e->recP.p, e->recHi.p);
 		ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemBlk.p, e->dctl };
-		run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0);
+		run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0, e->midTmp);
 		RB2_CUDA(cudaMemsetAsync(e->itemPieces.p, 0, maxItems * 4, e->st)); // 0 = not merged yet
 	}
 	ph_end(e, PH_DIR);
@@ -1337,7 +1390,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		// ---- new logical order ----------------------------------------------------------
 		if (attempt == 0) ph_begin(e, PH_DIR2);
 		RebuildScan rs = { e->dctl, e->dctl, e->nlog, dc.order, e->itemOff.p, e->itemPieces.p, e->itemFirst.p, e->itemRest.p, dnx.order };
-		run_scan<1, uint32_t, RebuildScan>(e, rs, e->nlog, e->scanCta, (uint32_t*)0);
+		run_scan<1, uint32_t, RebuildScan>(e, rs, e->nlog, e->scanCta, (uint32_t*)0, e->midTmp);
 		ctl_pull(e);
 		nItems = h->nItems;
 		if (!h->overflow) break;
@@ -1369,7 +1422,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	e->tileA.need((size_t)nT + 2);
 	LAUNCH(e, k_count_nul, nT, 256, 0, s, len, e->tileA.p);
 	uint32_t *dTot = e->tileA.p + nT; // grand total lands behind the tile array
-	LAUNCH(e, (scan_mid<1, uint32_t>), 1, 1024, 0, e->tileA.p, (uint64_t)nT, dTot);
+	run_mid<1, uint32_t>(e, e->tileA.p, (uint64_t)nT, dTot, e->midTmp);
 	uint32_t m = 0;
 	RB2_CUDA(cudaMemcpyAsync(&m, dTot, 4, cudaMemcpyDeviceToHost, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
@@ -1432,7 +1485,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
 		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
 		LAUNCH(e, k_member_fetch, nTile, 256, 0, e->T.p + (size_t)col * m, e->sid[cs].p, M, e->asym.p, e->tileB.p);
-		LAUNCH(e, (scan_mid<6, uint32_t>), 1, 1024, 0, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot);
+		run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 		ph_end(e, PH_MEMBERS);
 
 		// ---- groups: interval sizes, histograms, records ------------------------------
@@ -1445,7 +1498,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, e->dctl };
 		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 		else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
-		LAUNCH(e, (scan_mid<NGC, uint32_t>), 1, 1024, 0, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot);
+		run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
 		LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p);
 		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
 		else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
