@@ -134,7 +134,8 @@ __device__ __forceinline__ void decode_lane_simd(const uint4 &own, int lane, uin
 // img: RB2_IMG_BYTES of shared memory receiving the block image; cntScratch: 32 x 7 words.
 __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, uint8_t *img, uint32_t *cntScratch,
                                                   LaneDec &d, uint32_t &basePos, uint32_t (&baseCnt)[6],
-                                                  uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err, uint4 &own)
+                                                  uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err, uint4 &own,
+                                                  uint32_t *pureMask = 0)
 {
 	// plain (coherent) load: k_merge_blocks rewrites the same block in place later on
 	own = *(reinterpret_cast<const uint4*>(blk) + lane);
@@ -148,6 +149,7 @@ __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, 
 	if (lane == 0) any = (own.x & 0xffff0000u) | own.y | own.z | own.w;
 	const int lim = (int)nbytes + 2 - lane * 16;
 	const bool pure = (any & 0x80808080u) == 0 || lim <= 0;
+	if (pureMask) *pureMask = __ballot_sync(FULLMASK, pure);
 	if (pure) decode_lane_simd(own, lane, nbytes, d);
 	else decode_lane_serial(own, next0, lane, nbytes, cntScratch + lane * 7, d, err);
 	uint32_t incl = warp_incl_scan(d.len, lane);

@@ -642,7 +642,7 @@ struct ItemCtx {
 	int64_t blkStart;
 	const int64_t *cumCntBlk;
 	LaneDec d;
-	uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes;
+	uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes, pureMask;
 	uint4 own;
 };
 
@@ -776,12 +776,48 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 		uint32_t ca = F.laneBase[t * 7 + a];
 		const uint32_t nrt = F.laneNr[t];
 		uint32_t q = 0, nb;
-		bpq = t * 16 + F.laneFb[t];
-		for (;; ++q) { // run that contains symbol P-1 (the first run for P == 0)
-			parse_run(img, bpq, sym, len, nb);
-			if (pos + len >= P || q + 1 >= nrt) break;
-			ca += sym == a ? len : 0;
-			pos += len; bpq += nb;
+		if (((C.pureMask >> t) & 1u) && P > 0) {
+			// target lane holds only 1-byte runs: find the run with 4-byte SIMD steps.  Lengths are
+			// (byte >> 3); a multiply by 0x01010101 gives the inclusive prefix inside a word.
+			const uint4 tw = reinterpret_cast<const uint4*>(img)[t];
+			uint32_t w[4] = { tw.x, tw.y, tw.z, tw.w };
+			if (t == 0) w[0] &= 0xffff0000u;
+			const uint32_t prel = P - pos; // 1 .. symbols in the lane
+			const uint32_t tlo = a < 4 ? 1u << (8 * a) : 0u, thi = a >= 4 ? 1u << (8 * (a - 4)) : 0u;
+			uint32_t acc = 0, idx = 0;
+			bool found = false;
+#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t lens = (w[j] >> 3) & 0x0f0f0f0fu;
+				const uint32_t sy = w[j] & 0x07070707u;
+				const uint32_t tt = sy | (sy >> 4);
+				const uint32_t wt = __byte_perm(tlo, thi, (tt & 0xffu) | ((tt >> 8) & 0xff00u)); // 1 where symbol == a
+				const uint32_t wsum = __dp4a(lens, 0x01010101u, 0u);
+				if (!found) {
+					if (acc + wsum >= prel) {
+						const uint32_t pre = lens * 0x01010101u;
+						int i = 0;
+#pragma unroll
+						for (int x = 2; x >= 0; --x) if (acc + ((pre >> (8 * x)) & 0xffu) < prel) { i = x + 1; break; }
+						idx = 4 * j + i;
+						len = (lens >> (8 * i)) & 0xffu; sym = (sy >> (8 * i)) & 7u;
+						const uint32_t before = i ? (1u << (8 * i)) - 1u : 0u;
+						ca += __dp4a(lens & before, wt, 0u);
+						pos += acc + ((pre >> (8 * i)) & 0xffu) - len;
+						found = true;
+					} else { acc += wsum; ca += __dp4a(lens, wt, 0u); }
+				}
+			}
+			q = idx - F.laneFb[t];
+			bpq = t * 16 + idx;
+		} else {
+			bpq = t * 16 + F.laneFb[t];
+			for (;; ++q) { // run that contains symbol P-1 (the first run for P == 0)
+				parse_run(img, bpq, sym, len, nb);
+				if (pos + len >= P || q + 1 >= nrt) break;
+				ca += sym == a ? len : 0;
+				pos += len; bpq += nb;
+			}
 		}
 		off = P - pos;
 		const uint32_t dst = A.recDst[r];
@@ -995,7 +1031,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_blocks
 	C.phys = A.dir.order[C.i];
 	C.cumCntBlk = A.dir.cumCnt + (size_t)C.i * 6;
 	uint32_t err = 0;
-	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.img, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own);
+	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.img, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own, &C.pureMask);
 	if (err && lane == 0) atomicOr(&A.ctl->err, err);
 
 	bool done = false;
