@@ -174,14 +174,14 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from ropebwt2_b200.dist import Reducer, rank_info, shard_seed
+    rank, world, local = rank_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    red = Reducer(world, torch.device("cuda", local))
 
     from ropebwt2_b200 import Engine, MRope, load
     L = load()
@@ -193,7 +193,7 @@ def main():
     L.rb2_host_alloc.restype = C.c_void_p
     hptr = L.rb2_host_alloc(nbytes)
     host = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hptr))
-    fill_batch(host, n, ln, args.seed + 1000 * rank)
+    fill_batch(host, n, ln, shard_seed(args.seed, rank))
     eng = Engine(local, 1)
     dptr = eng.dev_alloc(nbytes)
     eng.dev_upload(dptr, host)
@@ -202,16 +202,10 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        red.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = red.max
 
     # ---- value leg: device-resident input ------------------------------------------------
     for _ in range(args.warmup):

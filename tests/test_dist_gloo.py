@@ -1,0 +1,68 @@
+"""CPU test of the N>1 host path: world_size-2 gloo process group, the same reductions bench.py uses
+to turn per-rank replica measurements into one whole-job number (sum of units / max of time), and the
+disjoint read shards."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ropebwt2_b200.dist import Reducer, rank_info, shard_seed, whole_job_throughput
+from ropebwt2_b200.synth import uniform_reads
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r, w, l = rank_info()
+        assert (r, w, l) == (rank, world, rank)
+        red = Reducer(w)
+        red.barrier()
+        # every rank "measures" a different time for the same amount of work
+        units, ms, thr = whole_job_throughput(1000.0, 10.0 * (rank + 1), red)
+        reads = uniform_reads(64, 20, shard_seed(7, r))
+        digest = float(np.frombuffer(reads.tobytes(), dtype=np.uint8).astype(np.int64).sum())
+        out.put((rank, units, ms, thr, red.max(digest), red.sum(digest), digest))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_reductions():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, units, ms, thr, dmax, dsum, digest in res:
+        assert units == 2000.0                 # units are summed over ranks
+        assert ms == 20.0                      # time is the max over ranks
+        assert abs(thr - 2000.0 / 0.020) < 1e-6
+    # shards differ between ranks (disjoint seeds) and the reductions saw both
+    assert res[0][6] != res[1][6]
+    assert res[0][5] == res[0][6] + res[1][6]
+    assert res[0][4] == max(res[0][6], res[1][6])
+
+
+def test_single_process_defaults():
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    assert rank_info() == (0, 1, 0)
+    red = Reducer(1)
+    assert whole_job_throughput(5.0, 2.0, red) == (5.0, 2.0, 2500.0)
