@@ -35,33 +35,56 @@ typedef struct {
 extern "C" {
 #endif
 
-/* max_nodes / block_len only shape the .fmr written by mr_dump (reference mrope.c:14-25) */
-mrope_t *mr_init(int max_nodes, int block_len, int sorting_order);
-void mr_destroy(mrope_t *r);
-int mr_thr_min(mrope_t *r, int thr_min);
-
-/* insert one string; str is the REVERSED string, NUL terminated (reference mrope.c:42-68) */
-int64_t mr_insert1(mrope_t *r, const uint8_t *str);
+/* ---- lifetime ------------------------------------------------------------------------------- */
 
 /*
- * insert a batch: s = len bytes, every string reversed and NUL terminated, concatenated;
- * s[len-1] must be NUL.  is_thr is accepted and ignored (the GPU is always used).
- * (reference mrope.c:258-345)
+ * mr_init: an empty index of six buckets on CUDA device $RB2_DEVICE (else $LOCAL_RANK, else 0).
+ * sorting_order is one of MR_SO_*; anything else aborts (reference mrope.c:14-25).  max_nodes and
+ * block_len only shape the .fmr written by mr_dump -- the device leaf size is fixed at 512 bytes.
+ */
+mrope_t *mr_init(int max_nodes, int block_len, int sorting_order);
+
+/* mr_destroy: releases the engine and the bucket handles that a freeing iteration left (mrope.c:27-33) */
+void mr_destroy(mrope_t *r);
+
+/* mr_thr_min: stored and returned like the reference does (mrope.c:35-40); no effect on the GPU path */
+int mr_thr_min(mrope_t *r, int thr_min);
+
+/* ---- insertion ------------------------------------------------------------------------------ */
+
+/*
+ * mr_insert_multi: the hot path (reference mrope.c:258-345).  s holds len bytes of nt6 codes, every
+ * string REVERSED and NUL terminated, strings concatenated, s[len-1] == 0 (violations abort, as the
+ * reference asserts).  The buffer is only read and may be reused on return.  is_thr is accepted for
+ * compatibility; the GPU is always used.
  */
 void mr_insert_multi(mrope_t *mr, int64_t len, const uint8_t *s, int is_thr);
 
-/* whole-index rank over the concatenated buckets (reference mrope.c:70-105) */
+/*
+ * mr_insert1: one REVERSED, NUL-terminated string (reference mrope.c:42-68), served by the same
+ * kernels as a one-string batch.  Returns the rank of the string's sentinel inside its bucket.
+ */
+int64_t mr_insert1(mrope_t *r, const uint8_t *str);
+
+/* ---- queries and traversal ---------------------------------------------------------------- */
+
+/* mr_rank2a: symbol counts in BWT[0,x) and BWT[0,y) over the concatenated buckets (mrope.c:70-105) */
 void mr_rank2a(const mrope_t *mr, int64_t x, int64_t y, int64_t *cx, int64_t *cy);
 #define mr_rank1a(mr, x, cx) mr_rank2a(mr, x, -1, cx, 0)
 
-/* walk the leaf blocks, buckets 0..5, left to right; decode with rle_dec1 (rle.h).
- * to_free: release each bucket's host handle once it has been walked (reference mrope.c:111-130) */
+/*
+ * Block iterator (reference mrope.c:111-130): buckets 0..5, leaves left to right.  Each block is
+ * [uint16 nbytes][runs] -- decode with rle_dec1 from rle.h.  With to_free != 0 a bucket's host
+ * handle is released once it has been walked (mr->r[a] becomes NULL), as in the reference.
+ */
 void mr_itr_first(mrope_t *r, mritr_t *i, int to_free);
 const uint8_t *mr_itr_next_block(mritr_t *i);
 
-void mr_print_tree(const mrope_t *mr);
-void mr_dump(mrope_t *mr, FILE *fp);   /* .fmr ("RB\2") writer, readable by the reference's -i */
-mrope_t *mr_restore(FILE *fp);         /* .fmr reader, accepts files written by the reference's -b */
+/* ---- persistence ----------------------------------------------------------------------------- */
+
+void mr_dump(mrope_t *mr, FILE *fp);   /* .fmr ("RB\2") writer; the reference's -i reads it */
+mrope_t *mr_restore(FILE *fp);         /* .fmr reader; accepts files written by the reference's -b */
+void mr_print_tree(const mrope_t *mr); /* Newick-style debug print of the tree mr_dump would write */
 
 #ifdef __cplusplus
 }

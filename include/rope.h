@@ -18,21 +18,28 @@
 #define ROPE_DEF_MAX_NODES 64
 #define ROPE_DEF_BLOCK_LEN 512
 
-/* kept for layout compatibility (reference rope.h:11-15); the engine has no tree nodes */
+/*
+ * Layout-compatibility types.  Nothing in this library walks a tree: the three structs below keep
+ * the reference's field order and sizes only because callers allocate them (iterators live on the
+ * caller's stack) or read them directly (mr_get_c reads rope_t::c).
+ */
+
+/* one B+-tree entry in the reference (rope.h:11-15): 8-byte pointer, 64-bit packed word, six counts */
 typedef struct rpnode_s {
 	struct rpnode_s *p;
 	uint64_t l:54, n:9, is_bottom:1;
 	int64_t c[6];
 } rpnode_t;
 
+/* per-bucket handle; byte offsets: 0 max_nodes, 4 block_len, 8 c[6], 56 root, 64 node, 72 leaf */
 typedef struct {
-	int32_t max_nodes, block_len; /* recorded for .fmr output; the device leaf size is fixed at 512 */
-	int64_t c[6];                 /* marginal symbol counts, always current (reference rope.h:19) */
-	rpnode_t *root;               /* unused (NULL) */
-	void *node, *leaf;            /* node: private handle of this library; leaf: unused */
+	int32_t max_nodes, block_len; /* recorded for .fmr output only; device leaves are always 512 bytes */
+	int64_t c[6];                 /* marginal symbol counts of the bucket, refreshed after every mutating call */
+	rpnode_t *root;               /* always NULL here */
+	void *node, *leaf;            /* node: private engine handle; leaf: bucket number */
 } rope_t;
 
-/* iterator state; same size as the reference's (rope.h:24-29) because callers allocate it */
+/* iterator cursor; the library stores its own state in pa[] (the struct is caller-allocated) */
 typedef struct {
 	const rope_t *rope;
 	const rpnode_t *pa[ROPE_MAX_DEPTH];
@@ -40,7 +47,7 @@ typedef struct {
 	int d;
 } rpitr_t;
 
-/* accepted and ignored: the reference uses it to resume leaf scans (rope.h:31-35) */
+/* leaf-scan resume state of the reference (rope.h:31-35); accepted by rope_insert_run and ignored */
 typedef struct {
 	int beg;
 	int64_t bc[6];
@@ -51,20 +58,38 @@ typedef struct {
 extern "C" {
 #endif
 
+/*
+ * Lifetime.  rope_init creates a private engine (CUDA device $RB2_DEVICE / $LOCAL_RANK / 0) whose
+ * bucket 0 backs the rope; rope_destroy releases it.  Ropes that belong to an mrope_t are created
+ * and destroyed by mr_init / mr_destroy.
+ */
 rope_t *rope_init(int max_nodes, int block_len);
 void rope_destroy(rope_t *rope);
-/* insert rl copies of symbol a behind the first x symbols; returns rank(a, x) before the insertion (reference rope.c:114-148) */
+
+/*
+ * rope_insert_run: put `rl` copies of symbol `a` behind the first `x` symbols and return
+ * rank(a, x) as it was before the insertion (reference rope.c:114-148).  One record through the
+ * merge kernels; meant for API completeness, not throughput -- batches go through mr_insert_multi.
+ */
 int64_t rope_insert_run(rope_t *rope, int64_t x, int a, int64_t rl, rpcache_t *cache);
-/* cx[a] = #a in [0,x), cy[a] = #a in [0,y); y < x or cy == NULL: only cx (reference rope.c:179-194) */
+
+/*
+ * rope_rank2a: cx[s] = number of s in [0,x), cy[s] = number of s in [0,y).  With y < x or
+ * cy == NULL only cx is produced (reference rope.c:179-194).
+ */
 void rope_rank2a(const rope_t *rope, int64_t x, int64_t y, int64_t *cx, int64_t *cy);
 #define rope_rank1a(rope, x, cx) rope_rank2a(rope, x, -1, cx, 0)
 
+/* leaf blocks left to right; each returned pointer is valid until the next call (reference rope.c:200-219) */
 void rope_itr_first(const rope_t *rope, rpitr_t *i);
 const uint8_t *rope_itr_next_block(rpitr_t *i);
 
-void rope_print_node(const rpnode_t *p); /* no tree nodes exist: prints nothing; use mr_print_tree */
+/* one rope's share of a .fmr file: int32 max_nodes, int32 block_len, nodes in pre-order (reference rope.c:253-318) */
 void rope_dump(const rope_t *r, FILE *fp);
 rope_t *rope_restore(FILE *fp);
+
+/* there are no tree nodes to print: a no-op kept for link compatibility; see mr_print_tree */
+void rope_print_node(const rpnode_t *p);
 
 #ifdef __cplusplus
 }

@@ -44,9 +44,9 @@ typedef struct {
 	int64_t n_strings, n_symbols;       /* inserted strings / symbols (sentinels included) */
 	int64_t n_columns;                  /* BCR columns executed */
 	int64_t n_launches;                 /* kernels launched by this library */
-	int64_t n_merge_launches;           /* launches of the dominant kernel (k_merge_blocks) */
-	int64_t merge_blocks;               /* leaf blocks read by k_merge_blocks, all launches */
-	int64_t merge_bytes_rw;             /* algorithmic HBM bytes of k_merge_blocks: blocks read + written, x512 */
+	int64_t n_merge_launches;           /* launches of the dominant kernel (k_merge_fast) */
+	int64_t merge_blocks;               /* work items (leaf blocks read) of the merge kernels, all launches */
+	int64_t merge_bytes_rw;             /* algorithmic HBM bytes of the merge kernels: blocks read + written, x512 */
 	int64_t n_records;                  /* (position, symbol, count) insertion records merged */
 	int64_t pool_blocks, pool_capacity; /* leaf blocks in use / allocated */
 	double  ms_total;                   /* device time of whole rb2_insert_multi* calls (CUDA events) */
@@ -54,8 +54,10 @@ typedef struct {
 	double  ms_transpose;               /* string split + column-major transpose */
 	double  ms_members;                 /* symbol fetch, radix partition of the string set */
 	double  ms_groups;                  /* group scan, record emission, rank pre-pass */
-	double  ms_merge;                   /* k_merge_blocks only */
+	double  ms_merge;                   /* k_merge_fast (the dominant kernel) */
 	double  ms_directory;               /* item planning + directory rebuild */
+	double  ms_merge_general;           /* k_merge_general: over-full / multi-item / empty blocks */
+	int64_t general_items;              /* work items that went through k_merge_general */
 } rb2_stats_t;
 
 int  rb2_device_count(void);

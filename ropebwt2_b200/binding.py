@@ -28,7 +28,8 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_destroy", "rb2_sorting_ord
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_strings", "n_symbols", "n_columns", "n_launches", "n_merge_launches",
                                          "merge_blocks", "merge_bytes_rw", "n_records", "pool_blocks", "pool_capacity")] + \
-               [(n, C.c_double) for n in ("ms_total", "ms_h2d", "ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_directory")]
+               [(n, C.c_double) for n in ("ms_total", "ms_h2d", "ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_directory",
+                                          "ms_merge_general")] + [("general_items", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -137,7 +137,7 @@ __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, 
                                                   uint32_t &blkLen, uint32_t (&blkCnt)[6], uint32_t &nbytes, uint32_t &err, uint4 &own,
                                                   uint32_t *pureMask = 0)
 {
-	// plain (coherent) load: k_merge_blocks rewrites the same block in place later on
+	// plain (coherent) load: the merge kernels rewrite the same block in place later on
 	own = *(reinterpret_cast<const uint4*>(blk) + lane);
 	reinterpret_cast<uint4*>(img)[lane] = own;
 	if (lane == 0) reinterpret_cast<uint4*>(img)[32] = make_uint4(0, 0, 0, 0);

@@ -18,7 +18,7 @@
 //      groups  : per-group symbol histogram -> one insertion RECORD per   (mrope.c:191-224)
 //                (group, symbol) in $,A,C,G,T,N / $,T,G,C,A,N order; every record with a
 //                symbol != $ is also the next column's group
-//      blocks  : k_merge_blocks: one warp per touched leaf block decodes it, merges its
+//      blocks  : k_merge_fast / k_merge_general: one warp per touched leaf block decodes it, merges its
 //                records into the run stream, re-encodes, splits overfull blocks, and returns
 //                rank(a, position) for every record = the next interval start (rope.c:114-148)
 //      directory rebuild (prefix sums).
@@ -38,7 +38,7 @@
 #define MERGE_WARPS 4
 #endif
 #ifndef MERGE_MINCTA
-#define MERGE_MINCTA 8
+#define MERGE_MINCTA 12
 #endif
 #define NONE32      0xffffffffu
 #define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
@@ -46,7 +46,8 @@
 
 struct Ctl { // device control block (one per engine), mirrored through pinned host memory
 	uint32_t poolUsed, err, nItems, nlogNew;
-	uint32_t overflow, failBase, pad0, pad1; // pool exhausted during k_merge_blocks: first block id that did not fit
+	uint32_t overflow, failBase;   // pool exhausted during a merge kernel: first block id that did not fit
+	uint32_t nTodo, todoNext;     // items the fast kernel left for k_merge_general, and its work counter
 	uint32_t blkBkt[8];     // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
 	uint32_t blkBktNew[8];
 	uint32_t gBkt[8], mBkt[8];         // this column: group / member index range per bucket
@@ -534,6 +535,7 @@ struct MergeArgs {
 	const int64_t *recP; const uint8_t *recSym; const uint32_t *recCnt, *recDst;
 	int64_t *gLNext;
 	uint32_t *itemPieces, *itemFirst, *itemRest;
+	uint32_t *todo;   // items left for k_merge_general
 	Ctl *ctl;
 };
 
@@ -554,10 +556,16 @@ struct FastScratch {                // edit-based fast path
 };
 #define OUT_OFF  0     // fast path: the output block image is assembled at stage[0, 1024)
 #define EBUF_OFF 1536  // fast path: replacement bytes of the edits, 16 per record, at stage[1536, 2048)
-struct alignas(16) MergeSmem {
+#define FAST_STAGE 2048
+struct alignas(16) FastSmem {       // per warp, k_merge_fast
 	uint8_t  img[RB2_IMG_BYTES];    // the input block, byte-addressable (+16 zero bytes)
-	uint8_t  stage[STAGE_BYTES];    // general: output run bytes; fast: output image + replacement bytes
-	union { GenScratch g; FastScratch f; } u;
+	uint8_t  stage[FAST_STAGE];     // output image + replacement bytes
+	FastScratch f;
+};
+struct alignas(16) GenSmem {        // per warp, k_merge_general
+	uint8_t  img[RB2_IMG_BYTES];
+	uint8_t  stage[STAGE_BYTES];    // output run bytes
+	GenScratch g;
 };
 
 // Sequential merge of one lane's old runs with the records that fall into them.
@@ -660,9 +668,9 @@ __device__ __forceinline__ uint32_t alloc_blocks(const MergeArgs &A, int lane, u
 }
 
 // ---- general path: any number of records, sub-items, empty blocks ---------------------------
-__device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, int lane, const ItemCtx &C)
+__device__ __forceinline__ void merge_general(const MergeArgs &A, GenSmem &S, int lane, const ItemCtx &C)
 {
-	GenScratch &G = S.u.g;
+	GenScratch &G = S.g;
 	const uint32_t r0 = C.r0, r1 = C.r1;
 	const int64_t blkStart = C.blkStart;
 	// the slice of old symbols this item re-emits: [posLo, posHi) relative to the block start
@@ -747,9 +755,9 @@ __device__ __forceinline__ void merge_general(const MergeArgs &A, MergeSmem &S, 
 // lane stores its 16 input bytes at their shifted position (bytes inside an edited span are
 // dropped), the group heads store their replacement bytes, then each lane reads back 16 aligned
 // bytes.  Returns false (no side effects besides idempotent rank writes) if it cannot place a split.
-__device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int lane, const ItemCtx &C)
+__device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int lane, const ItemCtx &C)
 {
-	FastScratch &F = S.u.f;
+	FastScratch &F = S.f;
 	const uint8_t *img = S.img;
 	const uint32_t nrec = C.r1 - C.r0, nbytes = C.nbytes, endBp = 2 + nbytes;
 	F.laneEnd[lane] = C.basePos + C.d.len;
@@ -1010,17 +1018,9 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, MergeSmem &S, int
 	return true;
 }
 
-// One warp per work item = (logical block, slice of <= RMAX of its records).
-__global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_blocks(MergeArgs A)
+// Common prologue of both merge kernels: which block, which records, decode the block.
+__device__ __forceinline__ void item_prologue(const MergeArgs &A, ItemCtx &C, int lane, uint8_t *img, uint32_t *cntScratch)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	ItemCtx C;
-	C.w = blockIdx.x * MERGE_WARPS + wid;
-	if (C.w >= A.ctl->nItems) return;
-	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
-	MergeSmem &S = reinterpret_cast<MergeSmem*>(smraw)[wid];
-
 	C.i = A.itemBlk[C.w];
 	const uint32_t it0 = A.itemOff[C.i];
 	C.nIt = A.itemOff[C.i + 1] - it0; C.sub = C.w - it0;
@@ -1031,12 +1031,51 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_blocks
 	C.phys = A.dir.order[C.i];
 	C.cumCntBlk = A.dir.cumCnt + (size_t)C.i * 6;
 	uint32_t err = 0;
-	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, S.img, S.u.g.lcnt, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own, &C.pureMask);
+	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, img, cntScratch, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own, &C.pureMask);
 	if (err && lane == 0) atomicOr(&A.ctl->err, err);
+}
 
+// One warp per work item = (logical block, slice of <= RMAX of its records).  Items the fast path
+// cannot take (several items per block, > 32 records, empty block, unplaceable split) are queued
+// for k_merge_general.
+__global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(MergeArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	ItemCtx C;
+	C.w = blockIdx.x * MERGE_WARPS + wid;
+	if (C.w >= A.ctl->nItems) return;
+	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
+	FastSmem &S = reinterpret_cast<FastSmem*>(smraw)[wid];
+	// eligibility is known before touching the block
+	const uint32_t i = A.itemBlk[C.w];
+	const uint32_t nIt = A.itemOff[i + 1] - A.itemOff[i];
 	bool done = false;
-	if (C.nIt == 1 && C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C);
-	if (!done) merge_general(A, S, lane, C);
+	if (nIt == 1) {
+		item_prologue(A, C, lane, S.img, S.f.laneBase);
+		if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C);
+	}
+	if (!done && lane == 0) A.todo[atomicAdd(&A.ctl->nTodo, 1u)] = C.w;
+}
+
+// Persistent kernel: warps pull queued items until the queue is empty.
+__global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_general(MergeArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	GenSmem &S = reinterpret_cast<GenSmem*>(smraw)[wid];
+	const uint32_t nTodo = A.ctl->nTodo;
+	for (;;) {
+		uint32_t k = 0;
+		if (lane == 0) k = atomicAdd(&A.ctl->todoNext, 1u);
+		k = __shfl_sync(FULLMASK, k, 0);
+		if (k >= nTodo) break;
+		ItemCtx C;
+		C.w = A.todo[k];
+		item_prologue(A, C, lane, S.img, S.g.lcnt);
+		merge_general(A, S, lane, C);
+		__syncwarp();
+	}
 }
 
 struct RebuildScan { // K=1: pieces per old logical block -> new logical order
@@ -1126,10 +1165,10 @@ template <typename T> struct DevBuf {
 	void release() { if (p) RB2_CUDA(cudaFree(p)); p = 0; cap = 0; }
 };
 
-enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_N };
+enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_MERGE2, PH_N };
 
 struct rb2_engine {
-	int dev, so;
+	int dev, so, nSM;
 	cudaStream_t st;
 	// leaf block pool + directory
 	uint8_t *pool; uint32_t *blkCnt; uint32_t poolCap;
@@ -1141,7 +1180,7 @@ struct rb2_engine {
 	// batch scratch
 	DevBuf<uint8_t> sbuf, T, asym, recSym, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
-	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recCnt, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, scanCta;
+	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recCnt, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, todo, scanCta;
 	DevBuf<int64_t> scanCta64, midTmp64;
 	DevBuf<uint32_t> midTmp;
 	unsigned long long *dMaxLen;
@@ -1281,7 +1320,7 @@ static void reserve_blocks(rb2_engine *e, uint64_t blocks)
 
 static void reserve_items(rb2_engine *e, uint64_t n)
 {
-	e->itemBlk.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n);
+	e->itemBlk.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n); e->todo.need(n);
 }
 
 extern "C" int rb2_device_count(void)
@@ -1312,7 +1351,9 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	for (int k = 0; k < 2; ++k) RB2_CUDA(cudaEventCreate(&e->evTot[k]));
 	e->pool = 0; e->blkCnt = 0; e->poolCap = 0;
 	memset(e->dir, 0, sizeof(e->dir)); e->cur = 0;
-	RB2_CUDA(cudaFuncSetAttribute(k_merge_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(MergeSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
+	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
@@ -1362,7 +1403,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recCnt.release(); e->recDst.release(); e->recHi.release();
-	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release();
+	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release();
 	e->scanCta.release(); e->scanCta64.release(); e->midTmp.release(); e->midTmp64.release();
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
@@ -1380,7 +1421,7 @@ static inline void ph_end(rb2_engine *e, int p) { RB2_CUDA(cudaEventRecord(e->ev
 static void ph_collect(rb2_engine *e, uint32_t mask)
 {
 	double *acc[PH_N] = { &e->stats.ms_h2d, &e->stats.ms_transpose, &e->stats.ms_members, &e->stats.ms_groups, &e->stats.ms_merge,
-	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members };
+	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members, &e->stats.ms_merge_general };
 	for (int p = 0; p < PH_N; ++p) if (mask >> p & 1) {
 		float ms = 0;
 		RB2_CUDA(cudaEventElapsedTime(&ms, e->ev[p][0], e->ev[p][1]));
@@ -1419,9 +1460,11 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		if (attempt == 0) ph_begin(e, PH_MERGE);
 		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
 		                 e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, gLNext,
-		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->dctl };
-		LAUNCH(e, k_merge_blocks, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(MergeSmem), ma);
-		if (attempt == 0) ph_end(e, PH_MERGE);
+		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->todo.p, e->dctl };
+		LAUNCH(e, k_merge_fast, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(FastSmem), ma);
+		if (attempt == 0) { ph_end(e, PH_MERGE); ph_begin(e, PH_MERGE2); }
+		LAUNCH(e, k_merge_general, e->nSM * 10, MERGE_WARPS * 32, MERGE_WARPS * sizeof(GenSmem), ma);
+		if (attempt == 0) ph_end(e, PH_MERGE2);
 		++e->stats.n_merge_launches;
 		// ---- new logical order ----------------------------------------------------------
 		if (attempt == 0) ph_begin(e, PH_DIR2);
@@ -1432,7 +1475,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		if (!h->overflow) break;
 		// pool ran out: the items that did not fit are untouched.  Grow and run them again.
 		if (attempt > 8) RB2_FATAL("block pool growth did not converge");
-		h->poolUsed = h->failBase; h->overflow = 0; h->failBase = NONE32;
+		h->poolUsed = h->failBase; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
 		reserve_blocks(e, (uint64_t)e->poolCap + e->poolCap / 2 + maxItems / 4 + 4096);
 		ctl_push(e);
 	}
@@ -1442,7 +1485,8 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 	rebuild_directory(e);
 	ph_end(e, PH_DIR2);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
-	ph_collect(e, (1u << PH_MERGE) | (1u << PH_DIR) | (1u << PH_DIR2));
+	ph_collect(e, (1u << PH_MERGE) | (1u << PH_MERGE2) | (1u << PH_DIR) | (1u << PH_DIR2));
+	e->stats.general_items += h->nTodo;
 	e->stats.merge_blocks += nItems;
 	// every item reads one leaf block and writes it back, plus the freshly allocated pieces
 	e->stats.merge_bytes_rw += ((int64_t)nItems * 2 + (int64_t)(h->poolUsed - usedBefore)) * RB2_BLK;
@@ -1512,7 +1556,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			for (int b = 0; b < 6; ++b) { h->cpost[b] = acc; acc += e->bktLen[b] + (mBkt[b + 1] - mBkt[b]); }
 			h->cpost[6] = h->cpost[7] = acc;
 		}
-		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32;
+		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
 		ctl_push(e);
 
 		// ---- members: next symbol + tile histograms ---------------------------------
@@ -1748,7 +1792,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	RB2_CUDA(cudaMemcpyAsync(e->recDst.p, D.data(), k * 4, cudaMemcpyHostToDevice, e->st));
 	Ctl *h = e->hctl;
 	for (int b = 0; b < 8; ++b) { h->blkBkt[b] = e->blkBkt[b]; h->recBkt[b] = b <= bucket ? 0 : k; h->cpost[b] = 0; }
-	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32;
+	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
 	ctl_push(e);
 	reserve_items(e, (uint64_t)k + 2);
 	apply_records(e, k, e->dRankOut);
