@@ -271,7 +271,7 @@ def main():
     traffic = None
     ncu_json = os.path.join(ROOT, "profiles", "merge_traffic.json")
     if os.path.exists(ncu_json):
-        traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")
+        traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")  # one late launch (column 90) at this workload size
     value = world * bp * args.steps / (ms_value * 1e-3) / 1e9
     e2e_val = world * bp * args.steps / (ms_e2e * 1e-3) / 1e9
     out = {

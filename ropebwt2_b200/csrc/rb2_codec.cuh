@@ -48,43 +48,41 @@ __device__ __forceinline__ void parse_run(const uint8_t *img, uint32_t bp, uint3
 	}
 }
 
-// byte i (0..19) of the 20-byte window {own 16 bytes, first word of the next lane}
-__device__ __forceinline__ uint32_t win_byte(const uint32_t (&W)[5], int i)
+// Run-serial accounting of one lane (any mix of 1/2/4-byte runs), parsed from the shared-memory
+// image.  Deliberately a rolled loop: it is the cold path for short-run data and must not bloat the
+// instruction footprint of the kernels that inline it.  `lcs` = 6 lane-private shared-memory words
+// (indexing registers by a run-time symbol would cost a 6-way select per run).
+__device__ __noinline__ uint64_t decode_lane_serial(const uint8_t *img, int lane, uint32_t nbytes, uint32_t *lcs)
 {
-	return (W[i >> 2] >> ((i & 3) * 8)) & 0xffu;
-}
-
-// Byte-serial accounting of one lane (any mix of 1/2/4-byte runs).  `lcs` = 6 lane-private
-// shared-memory words (indexing registers by a run-time symbol would cost a 6-way select per run).
-__device__ __forceinline__ void decode_lane_serial(const uint4 &own, uint32_t next0, int lane, uint32_t nbytes,
-                                                   uint32_t *lcs, LaneDec &d, uint32_t &err)
-{
-	const uint32_t W[5] = { own.x, own.y, own.z, own.w, next0 };
-	uint32_t nr = 0, tot = 0, fb = 16;
+	// returns nr | fb << 8 | err << 16 | (uint64)len << 32; per-symbol counts are left in lcs[0..5]
 	const int lim = (int)nbytes + 2 - lane * 16; // byte i of this lane is a run byte iff i < lim (and i >= 2 in lane 0)
+	const uint32_t hi = lim > 16 ? 16u : (lim < 0 ? 0u : (uint32_t)lim), base = lane * 16;
+	uint32_t i = lane == 0 ? 2u : 0u, nr = 0, tot = 0, err = 0;
 #pragma unroll
 	for (int a = 0; a < 6; ++a) lcs[a] = 0;
-#pragma unroll
-	for (int i = 0; i < 16; ++i) {
-		const uint32_t b = win_byte(W, i);
-		const bool start = (i >= 2 || lane > 0) && i < lim && (b & 0xC0u) != 0x80u;
-		if (start) {
-			uint32_t l;
-			if (b < 0x80u) l = b >> 3;
-			else if (b < 0xE0u) l = ((b & 0x18u) << 3) | (win_byte(W, i + 1) & 0x3fu);
-			else {
-				if (b >= 0xF0u) err |= RB2_ERR_RUN8;
-				l = ((b & 0x08u) << 15) | ((win_byte(W, i + 1) & 0x3fu) << 12)
-				  | ((win_byte(W, i + 2) & 0x3fu) << 6) | (win_byte(W, i + 3) & 0x3fu);
-			}
-			if (nr == 0) fb = i;
-			++nr; tot += l;
-			lcs[b & 7u] += l;
-		}
+	while (i < hi && (img[base + i] & 0xC0u) == 0x80u) ++i; // tail of a run that started in the previous lane
+	const uint32_t fb = i < hi ? i : 16u;
+#pragma unroll 1
+	while (i < hi) {
+		uint32_t s, l, nb;
+		parse_run(img, base + i, s, l, nb);
+		if (img[base + i] >= 0xF0u) err = RB2_ERR_RUN8;
+		++nr; tot += l; lcs[s] += l;
+		i += nb;
 	}
-	d.nr = nr; d.len = tot; d.fb = fb;
-#pragma unroll
-	for (int a = 0; a < 6; ++a) d.c[a] = lcs[a];
+	return (uint64_t)nr | (uint64_t)fb << 8 | (uint64_t)err << 16 | (uint64_t)tot << 32;
+}
+
+// exclusive scans of six per-lane counts that do not fit 16 bits (blocks with very long runs): cold.
+// lcs (lane-private shared-memory slice): in = the lane's counts, out = their exclusive prefixes.
+__device__ __noinline__ void wide_count_scans(int lane, uint32_t *lcs)
+{
+#pragma unroll 1
+	for (int a = 0; a < 6; ++a) {
+		const uint32_t c = lcs[a];
+		lcs[a] = warp_incl_scan(c, lane) - c;
+	}
+	__syncwarp();
 }
 
 // SIMD accounting of a lane whose run bytes are all 1-byte runs (every byte < 0x80; bytes behind
@@ -142,8 +140,7 @@ __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, 
 	reinterpret_cast<uint4*>(img)[lane] = own;
 	if (lane == 0) reinterpret_cast<uint4*>(img)[32] = make_uint4(0, 0, 0, 0);
 	nbytes = __shfl_sync(FULLMASK, own.x, 0) & 0xffffu;
-	uint32_t next0 = __shfl_down_sync(FULLMASK, own.x, 1);
-	if (lane == 31) next0 = 0;
+	__syncwarp(); // the image is complete: serial lanes read runs that reach into the next lane
 	// a lane is "pure" if none of its run bytes has the top bit set (no multi-byte run touches it)
 	uint32_t any = own.x | own.y | own.z | own.w;
 	if (lane == 0) any = (own.x & 0xffff0000u) | own.y | own.z | own.w;
@@ -151,7 +148,13 @@ __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, 
 	const bool pure = (any & 0x80808080u) == 0 || lim <= 0;
 	if (pureMask) *pureMask = __ballot_sync(FULLMASK, pure);
 	if (pure) decode_lane_simd(own, lane, nbytes, d);
-	else decode_lane_serial(own, next0, lane, nbytes, cntScratch + lane * 7, d, err);
+	else {
+		uint32_t *lcs = cntScratch + lane * 7;
+		const uint64_t r = decode_lane_serial(img, lane, nbytes, lcs);
+		d.nr = (uint32_t)r & 0xffu; d.fb = ((uint32_t)r >> 8) & 0xffu; err |= ((uint32_t)r >> 16) & 0xffu; d.len = (uint32_t)(r >> 32);
+#pragma unroll
+		for (int a = 0; a < 6; ++a) d.c[a] = lcs[a];
+	}
 	uint32_t incl = warp_incl_scan(d.len, lane);
 	basePos = incl - d.len;
 	blkLen = __shfl_sync(FULLMASK, incl, 31);
@@ -165,12 +168,16 @@ __device__ __forceinline__ void warp_decode_block(const uint8_t *blk, int lane, 
 			blkCnt[a] = t & 0xffffu; blkCnt[a + 1] = t >> 16;
 		}
 	} else {
+		uint32_t *lcs = cntScratch + lane * 7;
+		__syncwarp();
 #pragma unroll
-		for (int a = 0; a < 6; ++a) {
-			uint32_t x = warp_incl_scan(d.c[a], lane);
-			baseCnt[a] = x - d.c[a];
-			blkCnt[a] = __shfl_sync(FULLMASK, x, 31);
-		}
+		for (int a = 0; a < 6; ++a) lcs[a] = d.c[a];
+		wide_count_scans(lane, lcs);
+#pragma unroll
+		for (int a = 0; a < 6; ++a) { baseCnt[a] = lcs[a]; }
+		__syncwarp();
+#pragma unroll
+		for (int a = 0; a < 6; ++a) blkCnt[a] = cntScratch[31 * 7 + a] + __shfl_sync(FULLMASK, d.c[a], 31);
 	}
 	__syncwarp();
 }

@@ -38,7 +38,7 @@
 #define MERGE_WARPS 4
 #endif
 #ifndef MERGE_MINCTA
-#define MERGE_MINCTA 12
+#define MERGE_MINCTA 10
 #endif
 #define NONE32      0xffffffffu
 #define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
@@ -366,7 +366,7 @@ struct GroupArgs {
 	uint32_t G;
 	uint32_t *ctaTot;        // [nCta][NGC]: totals (MODE 0) / exclusive prefix (MODE 1)
 	int64_t *gSizeNext; uint32_t *gOffNext;
-	int64_t *recP; uint8_t *recSym; uint32_t *recCnt, *recDst;
+	int64_t *recP; uint32_t *recSC, *recDst; // recSC = count << 3 | symbol
 	Ctl *ctl;
 };
 
@@ -375,10 +375,30 @@ template <int MODE, bool COMP>
 __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 {
 	__shared__ uint32_t sm[NGC * 8];
+	__shared__ uint64_t sm64[3 * 8];
+	__shared__ uint32_t sCtl[24]; // [0,8) gBktNext, [8,16) mBktNext, [16,22) bucket starts inside this CTA, [22] any, [23] member base
 	const int lane = threadIdx.x & 31;
-	const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+	const uint32_t g0 = blockIdx.x * 256, g = g0 + threadIdx.x;
 	const bool valid = g < A.G;
-	const uint32_t S = valid ? A.gOff[g] : 0, E = valid ? A.gOff[g + 1] : 0, cnt = E - S;
+	const uint32_t nv = A.G - g0 < 256 ? A.G - g0 : 256;
+	if (threadIdx.x == 0) {
+		const uint32_t mb = A.gOff[g0];
+		sCtl[23] = mb;
+		sCtl[22] = A.gOff[g0 + nv] - mb == nv; // every group of this CTA is a singleton
+	}
+	if (MODE == 1) {
+		if (threadIdx.x < 8) { sCtl[threadIdx.x] = A.ctl->gBktNext[threadIdx.x]; sCtl[8 + threadIdx.x] = A.ctl->mBktNext[threadIdx.x]; }
+		if (threadIdx.x >= 32 && threadIdx.x < 38) {
+			const uint32_t gb = A.ctl->gBkt[threadIdx.x - 32];
+			sCtl[16 + threadIdx.x - 32] = gb >= g0 && gb < g0 + 256 ? gb : NONE32;
+		}
+	}
+	__syncthreads();
+	const bool allSingle = sCtl[22] != 0;
+	uint32_t S, E;
+	if (allSingle) { S = sCtl[23] + threadIdx.x; E = S + (valid ? 1 : 0); }
+	else { S = valid ? A.gOff[g] : 0; E = valid ? A.gOff[g + 1] : 0; }
+	const uint32_t cnt = E - S;
 	uint32_t h[6] = { 0, 0, 0, 0, 0, 0 };
 	if (valid && cnt <= SMALL_GROUP) {
 		for (uint32_t k = S; k < E; ++k) {
@@ -387,7 +407,7 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 			for (int a = 0; a < 6; ++a) h[a] += s == a;
 		}
 	}
-	uint32_t big = __ballot_sync(FULLMASK, valid && cnt > SMALL_GROUP);
+	uint32_t big = allSingle ? 0u : __ballot_sync(FULLMASK, valid && cnt > SMALL_GROUP);
 	while (big) {
 		const int src = __ffs(big) - 1; big &= big - 1;
 		uint32_t hh[6];
@@ -408,8 +428,7 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 	v[12] = nrec;
 	// All 13 counters of a CTA of small groups fit 16-bit fields (256 threads x <= 32 members), so
 	// three 64-bit scans replace thirteen 32-bit ones; a CTA holding a big group takes the wide path.
-	__shared__ uint64_t sm64[3 * 8];
-	const int anyBig = __syncthreads_or(valid && cnt > SMALL_GROUP);
+	const int anyBig = allSingle ? 0 : __syncthreads_or(valid && cnt > SMALL_GROUP);
 	if (!anyBig) {
 		uint64_t pk[3], pt[3];
 		pk[0] = (uint64_t)v[0] | (uint64_t)v[1] << 10 | (uint64_t)v[2] << 20 | (uint64_t)v[3] << 30 | (uint64_t)v[4] << 40 | (uint64_t)v[5] << 50;
@@ -433,12 +452,11 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 	if (!valid) return;
 #pragma unroll
 	for (int k = 0; k < NGC; ++k) v[k] += A.ctaTot[(size_t)blockIdx.x * NGC + k];
-	const Ctl *ctl = A.ctl;
 	// records of bucket b start at the record prefix of the bucket's first group
 #pragma unroll
-	for (int b = 0; b < 6; ++b) if (g == ctl->gBkt[b]) A.ctl->recBkt[b] = v[12];
-	const int64_t sz = A.gSize[g];
-	const bool nonempty = sz > 0 && A.sizes6 != 0;
+	for (int b = 0; b < 6; ++b) if (g == sCtl[16 + b]) A.ctl->recBkt[b] = v[12];
+	const bool useSizes = A.sizes6 != 0;
+	const bool nonempty = useSizes && A.gSize[g] > 0;
 	int64_t P = A.gL[g];
 	uint32_t r = v[12];
 	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
@@ -449,14 +467,14 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 		if (h[a]) {
 			uint32_t dst = NONE32;
 			if (a > 0) { // a child that continues: it is a group of the next column (bucket a)
-				dst = ctl->gBktNext[a] + v[a];
-				A.gSizeNext[dst] = sza;
-				A.gOffNext[dst] = ctl->mBktNext[a] + v[6 + a];
+				dst = sCtl[a] + v[a];
+				if (useSizes) A.gSizeNext[dst] = sza; // without an old index every interval stays empty and gSize is never read
+				A.gOffNext[dst] = sCtl[8 + a] + v[6 + a];
 			}
 			uint32_t rem = h[a];
 			while (rem) { // counts above the 4-byte run limit become several records at the same position
 				uint32_t c = rem < RB2_MAXRUN ? rem : RB2_MAXRUN;
-				A.recP[r] = P; A.recSym[r] = (uint8_t)a; A.recCnt[r] = c; A.recDst[r] = dst;
+				A.recP[r] = P; A.recSC[r] = (c << 3) | (uint32_t)a; A.recDst[r] = dst;
 				dst = NONE32; rem -= c; ++r;
 			}
 		}
@@ -532,7 +550,7 @@ struct ItemScan { // K=1: work items per logical block
 struct MergeArgs {
 	uint8_t *pool; uint32_t *blkCnt; Dir dir; uint32_t nlog;
 	const uint32_t *recHi, *itemOff, *itemBlk;
-	const int64_t *recP; const uint8_t *recSym; const uint32_t *recCnt, *recDst;
+	const int64_t *recP; const uint32_t *recSC, *recDst; // recSC = count << 3 | symbol
 	int64_t *gLNext;
 	uint32_t *itemPieces, *itemFirst, *itemRest;
 	uint32_t *todo;   // items left for k_merge_general
@@ -612,12 +630,12 @@ __device__ __forceinline__ uint32_t lane_merge(const uint8_t *img, uint32_t bp, 
 		if (b > a) emit(s, b - a);
 	};
 	auto do_record = [&]() {
-		const uint32_t a = A.recSym[r];
+		const uint32_t sc = A.recSC[r], a = sc & 7u;
 		if (EMIT) {
 			const uint32_t dst = A.recDst[r];
 			if (dst != NONE32) A.gLNext[dst] = A.ctl->cpost[a] + cumCntBlk[a] + lc[a];
 		}
-		emit(a, A.recCnt[r]);
+		emit(a, sc >> 3);
 		++r;
 		nextP = r < rhi ? (uint32_t)(A.recP[r] - blkStart) : 0xffffffffu;
 	};
@@ -776,7 +794,8 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 	uint32_t P = 0, a = 0, cnt = 0, bpq = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
 	if (act) {
 		const uint32_t r = C.r0 + lane;
-		P = (uint32_t)(A.recP[r] - C.blkStart); a = A.recSym[r]; cnt = A.recCnt[r];
+		P = (uint32_t)(A.recP[r] - C.blkStart);
+		{ const uint32_t sc = A.recSC[r]; a = sc & 7u; cnt = sc >> 3; }
 		uint32_t lo = 0, hi = 31;
 		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.laneEnd[mid] >= P) hi = mid; else lo = mid + 1; }
 		const uint32_t t = lo;
@@ -787,34 +806,32 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 		if (((C.pureMask >> t) & 1u) && P > 0) {
 			// target lane holds only 1-byte runs: find the run with 4-byte SIMD steps.  Lengths are
 			// (byte >> 3); a multiply by 0x01010101 gives the inclusive prefix inside a word.
-			const uint4 tw = reinterpret_cast<const uint4*>(img)[t];
-			uint32_t w[4] = { tw.x, tw.y, tw.z, tw.w };
-			if (t == 0) w[0] &= 0xffff0000u;
+			const uint32_t *tw = reinterpret_cast<const uint32_t*>(img) + t * 4;
 			const uint32_t prel = P - pos; // 1 .. symbols in the lane
 			const uint32_t tlo = a < 4 ? 1u << (8 * a) : 0u, thi = a >= 4 ? 1u << (8 * (a - 4)) : 0u;
 			uint32_t acc = 0, idx = 0;
-			bool found = false;
-#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const uint32_t lens = (w[j] >> 3) & 0x0f0f0f0fu;
-				const uint32_t sy = w[j] & 0x07070707u;
+#pragma unroll 1
+			for (int j = 0; j < 4; ++j) { // rolled on purpose (instruction footprint)
+				uint32_t wj = tw[j];
+				if (t == 0 && j == 0) wj &= 0xffff0000u;
+				const uint32_t lens = (wj >> 3) & 0x0f0f0f0fu;
+				const uint32_t sy = wj & 0x07070707u;
 				const uint32_t tt = sy | (sy >> 4);
 				const uint32_t wt = __byte_perm(tlo, thi, (tt & 0xffu) | ((tt >> 8) & 0xff00u)); // 1 where symbol == a
 				const uint32_t wsum = __dp4a(lens, 0x01010101u, 0u);
-				if (!found) {
-					if (acc + wsum >= prel) {
-						const uint32_t pre = lens * 0x01010101u;
-						int i = 0;
+				if (acc + wsum >= prel) {
+					const uint32_t pre = lens * 0x01010101u;
+					int i = 0;
 #pragma unroll
-						for (int x = 2; x >= 0; --x) if (acc + ((pre >> (8 * x)) & 0xffu) < prel) { i = x + 1; break; }
-						idx = 4 * j + i;
-						len = (lens >> (8 * i)) & 0xffu; sym = (sy >> (8 * i)) & 7u;
-						const uint32_t before = i ? (1u << (8 * i)) - 1u : 0u;
-						ca += __dp4a(lens & before, wt, 0u);
-						pos += acc + ((pre >> (8 * i)) & 0xffu) - len;
-						found = true;
-					} else { acc += wsum; ca += __dp4a(lens, wt, 0u); }
+					for (int x = 2; x >= 0; --x) if (acc + ((pre >> (8 * x)) & 0xffu) < prel) { i = x + 1; break; }
+					idx = 4 * j + i;
+					len = (lens >> (8 * i)) & 0xffu; sym = (sy >> (8 * i)) & 7u;
+					const uint32_t before = i ? (1u << (8 * i)) - 1u : 0u;
+					ca += __dp4a(lens & before, wt, 0u);
+					pos += acc + ((pre >> (8 * i)) & 0xffu) - len;
+					break;
 				}
+				acc += wsum; ca += __dp4a(lens, wt, 0u);
 			}
 			q = idx - F.laneFb[t];
 			bpq = t * 16 + idx;
@@ -865,7 +882,7 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 		};
 		auto next_rec = [&]() {
 			++rr_;
-			if (rr_ < rend) { nextP = (uint32_t)(A.recP[rr_] - C.blkStart); na = A.recSym[rr_]; nc = A.recCnt[rr_]; }
+			if (rr_ < rend) { nextP = (uint32_t)(A.recP[rr_] - C.blkStart); const uint32_t sc = A.recSC[rr_]; na = sc & 7u; nc = sc >> 3; }
 		};
 		for (uint32_t g = s; g <= eLast; ++g) {
 			uint32_t sy, rl, nb;
@@ -966,8 +983,8 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 			uint32_t curEnd = kk ? F.eEnd[kk - 1] : 0;                  // bytes below this belong to an edited span
 			uint32_t nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;  // first byte of the next edited span
 			uint32_t cum = (uint32_t)F.eCum[kk];
-#pragma unroll
-			for (int i = 0; i < 16; ++i) {
+#pragma unroll 1
+			for (int i = 0; i < 16; ++i) { // rolled on purpose (instruction footprint); bytes come from the image
 				const uint32_t bp = bp0 + i;
 				if (bp >= nextStart) { // distinct starts: at most one edit begins per byte
 					++kk;
@@ -975,7 +992,7 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 					nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;
 					cum = (uint32_t)F.eCum[kk];
 				}
-				if (bp >= curEnd) out[bp + cum] = (uint8_t)(w4[i >> 2] >> ((i & 3) * 8));
+				if (bp >= curEnd) out[bp + cum] = img[bp];
 			}
 		}
 		if (head) { // my group's replacement bytes
@@ -1178,9 +1195,9 @@ struct rb2_engine {
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
 	int64_t *dRankOut, *hRankOut;
 	// batch scratch
-	DevBuf<uint8_t> sbuf, T, asym, recSym, stage;
+	DevBuf<uint8_t> sbuf, T, asym, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
-	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recCnt, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, todo, scanCta;
+	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, todo, scanCta;
 	DevBuf<int64_t> scanCta64, midTmp64;
 	DevBuf<uint32_t> midTmp;
 	unsigned long long *dMaxLen;
@@ -1399,10 +1416,10 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
 	dir_free(e->dir[0]); dir_free(e->dir[1]);
-	e->sbuf.release(); e->T.release(); e->asym.release(); e->recSym.release(); e->stage.release();
+	e->sbuf.release(); e->T.release(); e->asym.release(); e->stage.release();
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
-	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recCnt.release(); e->recDst.release(); e->recHi.release();
+	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recSC.release(); e->recDst.release(); e->recHi.release();
 	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release();
 	e->scanCta.release(); e->scanCta64.release(); e->midTmp.release(); e->midTmp64.release();
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
@@ -1459,7 +1476,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		// ---- merge -----------------------------------------------------------------
 		if (attempt == 0) ph_begin(e, PH_MERGE);
 		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
-		                 e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, gLNext,
+		                 e->recP.p, e->recSC.p, e->recDst.p, gLNext,
 		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->todo.p, e->dctl };
 		LAUNCH(e, k_merge_fast, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(FastSmem), ma);
 		if (attempt == 0) { ph_end(e, PH_MERGE); ph_begin(e, PH_MERGE2); }
@@ -1529,7 +1546,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	for (int k = 0; k < 2; ++k) { e->gL[k].need(m); e->gSize[k].need(m); e->gOff[k].need((size_t)m + 1); e->sid[k].need((size_t)m + 4); }
 	e->asym.need((size_t)m + 8);
 	const size_t recCap = (size_t)m + m / RB2_MAXRUN + 64;
-	e->recP.need(recCap); e->recSym.need(recCap); e->recCnt.need(recCap); e->recDst.need(recCap);
+	e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
 	// Reserve leaf blocks for the whole batch up front (2 bytes of pool per new symbol covers random
 	// data at B+-tree fill plus blocks retired by multi-item merges); more is added on demand.
 	reserve_blocks(e, (uint64_t)e->hctl->poolUsed + (uint64_t)len * 2 / RB2_FILL + 4096);
@@ -1575,7 +1592,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const uint32_t nGC = cdiv(G, 256);
 		e->grpCta.need((size_t)nGC * NGC + NGC);
 		GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
-		                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSym.p, e->recCnt.p, e->recDst.p, e->dctl };
+		                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl };
 		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 		else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
 		run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
@@ -1780,15 +1797,13 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	if (bucket < 0 || bucket > 5 || a < 0 || a > 5 || rl <= 0) RB2_FATAL("rb2_insert_run: bad argument");
 	if (x < 0 || x > e->bktLen[bucket]) RB2_FATAL("rb2_insert_run: position out of range");
 	const uint32_t k = (uint32_t)((rl + RB2_MAXRUN - 1) / RB2_MAXRUN);
-	e->recP.need(k); e->recSym.need(k); e->recCnt.need(k); e->recDst.need(k);
+	e->recP.need(k); e->recSC.need(k); e->recDst.need(k);
 	std::vector<int64_t> P(k, bucket_start(e, bucket) + x);
-	std::vector<uint8_t> S(k, (uint8_t)a);
-	std::vector<uint32_t> C(k, RB2_MAXRUN), D(k, NONE32);
-	C[k - 1] = (uint32_t)(rl - (int64_t)(k - 1) * RB2_MAXRUN);
+	std::vector<uint32_t> C(k, (RB2_MAXRUN << 3) | (uint32_t)a), D(k, NONE32);
+	C[k - 1] = ((uint32_t)(rl - (int64_t)(k - 1) * RB2_MAXRUN) << 3) | (uint32_t)a;
 	D[0] = 0;
 	RB2_CUDA(cudaMemcpyAsync(e->recP.p, P.data(), k * 8, cudaMemcpyHostToDevice, e->st));
-	RB2_CUDA(cudaMemcpyAsync(e->recSym.p, S.data(), k, cudaMemcpyHostToDevice, e->st));
-	RB2_CUDA(cudaMemcpyAsync(e->recCnt.p, C.data(), k * 4, cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(e->recSC.p, C.data(), k * 4, cudaMemcpyHostToDevice, e->st));
 	RB2_CUDA(cudaMemcpyAsync(e->recDst.p, D.data(), k * 4, cudaMemcpyHostToDevice, e->st));
 	Ctl *h = e->hctl;
 	for (int b = 0; b < 8; ++b) { h->blkBkt[b] = e->blkBkt[b]; h->recBkt[b] = b <= bucket ? 0 : k; h->cpost[b] = 0; }
