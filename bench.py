@@ -269,8 +269,10 @@ def main():
     fast_bytes = fast_items * 2 * 512
     merge_gbs = fast_bytes / (st["ms_merge"] * 1e-3) / 1e9 if st["ms_merge"] > 0 else 0.0
     traffic = None
+    traffic_info = None
     ncu_json = os.path.join(ROOT, "profiles", "merge_traffic.json")
     if os.path.exists(ncu_json):
+        traffic_info = {k: v for k, v in json.load(open(ncu_json)).items() if k in ("capture", "items_in_launch", "algorithmic_bytes_same_launch", "note")}
         traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")  # one late launch (column 90) at this workload size
     value = world * bp * args.steps / (ms_value * 1e-3) / 1e9
     e2e_val = world * bp * args.steps / (ms_e2e * 1e-3) / 1e9
@@ -289,7 +291,7 @@ def main():
                 "api": "mr_insert_multi (include/mrope.h) on a pinned host buffer + mr_get_c counts"},
         "gpu_launches": int(st["n_launches"]),
         "roofline": {"bound": "hbm", "kernel": "k_merge_fast", "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": merge_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": merge_gbs / peak, "traffic": traffic, "traffic_capture": traffic_info, "peak_source": peak_src,
                      "launches": int(st["n_merge_launches"]), "ms_in_kernel": st["ms_merge"],
                      "algorithmic_bytes": int(fast_bytes), "items": int(fast_items),
                      "items_left_to_k_merge_general": int(st["general_items"]), "ms_in_k_merge_general": st["ms_merge_general"],
