@@ -498,6 +498,78 @@ __global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
 	if (bad) ctl->err |= RB2_ERR_ORDER;
 }
 
+// ---- all-singleton regime ----------------------------------------------------------------------
+// When every group has exactly one member (always in input order, mrope.c:282; in the sorted modes
+// as soon as all suffixes read so far are distinct) group index = member index = record index, and
+// the next group index of a string is its partition destination.  One kernel then does the work of
+// both group passes, their scans and the partition (mrope.c:195-198 is the reference's own
+// special case for this situation).
+__global__ void k_col_bases_single(Ctl *ctl, uint32_t *gOffNext, uint32_t M)
+{
+	uint32_t m = 0;
+	ctl->gBktNext[0] = 0; ctl->mBktNext[0] = 0;
+	for (int a = 1; a <= 6; ++a) {
+		ctl->gBktNext[a] = m; ctl->mBktNext[a] = m;
+		if (a < 6) m += ctl->memTot[a];
+	}
+	ctl->gBktNext[7] = m; ctl->mBktNext[7] = m;
+	ctl->Gnext = m; ctl->Mnext = m; ctl->nrec = M;
+	for (int b = 0; b < 8; ++b) ctl->recBkt[b] = ctl->mBkt[b]; // one record per member, same order
+	gOffNext[m] = m;
+}
+
+struct SingleArgs {
+	const uint32_t *sid; const uint8_t *asym; uint32_t M; const uint32_t *tilePre;
+	const int64_t *gL, *gSize, *sizes6; const Ctl *ctl;
+	uint32_t *sidNext; int64_t *gSizeNext; uint32_t *gOffNext;
+	int64_t *recP; uint32_t *recSC, *recDst;
+};
+
+template <bool COMP>
+__global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
+{
+	__shared__ uint32_t sm[6 * 8];
+	const uint32_t k = blockIdx.x * MEM_TILE + threadIdx.x * 4;
+	uint32_t a4 = 0, id[4] = { 0, 0, 0, 0 };
+	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 }, tot[6];
+	if (k < A.M) {
+		a4 = *reinterpret_cast<const uint32_t*>(A.asym + k);
+		for (int i = 0; i < 4; ++i) if (k + i < A.M) {
+			id[i] = A.sid[k + i];
+			const uint32_t a = (a4 >> (8 * i)) & 0xff;
+#pragma unroll
+			for (int x = 0; x < 6; ++x) c[x] += a == x;
+		}
+	}
+	cta_excl_scan<6, 256, uint32_t>(c, tot, sm);
+	if (k >= A.M) return;
+	uint32_t base[6];
+#pragma unroll
+	for (int x = 0; x < 6; ++x) base[x] = A.ctl->mBktNext[x] + A.tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
+	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
+	for (int i = 0; i < 4; ++i) if (k + i < A.M) {
+		const uint32_t g = k + i, a = (a4 >> (8 * i)) & 0xff;
+		uint32_t d = NONE32;
+#pragma unroll
+		for (int x = 1; x < 6; ++x) if (a == x) d = base[x]++;
+		int64_t P = A.gL[g], sza = 0;
+		if (A.sizes6 && A.gSize[g] > 0) { // insertion point: behind the old symbols of the earlier slots
+#pragma unroll
+			for (int slot = 0; slot < 6; ++slot) {
+				const int64_t z = A.sizes6[(size_t)g * 6 + ord[slot]];
+				if ((uint32_t)ord[slot] == a) { sza = z; break; }
+				P += z;
+			}
+		}
+		if (a) {
+			A.sidNext[d] = id[i];
+			A.gOffNext[d] = d;
+			if (A.sizes6) A.gSizeNext[d] = sza;
+		}
+		A.recP[g] = P; A.recSC[g] = (1u << 3) | a; A.recDst[g] = d;
+	}
+}
+
 // =====================================================================================
 // Blocks: plan work items, merge records into leaf blocks, rebuild the directory
 // =====================================================================================
@@ -1589,21 +1661,32 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		ph_begin(e, PH_GROUPS);
 		if (useSizes)
 			LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
-		const uint32_t nGC = cdiv(G, 256);
-		e->grpCta.need((size_t)nGC * NGC + NGC);
-		GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
-		                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl };
-		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
-		else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
-		run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
-		LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p);
-		if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
-		else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
-		ph_end(e, PH_GROUPS);
+		if (G == M) {
+			// every group is a singleton: records, next groups and the partition in one kernel
+			LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, M);
+			SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
+			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p };
+			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
+			else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
+			ph_end(e, PH_GROUPS);
+			ph_begin(e, PH_MEMBERS2); ph_end(e, PH_MEMBERS2);
+		} else {
+			const uint32_t nGC = cdiv(G, 256);
+			e->grpCta.need((size_t)nGC * NGC + NGC);
+			GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
+			                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl };
+			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
+			else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
+			run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
+			LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p);
+			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
+			else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
+			ph_end(e, PH_GROUPS);
 
-		ph_begin(e, PH_MEMBERS2);
-		LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[cs ^ 1].p);
-		ph_end(e, PH_MEMBERS2);
+			ph_begin(e, PH_MEMBERS2);
+			LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[cs ^ 1].p);
+			ph_end(e, PH_MEMBERS2);
+		}
 		ctl_pull(e);
 		ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2));
 		const uint32_t nrec = h->nrec;
