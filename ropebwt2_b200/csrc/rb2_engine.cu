@@ -601,9 +601,16 @@ __global__ void __launch_bounds__(256) k_rec_hi(Dir dir, uint32_t nlog, const Ct
 	recHi[i] = lo;
 }
 
+struct alignas(16) ItemMeta { // everything a merge warp needs to start, in two 128-bit loads
+	uint32_t i, phys, r0, r1;   // logical block, physical block, record range [r0, r1)
+	int64_t blkStart;           // global position of the block's first symbol
+	uint32_t nIt, sub;          // items of this block, index of this item among them
+};
+
 struct ItemScan { // K=1: work items per logical block
 	const Ctl *ctl; const uint32_t *recHi; uint32_t nlog;
-	uint32_t *itemOff, *itemBlk; Ctl *ctlw;
+	uint32_t *itemOff; ItemMeta *itemMeta; Ctl *ctlw;
+	const uint32_t *order; const int64_t *cumLen;
 	__device__ uint32_t rec_lo(uint32_t i) const {
 		const int b = bucket_of(ctl->blkBkt, i);
 		return i == ctl->blkBkt[b] ? ctl->recBkt[b] : recHi[i - 1];
@@ -614,14 +621,23 @@ struct ItemScan { // K=1: work items per logical block
 	}
 	__device__ void store(uint64_t i, const uint32_t (&own)[1], const uint32_t (&pre)[1]) const {
 		itemOff[i] = pre[0];
-		for (uint32_t s = 0; s < own[0]; ++s) itemBlk[pre[0] + s] = (uint32_t)i;
+		if (own[0]) {
+			const uint32_t lo = rec_lo((uint32_t)i), hi = recHi[i], ph = order[i];
+			const int64_t bs = cumLen[i];
+			for (uint32_t s = 0; s < own[0]; ++s) {
+				ItemMeta m;
+				m.i = (uint32_t)i; m.phys = ph; m.r0 = lo + s * RMAX; m.r1 = m.r0 + RMAX < hi ? m.r0 + RMAX : hi;
+				m.blkStart = bs; m.nIt = own[0]; m.sub = s;
+				itemMeta[pre[0] + s] = m;
+			}
+		}
 		if (i + 1 == nlog) { itemOff[nlog] = pre[0] + own[0]; ctlw->nItems = pre[0] + own[0]; }
 	}
 };
 
 struct MergeArgs {
 	uint8_t *pool; uint32_t *blkCnt; Dir dir; uint32_t nlog;
-	const uint32_t *recHi, *itemOff, *itemBlk;
+	const uint32_t *recHi, *itemOff; const ItemMeta *itemMeta;
 	const int64_t *recP; const uint32_t *recSC, *recDst; // recSC = count << 3 | symbol
 	int64_t *gLNext;
 	uint32_t *itemPieces, *itemFirst, *itemRest;
@@ -1110,14 +1126,8 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 // Common prologue of both merge kernels: which block, which records, decode the block.
 __device__ __forceinline__ void item_prologue(const MergeArgs &A, ItemCtx &C, int lane, uint8_t *img, uint32_t *cntScratch)
 {
-	C.i = A.itemBlk[C.w];
-	const uint32_t it0 = A.itemOff[C.i];
-	C.nIt = A.itemOff[C.i + 1] - it0; C.sub = C.w - it0;
-	const int b = bucket_of(A.ctl->blkBkt, C.i);
-	const uint32_t recLo = C.i == A.ctl->blkBkt[b] ? A.ctl->recBkt[b] : A.recHi[C.i - 1], recHiB = A.recHi[C.i];
-	C.r0 = recLo + C.sub * RMAX; C.r1 = C.r0 + RMAX < recHiB ? C.r0 + RMAX : recHiB;
-	C.blkStart = A.dir.cumLen[C.i];
-	C.phys = A.dir.order[C.i];
+	const ItemMeta m = A.itemMeta[C.w];
+	C.i = m.i; C.phys = m.phys; C.r0 = m.r0; C.r1 = m.r1; C.blkStart = m.blkStart; C.nIt = m.nIt; C.sub = m.sub;
 	C.cumCntBlk = A.dir.cumCnt + (size_t)C.i * 6;
 	uint32_t err = 0;
 	warp_decode_block(A.pool + (size_t)C.phys * RB2_BLK, lane, img, cntScratch, C.d, C.basePos, C.baseCnt, C.blkLen, C.blkCnt, C.nbytes, err, C.own, &C.pureMask);
@@ -1136,11 +1146,8 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(M
 	if (C.w >= A.ctl->nItems) return;
 	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
 	FastSmem &S = reinterpret_cast<FastSmem*>(smraw)[wid];
-	// eligibility is known before touching the block
-	const uint32_t i = A.itemBlk[C.w];
-	const uint32_t nIt = A.itemOff[i + 1] - A.itemOff[i];
 	bool done = false;
-	if (nIt == 1) {
+	if (A.itemMeta[C.w].nIt == 1) { // eligibility is known before touching the block
 		item_prologue(A, C, lane, S.img, S.f.laneBase);
 		if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C);
 	}
@@ -1269,7 +1276,8 @@ struct rb2_engine {
 	// batch scratch
 	DevBuf<uint8_t> sbuf, T, asym, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
-	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemBlk, itemPieces, itemFirst, itemRest, todo, scanCta;
+	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemPieces, itemFirst, itemRest, todo, scanCta;
+	DevBuf<ItemMeta> itemMeta;
 	DevBuf<int64_t> scanCta64, midTmp64;
 	DevBuf<uint32_t> midTmp;
 	unsigned long long *dMaxLen;
@@ -1409,7 +1417,7 @@ static void reserve_blocks(rb2_engine *e, uint64_t blocks)
 
 static void reserve_items(rb2_engine *e, uint64_t n)
 {
-	e->itemBlk.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n); e->todo.need(n);
+	e->itemMeta.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n); e->todo.need(n);
 }
 
 extern "C" int rb2_device_count(void)
@@ -1492,7 +1500,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recSC.release(); e->recDst.release(); e->recHi.release();
-	e->itemOff.release(); e->itemBlk.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release();
+	e->itemOff.release(); e->itemMeta.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release();
 	e->scanCta.release(); e->scanCta64.release(); e->midTmp.release(); e->midTmp64.release();
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
@@ -1536,7 +1544,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 	{
 		Dir &dc = e->dir[e->cur];
 		LAUNCH(e, k_rec_hi, cdiv(e->nlog, 256), 256, 0, dc, e->nlog, e->dctl, e->recP.p, e->recHi.p);
-		ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemBlk.p, e->dctl };
+		ItemScan is = { e->dctl, e->recHi.p, e->nlog, e->itemOff.p, e->itemMeta.p, e->dctl, dc.order, dc.cumLen };
 		run_scan<1, uint32_t, ItemScan>(e, is, e->nlog, e->scanCta, (uint32_t*)0, e->midTmp);
 		RB2_CUDA(cudaMemsetAsync(e->itemPieces.p, 0, maxItems * 4, e->st)); // 0 = not merged yet
 	}
@@ -1547,7 +1555,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		Dir &dc = e->dir[e->cur], &dnx = e->dir[e->cur ^ 1];
 		// ---- merge -----------------------------------------------------------------
 		if (attempt == 0) ph_begin(e, PH_MERGE);
-		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemBlk.p,
+		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemMeta.p,
 		                 e->recP.p, e->recSC.p, e->recDst.p, gLNext,
 		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->todo.p, e->dctl };
 		LAUNCH(e, k_merge_fast, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(FastSmem), ma);
