@@ -659,10 +659,13 @@ struct FastScratch {                // edit-based fast path
 	uint32_t eStart[FAST_MAXREC + 1], eEnd[FAST_MAXREC + 1], eNew[FAST_MAXREC + 1], eBuf[FAST_MAXREC + 1];
 	int32_t  eCum[FAST_MAXREC + 2];   // exclusive prefix of (new - old) byte deltas
 	uint32_t cntAdd[8];               // symbols added by the item's records
+	int64_t  cumBase[6];              // cumCnt of the block (per-symbol counts in front of it, all buckets)
 };
 #define OUT_OFF  0     // fast path: the output block image is assembled at stage[0, 1024)
 #define EBUF_OFF 1536  // fast path: replacement bytes of the edits, 16 per record, at stage[1536, 2048)
 #define FAST_STAGE 2048
+struct RecPre { int64_t P; uint32_t sc, dst; }; // one record, loaded ahead of the block decode
+
 struct alignas(16) FastSmem {       // per warp, k_merge_fast
 	uint8_t  img[RB2_IMG_BYTES];    // the input block, byte-addressable (+16 zero bytes)
 	uint8_t  stage[FAST_STAGE];     // output image + replacement bytes
@@ -861,7 +864,7 @@ __device__ __forceinline__ void merge_general(const MergeArgs &A, GenSmem &S, in
 // lane stores its 16 input bytes at their shifted position (bytes inside an edited span are
 // dropped), the group heads store their replacement bytes, then each lane reads back 16 aligned
 // bytes.  Returns false (no side effects besides idempotent rank writes) if it cannot place a split.
-__device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int lane, const ItemCtx &C)
+__device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int lane, const ItemCtx &C, const RecPre &rp)
 {
 	FastScratch &F = S.f;
 	const uint8_t *img = S.img;
@@ -881,9 +884,8 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 	const bool act = (uint32_t)lane < nrec;
 	uint32_t P = 0, a = 0, cnt = 0, bpq = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
 	if (act) {
-		const uint32_t r = C.r0 + lane;
-		P = (uint32_t)(A.recP[r] - C.blkStart);
-		{ const uint32_t sc = A.recSC[r]; a = sc & 7u; cnt = sc >> 3; }
+		P = (uint32_t)(rp.P - C.blkStart);
+		a = rp.sc & 7u; cnt = rp.sc >> 3;
 		uint32_t lo = 0, hi = 31;
 		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.laneEnd[mid] >= P) hi = mid; else lo = mid + 1; }
 		const uint32_t t = lo;
@@ -933,8 +935,7 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 			}
 		}
 		off = P - pos;
-		const uint32_t dst = A.recDst[r];
-		if (dst != NONE32) A.gLNext[dst] = A.ctl->cpost[a] + C.cumCntBlk[a] + ca + (sym == a ? off : 0);
+		if (rp.dst != NONE32) A.gLNext[rp.dst] = A.ctl->cpost[a] + F.cumBase[a] + ca + (sym == a ? off : 0);
 		atomicAdd(&F.cntAdd[a], cnt);
 		s = F.laneRunPre[t] + q;                                   // global index of that run
 		e = s + ((off == len && s + 1 < nRuns) ? 1 : 0);           // at a run boundary the next run may absorb the record
@@ -1147,9 +1148,17 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(M
 	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
 	FastSmem &S = reinterpret_cast<FastSmem*>(smraw)[wid];
 	bool done = false;
-	if (A.itemMeta[C.w].nIt == 1) { // eligibility is known before touching the block
+	const ItemMeta m = A.itemMeta[C.w];
+	if (m.nIt == 1) { // eligibility is known before touching the block
+		// issue the record loads before the block decode so that their latency overlaps it
+		RecPre rp = { 0, 0, NONE32 };
+		if (m.r1 - m.r0 <= FAST_MAXREC && m.r0 + lane < m.r1) {
+			const uint32_t r = m.r0 + lane;
+			rp.P = A.recP[r]; rp.sc = A.recSC[r]; rp.dst = A.recDst[r];
+		}
+		if (lane < 6) S.f.cumBase[lane] = A.dir.cumCnt[(size_t)m.i * 6 + lane];
 		item_prologue(A, C, lane, S.img, S.f.laneBase);
-		if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C);
+		if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C, rp);
 	}
 	if (!done && lane == 0) A.todo[atomicAdd(&A.ctl->nTodo, 1u)] = C.w;
 }
