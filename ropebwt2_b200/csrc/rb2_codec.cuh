@@ -52,16 +52,15 @@ __device__ __forceinline__ void parse_run(const uint8_t *img, uint32_t bp, uint3
 // image.  Deliberately a rolled loop: it is the cold path for short-run data and must not bloat the
 // instruction footprint of the kernels that inline it.  `lcs` = 6 lane-private shared-memory words
 // (indexing registers by a run-time symbol would cost a 6-way select per run).
-__device__ __noinline__ uint64_t decode_lane_serial(const uint8_t *img, int lane, uint32_t nbytes, uint32_t *lcs)
+// Accounts for the runs starting in image bytes [base+lo, base+hi); `none` = value of fb when no run starts there.
+__device__ __noinline__ uint64_t decode_span_serial(const uint8_t *img, uint32_t base, uint32_t lo, uint32_t hi, uint32_t none, uint32_t *lcs)
 {
 	// returns nr | fb << 8 | err << 16 | (uint64)len << 32; per-symbol counts are left in lcs[0..5]
-	const int lim = (int)nbytes + 2 - lane * 16; // byte i of this lane is a run byte iff i < lim (and i >= 2 in lane 0)
-	const uint32_t hi = lim > 16 ? 16u : (lim < 0 ? 0u : (uint32_t)lim), base = lane * 16;
-	uint32_t i = lane == 0 ? 2u : 0u, nr = 0, tot = 0, err = 0;
+	uint32_t i = lo, nr = 0, tot = 0, err = 0;
 #pragma unroll
 	for (int a = 0; a < 6; ++a) lcs[a] = 0;
 	while (i < hi && (img[base + i] & 0xC0u) == 0x80u) ++i; // tail of a run that started in the previous lane
-	const uint32_t fb = i < hi ? i : 16u;
+	const uint32_t fb = i < hi ? i : none;
 #pragma unroll 1
 	while (i < hi) {
 		uint32_t s, l, nb;
@@ -71,6 +70,13 @@ __device__ __noinline__ uint64_t decode_lane_serial(const uint8_t *img, int lane
 		i += nb;
 	}
 	return (uint64_t)nr | (uint64_t)fb << 8 | (uint64_t)err << 16 | (uint64_t)tot << 32;
+}
+
+__device__ __forceinline__ uint64_t decode_lane_serial(const uint8_t *img, int lane, uint32_t nbytes, uint32_t *lcs)
+{
+	const int lim = (int)nbytes + 2 - lane * 16; // byte i of this lane is a run byte iff i < lim (and i >= 2 in lane 0)
+	const uint32_t hi = lim > 16 ? 16u : (lim < 0 ? 0u : (uint32_t)lim);
+	return decode_span_serial(img, lane * 16, lane == 0 ? 2u : 0u, hi, 16u, lcs);
 }
 
 // exclusive scans of six per-lane counts that do not fit 16 bits (blocks with very long runs): cold.

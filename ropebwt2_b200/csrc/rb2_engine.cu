@@ -40,6 +40,9 @@
 #ifndef MERGE_MINCTA
 #define MERGE_MINCTA 10
 #endif
+#ifndef HALF_MINCTA
+#define HALF_MINCTA 8
+#endif
 #define NONE32      0xffffffffu
 #define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
 #define NGC         13     // group-scan counters: has[6], hist[6], nrec
@@ -48,6 +51,7 @@ struct Ctl { // device control block (one per engine), mirrored through pinned h
 	uint32_t poolUsed, err, nItems, nlogNew;
 	uint32_t overflow, failBase;   // pool exhausted during a merge kernel: first block id that did not fit
 	uint32_t nTodo, todoNext;     // items the fast kernel left for k_merge_general, and its work counter
+	uint32_t nTodoA, todoANext;   // items the half-warp kernel left for k_merge_fast, and its work counter
 	uint32_t blkBkt[8];     // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
 	uint32_t blkBktNew[8];
 	uint32_t gBkt[8], mBkt[8];         // this column: group / member index range per bucket
@@ -641,6 +645,7 @@ struct MergeArgs {
 	const int64_t *recP; const uint32_t *recSC, *recDst; // recSC = count << 3 | symbol
 	int64_t *gLNext;
 	uint32_t *itemPieces, *itemFirst, *itemRest;
+	uint32_t *todoA;  // items k_merge_half left for k_merge_fast
 	uint32_t *todo;   // items left for k_merge_general
 	Ctl *ctl;
 };
@@ -1124,6 +1129,369 @@ __device__ __forceinline__ bool merge_fast(const MergeArgs &A, FastSmem &S, int 
 	return true;
 }
 
+// ---- half-warp path: two items per warp, 16 lanes x 32 bytes each -------------------------------
+// Same algorithm as merge_fast, for items with <= 16 records (the bulk of all block visits).  The
+// per-record sections of merge_fast keep only the few lanes that hold a record busy; with two
+// items per warp every instruction of those sections serves both.  All collectives use the
+// half's own lane mask, so the two halves may diverge freely.
+#define HALF_MAXREC 16
+#define HALF_OUT    1024  // output image at stage[0, 1024)
+struct HalfScratch {
+	uint32_t laneBase[16 * 7];
+	uint32_t laneEnd[16], laneNr[16], laneRunPre[16], laneFb[16];
+	uint32_t eStart[HALF_MAXREC + 1], eEnd[HALF_MAXREC + 1], eNew[HALF_MAXREC + 1];
+	int32_t  eCum[HALF_MAXREC + 2];
+	uint32_t cntAdd[8];
+	int64_t  cumBase[6];
+};
+struct alignas(16) HalfSmem {
+	uint8_t img[RB2_IMG_BYTES];
+	uint8_t stage[HALF_OUT + HALF_MAXREC * 16];
+	HalfScratch h;
+};
+
+template <typename T>
+__device__ __forceinline__ T half_incl_scan(T v, int hl, uint32_t hmask)
+{
+#pragma unroll
+	for (int o = 1; o < 16; o <<= 1) {
+		T y = __shfl_up_sync(hmask, v, o, 16);
+		if (hl >= o) v += y;
+	}
+	return v;
+}
+
+__global__ void __launch_bounds__(MERGE_WARPS * 32, HALF_MINCTA) k_merge_half(MergeArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+	const uint32_t hmask = half ? 0xffff0000u : 0x0000ffffu;
+	const uint32_t w = (blockIdx.x * MERGE_WARPS + wid) * 2 + half;
+	if (w >= A.ctl->nItems) return;
+	if (A.itemPieces[w] != 0) return; // merged by an earlier launch (retry after pool growth)
+	HalfSmem &S = reinterpret_cast<HalfSmem*>(smraw)[wid * 2 + half];
+	HalfScratch &F = S.h;
+	const ItemMeta m = A.itemMeta[w];
+	const uint32_t nrec = m.r1 - m.r0;
+	auto defer = [&]() { if (hl == 0) A.todoA[atomicAdd(&A.ctl->nTodoA, 1u)] = w; };
+	if (m.nIt != 1 || nrec > HALF_MAXREC) { defer(); return; }
+
+	// ---- loads: my record, the block's directory counts, the block itself --------------------
+	const bool act = (uint32_t)hl < nrec;
+	int64_t recP = 0; uint32_t recSC = 0, recDst = NONE32;
+	if (act) { const uint32_t r = m.r0 + hl; recP = A.recP[r]; recSC = A.recSC[r]; recDst = A.recDst[r]; }
+	if (hl < 6) F.cumBase[hl] = A.dir.cumCnt[(size_t)m.i * 6 + hl];
+	const uint4 *blk = reinterpret_cast<const uint4*>(A.pool + (size_t)m.phys * RB2_BLK);
+	const uint4 o0 = blk[hl * 2], o1 = blk[hl * 2 + 1];
+	uint8_t *img = S.img;
+	reinterpret_cast<uint4*>(img)[hl * 2] = o0;
+	reinterpret_cast<uint4*>(img)[hl * 2 + 1] = o1;
+	if (hl == 0) reinterpret_cast<uint4*>(img)[32] = make_uint4(0, 0, 0, 0);
+	if (hl < 8) F.cntAdd[hl] = 0;
+	const uint32_t nbytes = __shfl_sync(hmask, o0.x, 0, 16) & 0xffffu, endBp = 2 + nbytes;
+	__syncwarp(hmask);
+	if (nbytes == 0) { defer(); return; }
+
+	// ---- decode: 32 bytes per lane ---------------------------------------------------------
+	uint32_t wv[8] = { o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w };
+	if (hl == 0) wv[0] &= 0xffff0000u;
+	const int lim = (int)nbytes + 2 - hl * 32;
+	const uint32_t vhi = lim > 32 ? 32u : (lim < 0 ? 0u : (uint32_t)lim), vlo = hl == 0 ? 2u : 0u;
+	uint32_t any = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) any |= wv[j];
+	const bool pure = (any & 0x80808080u) == 0 || lim <= 0;
+	const uint32_t pureMask = (__ballot_sync(hmask, pure) >> (16 * half)) & 0xffffu;
+	uint32_t dnr, dlen, dfb, dc[6] = { 0, 0, 0, 0, 0, 0 };
+	if (pure) {
+		if (vhi < 32) {
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				const int keep = (int)vhi - 4 * j;
+				wv[j] = keep >= 4 ? wv[j] : (keep <= 0 ? 0u : wv[j] & ((1u << (8 * keep)) - 1u));
+			}
+		}
+		dnr = vhi > vlo ? vhi - vlo : 0; dfb = vhi > vlo ? vlo : 32u; dlen = 0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t lens = (wv[j] >> 3) & 0x0f0f0f0fu;
+			const uint32_t sy = wv[j] & 0x07070707u;
+			const uint32_t t = sy | (sy >> 4);
+			const uint32_t sel = (t & 0xffu) | ((t >> 8) & 0xff00u);
+			dlen = __dp4a(lens, 0x01010101u, dlen);
+			dc[0] = __dp4a(lens, __byte_perm(0x00000001u, 0u, sel), dc[0]);
+			dc[1] = __dp4a(lens, __byte_perm(0x00000100u, 0u, sel), dc[1]);
+			dc[2] = __dp4a(lens, __byte_perm(0x00010000u, 0u, sel), dc[2]);
+			dc[3] = __dp4a(lens, __byte_perm(0x01000000u, 0u, sel), dc[3]);
+			dc[4] = __dp4a(lens, __byte_perm(0u, 0x00000001u, sel), dc[4]);
+			dc[5] = __dp4a(lens, __byte_perm(0u, 0x00000100u, sel), dc[5]);
+		}
+	} else {
+		uint32_t *lcs = F.laneBase + hl * 7;
+		const uint64_t r = decode_span_serial(img, hl * 32, vlo, vhi, 32u, lcs);
+		dnr = (uint32_t)r & 0xffu; dfb = ((uint32_t)r >> 8) & 0xffu; dlen = (uint32_t)(r >> 32);
+		if (((uint32_t)r >> 16) & 0xffu) atomicOr(&A.ctl->err, ((uint32_t)r >> 16) & 0xffu);
+#pragma unroll
+		for (int a = 0; a < 6; ++a) dc[a] = lcs[a];
+	}
+	const uint32_t lenIncl = half_incl_scan(dlen, hl, hmask);
+	const uint32_t basePos = lenIncl - dlen, blkLen = __shfl_sync(hmask, lenIncl, 15, 16);
+	if (blkLen >= 65536u) { defer(); return; } // counts would not fit the packed scans: full-warp kernel
+	uint32_t baseCnt[6], blkCnt[6];
+#pragma unroll
+	for (int a = 0; a < 6; a += 2) {
+		const uint32_t v = dc[a] | (dc[a + 1] << 16);
+		const uint32_t x = half_incl_scan(v, hl, hmask);
+		const uint32_t ex = x - v, t = __shfl_sync(hmask, x, 15, 16);
+		baseCnt[a] = ex & 0xffffu; baseCnt[a + 1] = ex >> 16;
+		blkCnt[a] = t & 0xffffu; blkCnt[a + 1] = t >> 16;
+	}
+	const uint32_t runIncl = half_incl_scan(dnr, hl, hmask);
+	const uint32_t nRuns = __shfl_sync(hmask, runIncl, 15, 16);
+	__syncwarp(hmask); // serial lanes are done with their laneBase scratch
+	F.laneEnd[hl] = basePos + dlen; F.laneNr[hl] = dnr; F.laneFb[hl] = dfb; F.laneRunPre[hl] = runIncl - dnr;
+#pragma unroll
+	for (int a = 0; a < 6; ++a) F.laneBase[hl * 7 + a] = baseCnt[a];
+	__syncwarp(hmask);
+
+	// ---- locate record `hl` ----------------------------------------------------------------
+	uint32_t P = 0, a = 0, cnt = 0, bpq = 0, off = 0, len = 0, sym = 0, pos = 0, s = 0, e = 0;
+	if (act) {
+		P = (uint32_t)(recP - m.blkStart);
+		a = recSC & 7u; cnt = recSC >> 3;
+		uint32_t lo = 0, hi = 15;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.laneEnd[mid] >= P) hi = mid; else lo = mid + 1; }
+		const uint32_t t = lo;
+		pos = t ? F.laneEnd[t - 1] : 0;
+		uint32_t ca = F.laneBase[t * 7 + a];
+		const uint32_t nrt = F.laneNr[t];
+		uint32_t q = 0, nb;
+		if (((pureMask >> t) & 1u) && P > 0) {
+			const uint32_t *tw = reinterpret_cast<const uint32_t*>(img) + t * 8;
+			const uint32_t prel = P - pos;
+			const uint32_t tlo = a < 4 ? 1u << (8 * a) : 0u, thi = a >= 4 ? 1u << (8 * (a - 4)) : 0u;
+			uint32_t acc = 0, idx = 0;
+#pragma unroll 1
+			for (int j = 0; j < 8; ++j) {
+				uint32_t wj = tw[j];
+				if (t == 0 && j == 0) wj &= 0xffff0000u;
+				const uint32_t lens = (wj >> 3) & 0x0f0f0f0fu;
+				const uint32_t sy = wj & 0x07070707u;
+				const uint32_t tt = sy | (sy >> 4);
+				const uint32_t wt = __byte_perm(tlo, thi, (tt & 0xffu) | ((tt >> 8) & 0xff00u));
+				const uint32_t wsum = __dp4a(lens, 0x01010101u, 0u);
+				if (acc + wsum >= prel) {
+					const uint32_t pre = lens * 0x01010101u;
+					int i = 0;
+#pragma unroll
+					for (int x = 2; x >= 0; --x) if (acc + ((pre >> (8 * x)) & 0xffu) < prel) { i = x + 1; break; }
+					idx = 4 * j + i;
+					len = (lens >> (8 * i)) & 0xffu; sym = (sy >> (8 * i)) & 7u;
+					const uint32_t before = i ? (1u << (8 * i)) - 1u : 0u;
+					ca += __dp4a(lens & before, wt, 0u);
+					pos += acc + ((pre >> (8 * i)) & 0xffu) - len;
+					break;
+				}
+				acc += wsum; ca += __dp4a(lens, wt, 0u);
+			}
+			q = idx - F.laneFb[t];
+			bpq = t * 32 + idx;
+		} else {
+			bpq = t * 32 + F.laneFb[t];
+			for (;; ++q) {
+				parse_run(img, bpq, sym, len, nb);
+				if (pos + len >= P || q + 1 >= nrt) break;
+				ca += sym == a ? len : 0;
+				pos += len; bpq += nb;
+			}
+		}
+		off = P - pos;
+		if (recDst != NONE32) A.gLNext[recDst] = A.ctl->cpost[a] + F.cumBase[a] + ca + (sym == a ? off : 0);
+		atomicAdd(&F.cntAdd[a], cnt);
+		s = F.laneRunPre[t] + q;
+		e = s + ((off == len && s + 1 < nRuns) ? 1 : 0);
+	}
+	// ---- groups of records with overlapping spans -----------------------------------------------
+	const uint32_t ePrev = __shfl_up_sync(hmask, e, 1, 16);
+	const bool head = act && (hl == 0 || s > ePrev);
+	const uint32_t H = (__ballot_sync(hmask, head) >> (16 * half)) & 0xffffu;
+	const uint32_t ng = __popc(H);
+	const uint32_t above = H & ~((2u << hl) - 1u);
+	const uint32_t gend = above ? (uint32_t)(__ffs(above) - 1) : nrec;
+	const uint32_t eLast = __shfl_sync(hmask, e, (gend - 1) & 15, 16);
+	const uint32_t k = __popc(H & ((1u << hl) - 1u));
+	uint8_t *ebuf = S.stage + HALF_OUT + hl * 16;
+	if (head) {
+		uint32_t o = 0, psym = 8, plen = 0;
+		uint32_t rr_ = m.r0 + hl;
+		const uint32_t rend = m.r0 + gend;
+		uint32_t nextP = P, na = a, nc = cnt;
+		uint32_t bp = bpq, p0 = pos;
+		auto flush = [&]() {
+			while (plen) {
+				const uint32_t l = plen < RB2_MAXRUN ? plen : RB2_MAXRUN;
+				o += enc_run(ebuf + o, psym, l);
+				plen -= l;
+			}
+		};
+		auto emit = [&](uint32_t sy, uint32_t l) {
+			if (l == 0) return;
+			if (sy != psym) { flush(); psym = sy; }
+			plen += l;
+		};
+		auto next_rec = [&]() {
+			++rr_;
+			if (rr_ < rend) { nextP = (uint32_t)(A.recP[rr_] - m.blkStart); const uint32_t sc = A.recSC[rr_]; na = sc & 7u; nc = sc >> 3; }
+		};
+		for (uint32_t g = s; g <= eLast; ++g) {
+			uint32_t sy, rl, nb;
+			parse_run(img, bp, sy, rl, nb);
+			bp += nb;
+			const uint32_t end = p0 + rl;
+			uint32_t cur = p0;
+			while (rr_ < rend && nextP < end) {
+				if (nextP > cur) { emit(sy, nextP - cur); cur = nextP; }
+				emit(na, nc);
+				next_rec();
+			}
+			emit(sy, end - cur);
+			p0 = end;
+		}
+		while (rr_ < rend) { emit(na, nc); next_rec(); }
+		flush();
+		F.eStart[k] = bpq; F.eEnd[k] = bp; F.eNew[k] = o;
+	}
+	__syncwarp(hmask);
+	// ---- output geometry ---------------------------------------------------------------
+	int32_t delta = 0;
+	if ((uint32_t)hl < ng) delta = (int32_t)F.eNew[hl] - (int32_t)(F.eEnd[hl] - F.eStart[hl]);
+	const int32_t dIncl = half_incl_scan(delta, hl, hmask);
+	if ((uint32_t)hl < ng) F.eCum[hl] = dIncl - delta;
+	const int32_t totalDelta = __shfl_sync(hmask, dIncl, 15, 16);
+	if (hl == 0) F.eCum[ng] = totalDelta;
+	__syncwarp(hmask);
+	const uint32_t outEnd = endBp + totalDelta, outBytes = outEnd - 2;
+	const uint32_t bp0 = hl * 32;
+	uint32_t kA = 0;
+	{ uint32_t lo = 0, hi = ng; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.eStart[mid] <= bp0) lo = mid + 1; else hi = mid; } kA = lo; }
+	const bool insideFirst = kA && bp0 < F.eEnd[kA - 1];
+	const bool simple = !insideFirst && (kA >= ng || F.eStart[kA] >= bp0 + 32);
+	uint32_t K = 1, cutImg = outEnd, cutLane = 16;
+	if (outBytes > RB2_FILL) {
+		K = 2;
+		uint32_t score = 0xffffffffu;
+		if (dnr) {
+			const uint32_t bpF = bp0 + dfb;
+			uint32_t kk = kA;
+			while (kk < ng && F.eStart[kk] <= bpF) ++kk;
+			const bool inside = kk && bpF < F.eEnd[kk - 1];
+			const uint32_t cand = bpF + F.eCum[kk];
+			if (!inside && cand > 2 && cand - 2 <= RB2_FILL && outEnd - cand <= RB2_FILL && cand < outEnd) {
+				const uint32_t mid = 2 + outBytes / 2;
+				score = ((cand > mid ? cand - mid : mid - cand) << 4) | hl;
+				cutImg = cand;
+			}
+		}
+		uint32_t best = score;
+#pragma unroll
+		for (int o = 8; o > 0; o >>= 1) { const uint32_t y = __shfl_xor_sync(hmask, best, o, 16); best = y < best ? y : best; }
+		if (best == 0xffffffffu) { defer(); return; } // ranks already written are idempotent
+		cutLane = best & 15;
+		cutImg = __shfl_sync(hmask, cutImg, cutLane, 16);
+	}
+	uint32_t newBase = 0;
+	if (K == 2) {
+		if (hl == 0) {
+			newBase = atomicAdd(&A.ctl->poolUsed, 1u);
+			if (newBase + 1 > A.ctl->poolCap) { atomicMin(&A.ctl->failBase, newBase); A.ctl->overflow = 1; newBase = NONE32; }
+		}
+		newBase = __shfl_sync(hmask, newBase, 0, 16);
+		if (newBase == NONE32) return; // pool exhausted: item stays unmerged, the host retries
+	}
+	// ---- per-block symbol counts -------------------------------------------------------------
+	if (K == 1) {
+		if (hl < 6) {
+			uint32_t v = 0;
+#pragma unroll
+			for (int x = 0; x < 6; ++x) if (hl == x) v = blkCnt[x];
+			A.blkCnt[(size_t)m.phys * 6 + hl] = v + F.cntAdd[hl];
+		}
+	} else {
+		const uint32_t cutPos = __shfl_sync(hmask, basePos, cutLane, 16);
+		uint32_t v0 = 0, v1 = 0;
+#pragma unroll
+		for (int x = 0; x < 6; ++x) {
+			uint32_t add0 = act && a == (uint32_t)x && P < cutPos ? cnt : 0u;
+#pragma unroll
+			for (int o = 8; o > 0; o >>= 1) add0 += __shfl_xor_sync(hmask, add0, o, 16);
+			const uint32_t before = __shfl_sync(hmask, baseCnt[x], cutLane, 16);
+			if (hl == x) { v0 = before + add0; v1 = blkCnt[x] - before + F.cntAdd[x] - add0; }
+		}
+		if (hl < 6) { A.blkCnt[(size_t)m.phys * 6 + hl] = v0; A.blkCnt[(size_t)newBase * 6 + hl] = v1; }
+	}
+	// ---- assemble: push input bytes and replacement bytes -----------------------------------------
+	uint8_t *out = S.stage;
+	if (simple) {
+		const uint32_t d0 = bp0 + (uint32_t)F.eCum[kA];
+		const uint32_t ow[8] = { o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w };
+#pragma unroll
+		for (int i = 0; i < 32; ++i) out[d0 + i] = (uint8_t)(ow[i >> 2] >> ((i & 3) * 8));
+	} else {
+		uint32_t kk = kA;
+		uint32_t curEnd = kk ? F.eEnd[kk - 1] : 0;
+		uint32_t nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;
+		uint32_t cum = (uint32_t)F.eCum[kk];
+#pragma unroll 1
+		for (int i = 0; i < 32; ++i) {
+			const uint32_t bp = bp0 + i;
+			if (bp >= nextStart) {
+				++kk;
+				curEnd = F.eEnd[kk - 1];
+				nextStart = kk < ng ? F.eStart[kk] : 0xffffffffu;
+				cum = (uint32_t)F.eCum[kk];
+			}
+			if (bp >= curEnd) out[bp + cum] = img[bp];
+		}
+	}
+	if (head) {
+		const uint32_t d0 = F.eStart[k] + (uint32_t)F.eCum[k], n = F.eNew[k];
+		for (uint32_t i = 0; i < n; ++i) out[d0 + i] = ebuf[i];
+	}
+	if (totalDelta < 0 && hl == 15) for (int32_t i = totalDelta; i < 0; ++i) out[RB2_BLK + i] = 0;
+	__syncwarp(hmask);
+	auto tail_mask = [&](uint4 v, uint32_t base, uint32_t end) -> uint4 {
+		if (base + 16 <= end) return v;
+		uint32_t x[4] = { v.x, v.y, v.z, v.w };
+		const uint32_t keep = end > base ? end - base : 0;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const uint32_t kb = keep > (uint32_t)j * 4 ? keep - j * 4 : 0;
+			x[j] = kb >= 4 ? x[j] : (kb ? x[j] & ((1u << (kb * 8)) - 1u) : 0u);
+		}
+		return make_uint4(x[0], x[1], x[2], x[3]);
+	};
+	const uint32_t end0 = K == 1 ? outEnd : cutImg;
+	uint4 a0 = reinterpret_cast<const uint4*>(out)[hl * 2], a1 = reinterpret_cast<const uint4*>(out)[hl * 2 + 1];
+	if (K == 2) { a0 = tail_mask(a0, bp0, end0); a1 = tail_mask(a1, bp0 + 16, end0); }
+	if (hl == 0) a0.x = (a0.x & 0xffff0000u) | (end0 - 2);
+	uint4 *dst0 = reinterpret_cast<uint4*>(A.pool + (size_t)m.phys * RB2_BLK);
+	dst0[hl * 2] = a0; dst0[hl * 2 + 1] = a1;
+	if (K == 2) {
+		auto fetch = [&](uint32_t src) -> uint4 {
+			const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.stage) + (src >> 2);
+			const uint32_t sh = (src & 3) * 8;
+			const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4];
+			return make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
+		};
+		const uint32_t b1 = cutImg - 2 + bp0;
+		uint4 c0 = tail_mask(fetch(b1), b1, outEnd), c1 = tail_mask(fetch(b1 + 16), b1 + 16, outEnd);
+		if (hl == 0) c0.x = (c0.x & 0xffff0000u) | (outEnd - cutImg);
+		uint4 *dst1 = reinterpret_cast<uint4*>(A.pool + (size_t)newBase * RB2_BLK);
+		dst1[hl * 2] = c0; dst1[hl * 2 + 1] = c1;
+	}
+	if (hl == 0) { A.itemPieces[w] = K; A.itemFirst[w] = m.phys; A.itemRest[w] = newBase; }
+}
+
 // Common prologue of both merge kernels: which block, which records, decode the block.
 __device__ __forceinline__ void item_prologue(const MergeArgs &A, ItemCtx &C, int lane, uint8_t *img, uint32_t *cntScratch)
 {
@@ -1140,27 +1508,34 @@ __device__ __forceinline__ void item_prologue(const MergeArgs &A, ItemCtx &C, in
 // for k_merge_general.
 __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(MergeArgs A)
 {
+	// persistent: warps pull the items k_merge_half deferred
 	extern __shared__ __align__(16) uint8_t smraw[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	ItemCtx C;
-	C.w = blockIdx.x * MERGE_WARPS + wid;
-	if (C.w >= A.ctl->nItems) return;
-	if (A.itemPieces[C.w] != 0) return; // already merged by an earlier launch (retry after pool growth)
 	FastSmem &S = reinterpret_cast<FastSmem*>(smraw)[wid];
-	bool done = false;
-	const ItemMeta m = A.itemMeta[C.w];
-	if (m.nIt == 1) { // eligibility is known before touching the block
-		// issue the record loads before the block decode so that their latency overlaps it
-		RecPre rp = { 0, 0, NONE32 };
-		if (m.r1 - m.r0 <= FAST_MAXREC && m.r0 + lane < m.r1) {
-			const uint32_t r = m.r0 + lane;
-			rp.P = A.recP[r]; rp.sc = A.recSC[r]; rp.dst = A.recDst[r];
+	const uint32_t nTodoA = A.ctl->nTodoA;
+	for (;;) {
+		uint32_t q = 0;
+		if (lane == 0) q = atomicAdd(&A.ctl->todoANext, 1u);
+		q = __shfl_sync(FULLMASK, q, 0);
+		if (q >= nTodoA) break;
+		ItemCtx C;
+		C.w = A.todoA[q];
+		bool done = false;
+		const ItemMeta m = A.itemMeta[C.w];
+		if (m.nIt == 1) { // eligibility is known before touching the block
+			// issue the record loads before the block decode so that their latency overlaps it
+			RecPre rp = { 0, 0, NONE32 };
+			if (m.r1 - m.r0 <= FAST_MAXREC && m.r0 + lane < m.r1) {
+				const uint32_t r = m.r0 + lane;
+				rp.P = A.recP[r]; rp.sc = A.recSC[r]; rp.dst = A.recDst[r];
+			}
+			if (lane < 6) S.f.cumBase[lane] = A.dir.cumCnt[(size_t)m.i * 6 + lane];
+			item_prologue(A, C, lane, S.img, S.f.laneBase);
+			if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C, rp);
 		}
-		if (lane < 6) S.f.cumBase[lane] = A.dir.cumCnt[(size_t)m.i * 6 + lane];
-		item_prologue(A, C, lane, S.img, S.f.laneBase);
-		if (C.r1 - C.r0 <= FAST_MAXREC && C.nbytes > 0) done = merge_fast(A, S, lane, C, rp);
+		if (!done && lane == 0) A.todo[atomicAdd(&A.ctl->nTodo, 1u)] = C.w;
+		__syncwarp();
 	}
-	if (!done && lane == 0) A.todo[atomicAdd(&A.ctl->nTodo, 1u)] = C.w;
 }
 
 // Persistent kernel: warps pull queued items until the queue is empty.
@@ -1285,7 +1660,7 @@ struct rb2_engine {
 	// batch scratch
 	DevBuf<uint8_t> sbuf, T, asym, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
-	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemPieces, itemFirst, itemRest, todo, scanCta;
+	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemPieces, itemFirst, itemRest, todo, todoA, scanCta;
 	DevBuf<ItemMeta> itemMeta;
 	DevBuf<int64_t> scanCta64, midTmp64;
 	DevBuf<uint32_t> midTmp;
@@ -1426,7 +1801,7 @@ static void reserve_blocks(rb2_engine *e, uint64_t blocks)
 
 static void reserve_items(rb2_engine *e, uint64_t n)
 {
-	e->itemMeta.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n); e->todo.need(n);
+	e->itemMeta.need(n); e->itemPieces.need(n); e->itemFirst.need(n); e->itemRest.need(n); e->todo.need(n); e->todoA.need(n);
 }
 
 extern "C" int rb2_device_count(void)
@@ -1457,6 +1832,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	for (int k = 0; k < 2; ++k) RB2_CUDA(cudaEventCreate(&e->evTot[k]));
 	e->pool = 0; e->blkCnt = 0; e->poolCap = 0;
 	memset(e->dir, 0, sizeof(e->dir)); e->cur = 0;
+	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
@@ -1509,7 +1885,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recSC.release(); e->recDst.release(); e->recHi.release();
-	e->itemOff.release(); e->itemMeta.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release();
+	e->itemOff.release(); e->itemMeta.release(); e->itemPieces.release(); e->itemFirst.release(); e->itemRest.release(); e->todo.release(); e->todoA.release();
 	e->scanCta.release(); e->scanCta64.release(); e->midTmp.release(); e->midTmp64.release();
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
@@ -1566,9 +1942,10 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		if (attempt == 0) ph_begin(e, PH_MERGE);
 		MergeArgs ma = { e->pool, e->blkCnt, dc, e->nlog, e->recHi.p, e->itemOff.p, e->itemMeta.p,
 		                 e->recP.p, e->recSC.p, e->recDst.p, gLNext,
-		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->todo.p, e->dctl };
-		LAUNCH(e, k_merge_fast, cdiv(maxItems, MERGE_WARPS), MERGE_WARPS * 32, MERGE_WARPS * sizeof(FastSmem), ma);
+		                 e->itemPieces.p, e->itemFirst.p, e->itemRest.p, e->todoA.p, e->todo.p, e->dctl };
+		LAUNCH(e, k_merge_half, cdiv(maxItems, MERGE_WARPS * 2), MERGE_WARPS * 32, MERGE_WARPS * 2 * sizeof(HalfSmem), ma);
 		if (attempt == 0) { ph_end(e, PH_MERGE); ph_begin(e, PH_MERGE2); }
+		LAUNCH(e, k_merge_fast, e->nSM * MERGE_MINCTA, MERGE_WARPS * 32, MERGE_WARPS * sizeof(FastSmem), ma);
 		LAUNCH(e, k_merge_general, e->nSM * 10, MERGE_WARPS * 32, MERGE_WARPS * sizeof(GenSmem), ma);
 		if (attempt == 0) ph_end(e, PH_MERGE2);
 		++e->stats.n_merge_launches;
@@ -1581,7 +1958,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		if (!h->overflow) break;
 		// pool ran out: the items that did not fit are untouched.  Grow and run them again.
 		if (attempt > 8) RB2_FATAL("block pool growth did not converge");
-		h->poolUsed = h->failBase; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
+		h->poolUsed = h->failBase; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0; h->nTodoA = 0; h->todoANext = 0;
 		reserve_blocks(e, (uint64_t)e->poolCap + e->poolCap / 2 + maxItems / 4 + 4096);
 		ctl_push(e);
 	}
@@ -1592,7 +1969,7 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 	ph_end(e, PH_DIR2);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	ph_collect(e, (1u << PH_MERGE) | (1u << PH_MERGE2) | (1u << PH_DIR) | (1u << PH_DIR2));
-	e->stats.general_items += h->nTodo;
+	e->stats.general_items += h->nTodoA;
 	e->stats.merge_blocks += nItems;
 	// every item reads one leaf block and writes it back, plus the freshly allocated pieces
 	e->stats.merge_bytes_rw += ((int64_t)nItems * 2 + (int64_t)(h->poolUsed - usedBefore)) * RB2_BLK;
@@ -1662,7 +2039,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			for (int b = 0; b < 6; ++b) { h->cpost[b] = acc; acc += e->bktLen[b] + (mBkt[b + 1] - mBkt[b]); }
 			h->cpost[6] = h->cpost[7] = acc;
 		}
-		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
+		h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0; h->nTodoA = 0; h->todoANext = 0;
 		ctl_push(e);
 
 		// ---- members: next symbol + tile histograms ---------------------------------
@@ -1907,7 +2284,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	RB2_CUDA(cudaMemcpyAsync(e->recDst.p, D.data(), k * 4, cudaMemcpyHostToDevice, e->st));
 	Ctl *h = e->hctl;
 	for (int b = 0; b < 8; ++b) { h->blkBkt[b] = e->blkBkt[b]; h->recBkt[b] = b <= bucket ? 0 : k; h->cpost[b] = 0; }
-	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0;
+	h->poolCap = e->poolCap; h->nItems = 0; h->err = 0; h->overflow = 0; h->failBase = NONE32; h->nTodo = 0; h->todoNext = 0; h->nTodoA = 0; h->todoANext = 0;
 	ctl_push(e);
 	reserve_items(e, (uint64_t)k + 2);
 	apply_records(e, k, e->dRankOut);
