@@ -58,6 +58,8 @@ typedef struct {
 	double  ms_directory;               /* item planning + directory rebuild */
 	double  ms_merge_general;           /* k_merge_general: over-full / multi-item / empty blocks */
 	int64_t general_items;              /* work items that went through k_merge_general */
+	double  ms_exchange;                /* sharded build: string-state transfer between ranks */
+	int64_t exch_bytes;                 /* sharded build: bytes of string state this rank received */
 } rb2_stats_t;
 
 int  rb2_device_count(void);
@@ -109,6 +111,30 @@ void  rb2_host_free(void *p);
 int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a, int64_t rl);
 void    rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6]);
 int64_t rb2_last_sentinel_rank(rb2_engine_t *e);
+
+/*
+ * Sharded build: ONE index spread over several GPUs.  The six buckets of the
+ * reference's worker threads (mrope.c:312-325) are cut once more by the second symbol of the suffix
+ * into 36 sub-buckets, each owned by one rank; per column the ranks all-gather the per-sub-bucket
+ * symbol counts (the cross-bucket offsets of mrope.c:332-340) and hand every string to the owner of
+ * the sub-bucket it inserts into next.
+ *
+ * Ranks are either processes (one per GPU, `nccl_uid` = 128 bytes from rb2_nccl_unique_id() on rank
+ * 0, distributed by the caller) or threads of one process (`group` from rb2_group_create()).
+ * rb2_insert_multi_sharded* is collective: every rank calls it with ITS share of the batch (len may
+ * be 0); the strings are ordered by (rank, position in the rank's buffer).  rb2_counts, rb2_reset,
+ * rb2_get_stats work as before; rb2_num_blocks / rb2_fetch_blocks address sub-bucket x*6+y (blocks
+ * exist only on its owner, rb2_shard_owner()); the whole BWT is the concatenation over sub-buckets.
+ */
+typedef struct rb2_group rb2_group_t;
+rb2_group_t *rb2_group_create(int nranks);
+void rb2_group_destroy(rb2_group_t *g);
+void rb2_nccl_unique_id(uint8_t out[128]);
+rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int rank, int nranks, rb2_group_t *group, const uint8_t *nccl_uid);
+void rb2_insert_multi_sharded(rb2_engine_t *e, int64_t len, const uint8_t *s_host);
+void rb2_insert_multi_sharded_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev);
+int  rb2_shard_owner(int nranks, int subbucket);
+int  rb2_num_buckets(const rb2_engine_t *e); /* 6, or 36 for a sharded engine */
 
 #ifdef __cplusplus
 }

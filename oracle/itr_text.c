@@ -90,3 +90,24 @@ int64_t itr_runs(void *mr, itr_first_fn first, itr_next_fn next, int to_free,
 	if (cur_c >= 0) { if (n < cap) syms[n] = (uint8_t)cur_c, lens[n] = cur_l; ++n; }
 	return n <= cap? n : -n;
 }
+
+/*
+ * Decode `n` leaf blocks laid out back to back (512 bytes each, [uint16 nbytes][runs...]) into one
+ * nt6 code per symbol.  Used for indexes that are fetched block-wise (the sharded build, whose
+ * sub-buckets live on different ranks).  Returns the number of symbols or -(needed).
+ */
+int64_t blocks_text(const uint8_t *blocks, int64_t n_blocks, uint8_t *out, int64_t cap)
+{
+	int64_t n = 0, b;
+	for (b = 0; b < n_blocks; ++b) {
+		const uint8_t *blk = blocks + b * 512;
+		const uint8_t *q = blk + 2, *end = blk + 2 + *(const uint16_t*)blk;
+		while (q < end) {
+			int c; int64_t l, j;
+			q = dec_run(q, &c, &l);
+			if (n + l <= cap) for (j = 0; j < l; ++j) out[n + j] = (uint8_t)c;
+			n += l;
+		}
+	}
+	return n <= cap? n : -n;
+}

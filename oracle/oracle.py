@@ -127,7 +127,20 @@ def _itrlib():
     L.itr_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u8p, C.c_int64, C.c_int, _i64p, _i64p]
     L.itr_runs.restype = C.c_int64
     L.itr_runs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _u8p, _i64p, C.c_int64]
+    L.blocks_text.restype = C.c_int64
+    L.blocks_text.argtypes = [_u8p, C.c_int64, _u8p, C.c_int64]
     return L
+
+
+def decode_blocks(blocks: np.ndarray, total: int) -> np.ndarray:
+    """Decode an [n, 512] uint8 array of leaf blocks (rle.h layout) into ``total`` nt6 symbols."""
+    il = _itrlib()
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+    out = np.empty(max(total, 1), dtype=np.uint8)
+    n = il.blocks_text(blocks.ctypes.data_as(_u8p), blocks.shape[0], out.ctypes.data_as(_u8p), total)
+    if n != total:
+        raise AssertionError(f"blocks decode to {n} symbols, expected {total}")
+    return out[:total]
 
 
 def decode_index(lib: C.CDLL, mr, total: int, to_free: int = 0, ascii: bool = False):

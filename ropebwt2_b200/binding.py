@@ -22,14 +22,17 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_destroy", "rb2_sorting_ord
                "rb2_insert_multi_dev", "rb2_counts", "rb2_rank2a", "rb2_num_blocks", "rb2_fetch_blocks",
                "rb2_load_blocks", "rb2_get_stats", "rb2_reset_stats", "rb2_stream", "rb2_dev_alloc",
                "rb2_dev_free", "rb2_dev_upload", "rb2_reset", "rb2_host_alloc", "rb2_host_free", "rb2_insert_run",
-               "rb2_bucket_rank2a", "rb2_last_sentinel_rank"]
+               "rb2_bucket_rank2a", "rb2_last_sentinel_rank",
+               "rb2_group_create", "rb2_group_destroy", "rb2_nccl_unique_id", "rb2_create_sharded",
+               "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets"]
 
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_strings", "n_symbols", "n_columns", "n_launches", "n_merge_launches",
                                          "merge_blocks", "merge_bytes_rw", "n_records", "pool_blocks", "pool_capacity")] + \
                [(n, C.c_double) for n in ("ms_total", "ms_h2d", "ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_directory",
-                                          "ms_merge_general")] + [("general_items", C.c_int64)]
+                                          "ms_merge_general")] + [("general_items", C.c_int64), ("ms_exchange", C.c_double),
+                                                                  ("exch_bytes", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -109,6 +112,18 @@ def load(rebuild: bool = False) -> C.CDLL:
     L.rb2_bucket_rank2a.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, _i64p, _i64p]
     L.rb2_last_sentinel_rank.restype = C.c_int64
     L.rb2_last_sentinel_rank.argtypes = [C.c_void_p]
+    L.rb2_group_create.restype = C.c_void_p
+    L.rb2_group_create.argtypes = [C.c_int]
+    L.rb2_group_destroy.argtypes = [C.c_void_p]
+    L.rb2_nccl_unique_id.argtypes = [_u8p]
+    L.rb2_create_sharded.restype = C.c_void_p
+    L.rb2_create_sharded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.rb2_insert_multi_sharded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.rb2_insert_multi_sharded_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.rb2_shard_owner.restype = C.c_int
+    L.rb2_shard_owner.argtypes = [C.c_int, C.c_int]
+    L.rb2_num_buckets.restype = C.c_int
+    L.rb2_num_buckets.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -274,3 +289,47 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+class ShardedEngine(Engine):
+    """One rank of a sharded build (one index over several GPUs, include/ropebwt2_b200.h).
+    ``group``: handle from ``local_group()`` when the ranks are threads of this process;
+    ``nccl_uid``: 128 bytes from ``nccl_unique_id()`` when they are processes (one per GPU)."""
+
+    def __init__(self, device: int, so: int, rank: int, nranks: int, group=None, nccl_uid: bytes = None):
+        self.L = load()
+        self.rank, self.nranks = rank, nranks
+        uid = (C.c_uint8 * 128).from_buffer_copy(nccl_uid) if nccl_uid is not None else None
+        self.h = self.L.rb2_create_sharded(device, so, rank, nranks, group, uid)
+
+    def insert_multi(self, buf) -> None:
+        """Collective: every rank passes its own share of the batch (may be empty)."""
+        a = np.ascontiguousarray(buf, dtype=np.uint8)
+        self.L.rb2_insert_multi_sharded(self.h, a.size, a.ctypes.data if a.size else None)
+
+    def insert_multi_ptr(self, host_ptr: int, n: int) -> None:
+        self.L.rb2_insert_multi_sharded(self.h, n, host_ptr)
+
+    def insert_multi_dev(self, dev_ptr: int, n: int) -> None:
+        self.L.rb2_insert_multi_sharded_dev(self.h, n, dev_ptr)
+
+    def owned(self):
+        return [s for s in range(36) if self.L.rb2_shard_owner(self.nranks, s) == self.rank]
+
+    def fetch_subbucket(self, s: int) -> np.ndarray:
+        n = self.L.rb2_num_blocks(self.h, s)
+        buf = np.zeros((n, 512), dtype=np.uint8)
+        if n:
+            got = self.L.rb2_fetch_blocks(self.h, s, 0, n, buf.ctypes.data_as(_u8p), None)
+            assert got == n
+        return buf
+
+
+def local_group(nranks: int):
+    return load().rb2_group_create(nranks)
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    load().rb2_nccl_unique_id(buf)
+    return bytes(buf)

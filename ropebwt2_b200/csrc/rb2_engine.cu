@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <vector>
 #include "rb2_codec.cuh"
+#include "rb2_comm.h"
 #include "../../include/ropebwt2_b200.h"
 
 #define MEM_TILE    1024   // members per CTA in the fetch / partition kernels (256 threads x 4)
@@ -47,20 +48,27 @@
 #define SMALL_GROUP 32     // groups up to this size are histogrammed by one thread
 #define NGC         13     // group-scan counters: has[6], hist[6], nrec
 
+#define NBMAX 36          // buckets: 6 (one GPU: bucket = following symbol) or 36 (sharded: sub-bucket = following two symbols)
+#define NBA   (NBMAX + 4)  // bucket-range arrays hold nb+1 boundaries plus padding
+
 struct Ctl { // device control block (one per engine), mirrored through pinned host memory
 	uint32_t poolUsed, err, nItems, nlogNew;
 	uint32_t overflow, failBase;   // pool exhausted during a merge kernel: first block id that did not fit
 	uint32_t nTodo, todoNext;     // items the fast kernel left for k_merge_general, and its work counter
 	uint32_t nTodoA, todoANext;   // items the half-warp kernel left for k_merge_fast, and its work counter
-	uint32_t blkBkt[8];     // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
-	uint32_t blkBktNew[8];
-	uint32_t gBkt[8], mBkt[8];         // this column: group / member index range per bucket
-	uint32_t gBktNext[8], mBktNext[8]; // next column
-	uint32_t recBkt[8];     // record index range per bucket (this column)
+	uint32_t nb, tables;          // number of buckets; sharded engines also fill grpPre / memPre
 	uint32_t nrec, Gnext, Mnext, poolCap;
-	int64_t  cpost[8];      // global start position of each bucket AFTER this column's insertions
+	uint32_t blkBkt[NBA];   // logical block range of bucket b: [blkBkt[b], blkBkt[b+1])
+	uint32_t blkBktNew[NBA];
+	uint32_t gBkt[NBA], mBkt[NBA];     // this column: group / member index range per bucket
+	uint32_t recBkt[NBA];   // record index range per bucket (this column)
+	uint32_t gSymBase[8], mSymBase[8]; // next column: first group / member index of the strings that insert symbol a now
+	int64_t  cpost[8];      // global start position of bucket a AFTER this column's insertions
 	uint32_t memTot[8];     // members per next symbol
 	uint32_t grpTot[16];    // grand totals of the NGC group counters
+	// sharded engines: per-symbol exclusive prefix of next groups / members at the first group of
+	// every bucket (row nb = totals); the differences of two rows are what a bucket sends on
+	uint32_t grpPre[(NBMAX + 1) * 6], memPre[(NBMAX + 1) * 6];
 };
 
 struct Dir {
@@ -171,7 +179,23 @@ __global__ void k_init_state(int sorted, uint32_t m, int64_t n0, int64_t *gL, in
 // Members: fetch the next symbol of every live string; stable 6-way partition
 // =====================================================================================
 
-__global__ void __launch_bounds__(256) k_member_fetch(const uint8_t *Tcol, const uint32_t *sid, uint32_t M, uint8_t *asym, uint32_t *tileTot)
+// The column-major symbol matrix of a batch.  A sharded build keeps one matrix per rank (the rank's
+// own strings), replicated on every GPU; string ids are global, rank r owns [off[r], off[r+1]).
+#define TV_MAX 8
+struct TView { int n; uint32_t off[TV_MAX + 1]; const uint8_t *col[TV_MAX]; }; // col[r] = rank r's current column
+
+__device__ __forceinline__ uint32_t tview_fetch(const TView &tv, uint32_t id)
+{
+	int r = 0;
+#pragma unroll
+	for (int x = 1; x < TV_MAX; ++x) r += x < tv.n && id >= tv.off[x];
+	const uint8_t *c = tv.col[0]; uint32_t o = tv.off[0];
+#pragma unroll
+	for (int x = 1; x < TV_MAX; ++x) if (r == x) { c = tv.col[x]; o = tv.off[x]; }
+	return c[id - o];
+}
+
+__global__ void __launch_bounds__(256) k_member_fetch(const TView tv, const uint32_t *sid, uint32_t M, uint8_t *asym, uint32_t *tileTot)
 {
 	__shared__ uint32_t sm[6 * 8];
 	const uint32_t k = blockIdx.x * MEM_TILE + threadIdx.x * 4;
@@ -184,7 +208,7 @@ __global__ void __launch_bounds__(256) k_member_fetch(const uint8_t *Tcol, const
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			if (k + i < M) {
-				uint32_t a = Tcol[id[i]];
+				uint32_t a = tv.n == 1 ? tv.col[0][id[i]] : tview_fetch(tv, id[i]);
 				packed |= a << (8 * i);
 #pragma unroll
 				for (int x = 0; x < 6; ++x) c[x] += a == x;
@@ -227,7 +251,7 @@ __global__ void __launch_bounds__(256) k_partition(const uint32_t *sid, const ui
 	if (k < M) {
 		uint32_t base[6];
 #pragma unroll
-		for (int x = 0; x < 6; ++x) base[x] = ctl->mBktNext[x] + tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
+		for (int x = 0; x < 6; ++x) base[x] = ctl->mSymBase[x] + tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
 		for (int i = 0; i < 4; ++i) if (k + i < M) {
 			uint32_t a = (a4 >> (8 * i)) & 0xff;
 			uint32_t d = 0;
@@ -260,6 +284,13 @@ __device__ void warp_rank6(const uint8_t *pool, Dir dir, uint32_t nlog, int64_t 
 {
 	uint32_t i = find_block(dir.cumLen, 0, nlog - 1, x);
 	if (i >= nlog) i = nlog - 1;
+	// x at the very end of block i: the answer is the directory entry of block i+1.  In a sharded
+	// engine this also steps over the symbols that other ranks hold between the two blocks.
+	if (i + 1 < nlog && x >= dir.cumLen[i + 1]) {
+#pragma unroll
+		for (int a = 0; a < 6; ++a) out[a] = dir.cumCnt[(size_t)(i + 1) * 6 + a];
+		return;
+	}
 	const uint32_t xrel = (uint32_t)(x - dir.cumLen[i]);
 	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes; uint4 own;
 	warp_decode_block(pool + (size_t)dir.order[i] * RB2_BLK, lane, img, cntScratch, d, basePos, baseCnt, blkLen, blkCnt, nbytes, err, own);
@@ -380,7 +411,8 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 {
 	__shared__ uint32_t sm[NGC * 8];
 	__shared__ uint64_t sm64[3 * 8];
-	__shared__ uint32_t sCtl[24]; // [0,8) gBktNext, [8,16) mBktNext, [16,22) bucket starts inside this CTA, [22] any, [23] member base
+	__shared__ uint32_t sCtl[24]; // [0,8) gSymBase, [8,16) mSymBase, [21] a bucket starts inside this CTA, [22] all singletons, [23] member base
+	__shared__ uint32_t sBkt[NBA]; // first group of bucket b if it lies inside this CTA
 	const int lane = threadIdx.x & 31;
 	const uint32_t g0 = blockIdx.x * 256, g = g0 + threadIdx.x;
 	const bool valid = g < A.G;
@@ -391,10 +423,17 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 		sCtl[22] = A.gOff[g0 + nv] - mb == nv; // every group of this CTA is a singleton
 	}
 	if (MODE == 1) {
-		if (threadIdx.x < 8) { sCtl[threadIdx.x] = A.ctl->gBktNext[threadIdx.x]; sCtl[8 + threadIdx.x] = A.ctl->mBktNext[threadIdx.x]; }
-		if (threadIdx.x >= 32 && threadIdx.x < 38) {
-			const uint32_t gb = A.ctl->gBkt[threadIdx.x - 32];
-			sCtl[16 + threadIdx.x - 32] = gb >= g0 && gb < g0 + 256 ? gb : NONE32;
+		if (threadIdx.x < 8) { sCtl[threadIdx.x] = A.ctl->gSymBase[threadIdx.x]; sCtl[8 + threadIdx.x] = A.ctl->mSymBase[threadIdx.x]; }
+		if (threadIdx.x >= 32 && threadIdx.x < 96) { // two warps cover up to 64 buckets
+			const uint32_t b = threadIdx.x - 32;
+			bool in = false;
+			if (b < A.ctl->nb) {
+				const uint32_t gb = A.ctl->gBkt[b];
+				in = gb >= g0 && gb < g0 + 256;
+				sBkt[b] = in ? gb : NONE32;
+			}
+			const uint32_t any = __ballot_sync(FULLMASK, in);
+			if (lane == 0) sCtl[20 + (b >> 5)] = any != 0; // [20], [21]
 		}
 	}
 	__syncthreads();
@@ -457,8 +496,16 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 #pragma unroll
 	for (int k = 0; k < NGC; ++k) v[k] += A.ctaTot[(size_t)blockIdx.x * NGC + k];
 	// records of bucket b start at the record prefix of the bucket's first group
+	if (sCtl[20] | sCtl[21]) {
+		const uint32_t nb = A.ctl->nb, tables = A.ctl->tables;
+		for (uint32_t b = 0; b < nb; ++b) if (g == sBkt[b]) {
+			A.ctl->recBkt[b] = v[12];
+			if (tables) {
 #pragma unroll
-	for (int b = 0; b < 6; ++b) if (g == sCtl[16 + b]) A.ctl->recBkt[b] = v[12];
+				for (int a = 0; a < 6; ++a) { A.ctl->grpPre[b * 6 + a] = v[a]; A.ctl->memPre[b * 6 + a] = v[6 + a]; }
+			}
+		}
+	}
 	const bool useSizes = A.sizes6 != 0;
 	const bool nonempty = useSizes && A.gSize[g] > 0;
 	int64_t P = A.gL[g];
@@ -490,14 +537,18 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 __global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
 {
 	uint32_t g = 0, m = 0, bad = 0;
-	ctl->gBktNext[0] = 0; ctl->mBktNext[0] = 0;
+	ctl->gSymBase[0] = 0; ctl->mSymBase[0] = 0;
 	for (int a = 1; a <= 6; ++a) {
-		ctl->gBktNext[a] = g; ctl->mBktNext[a] = m;
+		ctl->gSymBase[a] = g; ctl->mSymBase[a] = m;
 		if (a < 6) { g += ctl->grpTot[a]; m += ctl->grpTot[6 + a]; bad |= ctl->grpTot[6 + a] != ctl->memTot[a]; }
 	}
-	ctl->gBktNext[7] = g; ctl->mBktNext[7] = m;
+	ctl->gSymBase[7] = g; ctl->mSymBase[7] = m;
 	ctl->Gnext = g; ctl->Mnext = m; ctl->nrec = ctl->grpTot[12];
-	for (int b = 0; b < 8; ++b) ctl->recBkt[b] = ctl->grpTot[12];
+	// buckets whose first group is never visited (empty buckets at the very end) start at the totals
+	for (uint32_t b = 0; b < ctl->nb + 2; ++b) ctl->recBkt[b] = ctl->grpTot[12];
+	if (ctl->tables)
+		for (uint32_t b = 0; b <= ctl->nb; ++b)
+			for (int a = 0; a < 6; ++a) { ctl->grpPre[b * 6 + a] = ctl->grpTot[a]; ctl->memPre[b * 6 + a] = ctl->grpTot[6 + a]; }
 	gOffNext[g] = m;
 	if (bad) ctl->err |= RB2_ERR_ORDER;
 }
@@ -511,20 +562,23 @@ __global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
 __global__ void k_col_bases_single(Ctl *ctl, uint32_t *gOffNext, uint32_t M)
 {
 	uint32_t m = 0;
-	ctl->gBktNext[0] = 0; ctl->mBktNext[0] = 0;
+	ctl->gSymBase[0] = 0; ctl->mSymBase[0] = 0;
 	for (int a = 1; a <= 6; ++a) {
-		ctl->gBktNext[a] = m; ctl->mBktNext[a] = m;
+		ctl->gSymBase[a] = m; ctl->mSymBase[a] = m;
 		if (a < 6) m += ctl->memTot[a];
 	}
-	ctl->gBktNext[7] = m; ctl->mBktNext[7] = m;
+	ctl->gSymBase[7] = m; ctl->mSymBase[7] = m;
 	ctl->Gnext = m; ctl->Mnext = m; ctl->nrec = M;
-	for (int b = 0; b < 8; ++b) ctl->recBkt[b] = ctl->mBkt[b]; // one record per member, same order
+	for (uint32_t b = 0; b < ctl->nb + 2; ++b) ctl->recBkt[b] = ctl->mBkt[b]; // one record per member, same order
+	if (ctl->tables)
+		for (uint32_t b = 0; b <= ctl->nb; ++b)
+			for (int a = 0; a < 6; ++a) ctl->memPre[b * 6 + a] = ctl->memTot[a];
 	gOffNext[m] = m;
 }
 
 struct SingleArgs {
 	const uint32_t *sid; const uint8_t *asym; uint32_t M; const uint32_t *tilePre;
-	const int64_t *gL, *gSize, *sizes6; const Ctl *ctl;
+	const int64_t *gL, *gSize, *sizes6; Ctl *ctl;
 	uint32_t *sidNext; int64_t *gSizeNext; uint32_t *gOffNext;
 	int64_t *recP; uint32_t *recSC, *recDst;
 };
@@ -533,9 +587,20 @@ template <bool COMP>
 __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 {
 	__shared__ uint32_t sm[6 * 8];
+	__shared__ uint32_t sBkt[NBA], sAny;
 	const uint32_t k = blockIdx.x * MEM_TILE + threadIdx.x * 4;
 	uint32_t a4 = 0, id[4] = { 0, 0, 0, 0 };
 	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 }, tot[6];
+	if (A.ctl->tables) { // sharded engines: which buckets start inside this tile
+		if (threadIdx.x == 0) sAny = 0;
+		__syncthreads();
+		if (threadIdx.x < A.ctl->nb) {
+			const uint32_t mb = A.ctl->mBkt[threadIdx.x];
+			const bool in = mb >= blockIdx.x * MEM_TILE && mb < (blockIdx.x + 1) * MEM_TILE && mb < A.M;
+			sBkt[threadIdx.x] = in ? mb : NONE32;
+			if (in) sAny = 1;
+		}
+	} else if (threadIdx.x == 0) sAny = 0;
 	if (k < A.M) {
 		a4 = *reinterpret_cast<const uint32_t*>(A.asym + k);
 		for (int i = 0; i < 4; ++i) if (k + i < A.M) {
@@ -549,13 +614,22 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 	if (k >= A.M) return;
 	uint32_t base[6];
 #pragma unroll
-	for (int x = 0; x < 6; ++x) base[x] = A.ctl->mBktNext[x] + A.tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
+	for (int x = 0; x < 6; ++x) base[x] = A.ctl->mSymBase[x] + A.tilePre[(size_t)blockIdx.x * 6 + x] + c[x];
 	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
+	const bool marks = sAny != 0; // (written before the scan's barriers)
 	for (int i = 0; i < 4; ++i) if (k + i < A.M) {
 		const uint32_t g = k + i, a = (a4 >> (8 * i)) & 0xff;
+		if (marks) {
+			const uint32_t nb = A.ctl->nb;
+			for (uint32_t b = 0; b < nb; ++b) if (g == sBkt[b]) {
+#pragma unroll
+				for (int x = 0; x < 6; ++x) A.ctl->memPre[b * 6 + x] = base[x] - A.ctl->mSymBase[x];
+			}
+		}
 		uint32_t d = NONE32;
 #pragma unroll
 		for (int x = 1; x < 6; ++x) if (a == x) d = base[x]++;
+		if (a == 0) ++base[0]; // only the bucket-start prefixes of a sharded engine look at it
 		int64_t P = A.gL[g], sza = 0;
 		if (A.sizes6 && A.gSize[g] > 0) { // insertion point: behind the old symbols of the earlier slots
 #pragma unroll
@@ -578,12 +652,19 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 // Blocks: plan work items, merge records into leaf blocks, rebuild the directory
 // =====================================================================================
 
-__device__ __forceinline__ int bucket_of(const uint32_t *bkt, uint32_t i)
+// bucket of logical block i: the last b with bkt[b] <= i (empty buckets share their start with the
+// next non-empty one, which is the one that is found)
+__device__ __forceinline__ int bucket_of(const uint32_t *bkt, uint32_t nb, uint32_t i)
 {
-	int b = 0;
+	if (nb == 6) {
+		int b = 0;
 #pragma unroll
-	for (int x = 1; x < 6; ++x) b += i >= bkt[x];
-	return b;
+		for (int x = 1; x < 6; ++x) b += i >= bkt[x];
+		return b;
+	}
+	uint32_t lo = 0, hi = nb - 1;
+	while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (bkt[mid] <= i) lo = mid; else hi = mid - 1; }
+	return (int)lo;
 }
 
 // recHi[i] = #records (global index) at positions <= end of logical block i, inside the
@@ -593,7 +674,7 @@ __global__ void __launch_bounds__(256) k_rec_hi(Dir dir, uint32_t nlog, const Ct
 {
 	const uint32_t i = blockIdx.x * 256 + threadIdx.x;
 	if (i >= nlog) return;
-	const int b = bucket_of(ctl->blkBkt, i);
+	const int b = bucket_of(ctl->blkBkt, ctl->nb, i);
 	uint32_t lo = ctl->recBkt[b], hi = ctl->recBkt[b + 1];
 	if (i + 1 != ctl->blkBkt[b + 1]) {
 		const int64_t key = dir.cumLen[i + 1];
@@ -616,7 +697,7 @@ struct ItemScan { // K=1: work items per logical block
 	uint32_t *itemOff; ItemMeta *itemMeta; Ctl *ctlw;
 	const uint32_t *order; const int64_t *cumLen;
 	__device__ uint32_t rec_lo(uint32_t i) const {
-		const int b = bucket_of(ctl->blkBkt, i);
+		const int b = bucket_of(ctl->blkBkt, ctl->nb, i);
 		return i == ctl->blkBkt[b] ? ctl->recBkt[b] : recHi[i - 1];
 	}
 	__device__ void load(uint64_t i, uint32_t (&v)[1]) const {
@@ -1574,15 +1655,26 @@ struct RebuildScan { // K=1: pieces per old logical block -> new logical order
 			orderNew[o++] = itemFirst[it];
 			for (uint32_t k = 1; k < itemPieces[it]; ++k) orderNew[o++] = itemRest[it] + (k - 1);
 		}
+		const uint32_t nb = ctl->nb;
+		if (nb == 6) {
 #pragma unroll
-		for (int b = 0; b < 6; ++b) if (i == ctl->blkBkt[b]) ctlw->blkBktNew[b] = pre[0];
-		if (i + 1 == nlog) { ctlw->nlogNew = pre[0] + own[0]; ctlw->blkBktNew[6] = pre[0] + own[0]; ctlw->blkBktNew[7] = pre[0] + own[0]; }
+			for (int b = 0; b < 6; ++b) if (i == ctl->blkBkt[b]) ctlw->blkBktNew[b] = pre[0];
+		} else if (i == 0 || bucket_of(ctl->blkBkt, nb, (uint32_t)i) != bucket_of(ctl->blkBkt, nb, (uint32_t)i - 1)) {
+			for (uint32_t b = 0; b < nb; ++b) if (i == ctl->blkBkt[b]) ctlw->blkBktNew[b] = pre[0];
+		}
+		if (i + 1 == nlog) {
+			ctlw->nlogNew = pre[0] + own[0];
+			for (uint32_t b = 0; b < nb + 2; ++b) if (b >= nb || ctl->blkBkt[b] >= nlog) ctlw->blkBktNew[b] = pre[0] + own[0];
+		}
 	}
 };
 
 struct DirScan { // K=7 (int64): per-symbol counts + length of every logical block -> cumCnt / cumLen
 	const uint32_t *order, *blkCnt; uint32_t nlog;
 	int64_t *cumLen, *cumCnt;
+	// sharded engines: off[b][0..5] / off[b][6] = symbols of the index that sit in front of bucket b on
+	// OTHER ranks (counts / length), so that the directory is in whole-index coordinates
+	const int64_t *off; const uint32_t *bkt; uint32_t nb;
 	__device__ void load(uint64_t i, int64_t (&v)[7]) const {
 		const uint32_t *c = blkCnt + (size_t)order[i] * 6;
 		int64_t t = 0;
@@ -1591,13 +1683,19 @@ struct DirScan { // K=7 (int64): per-symbol counts + length of every logical blo
 		v[6] = t;
 	}
 	__device__ void store(uint64_t i, const int64_t (&own)[7], const int64_t (&pre)[7]) const {
+		int64_t o[7] = { 0, 0, 0, 0, 0, 0, 0 };
+		if (off) {
+			const int64_t *ob = off + (size_t)bucket_of(bkt, nb, (uint32_t)i) * 7;
 #pragma unroll
-		for (int a = 0; a < 6; ++a) cumCnt[i * 6 + a] = pre[a];
-		cumLen[i] = pre[6];
+			for (int a = 0; a < 7; ++a) o[a] = ob[a];
+		}
+#pragma unroll
+		for (int a = 0; a < 6; ++a) cumCnt[i * 6 + a] = pre[a] + o[a];
+		cumLen[i] = pre[6] + o[6];
 		if (i + 1 == nlog) {
 #pragma unroll
-			for (int a = 0; a < 6; ++a) cumCnt[(i + 1) * 6 + a] = pre[a] + own[a];
-			cumLen[i + 1] = pre[6] + own[6];
+			for (int a = 0; a < 6; ++a) cumCnt[(i + 1) * 6 + a] = pre[a] + own[a] + o[a];
+			cumLen[i + 1] = pre[6] + own[6] + o[6];
 		}
 	}
 };
@@ -1645,7 +1743,7 @@ template <typename T> struct DevBuf {
 	void release() { if (p) RB2_CUDA(cudaFree(p)); p = 0; cap = 0; }
 };
 
-enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_MERGE2, PH_N };
+enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_MERGE2, PH_EXCH, PH_N };
 
 struct rb2_engine {
 	int dev, so, nSM;
@@ -1653,7 +1751,14 @@ struct rb2_engine {
 	// leaf block pool + directory
 	uint8_t *pool; uint32_t *blkCnt; uint32_t poolCap;
 	Dir dir[2]; int cur;
-	uint32_t nlog; uint32_t blkBkt[8];
+	uint32_t nlog; uint32_t blkBkt[NBA];
+	int nb;             // 6 (bucket = following symbol) or 36 (sharded: following two symbols)
+	// sharded build (rb2_shard.inl): my rank, the exchange layer, the owner of every sub-bucket, the
+	// whole-index symbol totals of all sub-buckets (identical on every rank), directory offsets
+	int rank, nranks; Comm *comm; int owner[NBMAX];
+	int64_t gtot[NBMAX][6];
+	int64_t *dDirOff, *hDirOff;
+	uint32_t *hPlan; DevBuf<uint32_t> plan;
 	int64_t tot[6][6]; int64_t bktLen[6];
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
 	int64_t *dRankOut, *hRankOut;
@@ -1737,10 +1842,13 @@ static void ctl_push(rb2_engine *e)
 }
 
 // rebuild cumLen/cumCnt of the current directory from blkCnt + order
-static void rebuild_directory(rb2_engine *e)
+static void rebuild_directory(rb2_engine *e, bool afterMerge)
 {
 	Dir &d = e->dir[e->cur];
-	DirScan f = { d.order, e->blkCnt, e->nlog, d.cumLen, d.cumCnt };
+	// a sharded engine adds the symbols other ranks hold in front of each of its sub-buckets; right
+	// behind a merge the device control block holds the new block ranges in blkBktNew
+	DirScan f = { d.order, e->blkCnt, e->nlog, d.cumLen, d.cumCnt, e->comm ? e->dDirOff : (const int64_t*)0,
+	              afterMerge ? e->dctl->blkBktNew : e->dctl->blkBkt, (uint32_t)e->nb };
 	run_scan<7, int64_t, DirScan>(e, f, e->nlog, e->scanCta64, (int64_t*)0, e->midTmp64);
 }
 
@@ -1821,6 +1929,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	rb2_engine *e = new rb2_engine();
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
+	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->hPlan = 0;
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
 	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
@@ -1842,26 +1951,29 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
 	LAUNCH(e, k_fill_u32, 1, 32, 0, e->dir[0].order, 6u, 0u, 1u);
 	e->nlog = 6;
-	for (int b = 0; b < 8; ++b) e->blkBkt[b] = b < 6 ? b : 6;
+	for (int b = 0; b < NBA; ++b) e->blkBkt[b] = b < 6 ? b : 6;
+	e->nb = 6; e->hctl->nb = 6; e->hctl->tables = 0;
 	e->hctl->poolUsed = 6; e->hctl->poolCap = e->poolCap;
 	ctl_push(e);
-	rebuild_directory(e);
+	rebuild_directory(e, false);
 	pull_totals(e);
 	return e;
 }
 
 // Empty the index but keep every allocation (bench steps and tests reuse one engine).
+static void shard_reset_index(rb2_engine *e);
 extern "C" void rb2_reset(rb2_engine_t *e)
 {
 	RB2_CUDA(cudaSetDevice(e->dev));
+	if (e->comm) { shard_reset_index(e); return; }
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
 	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
 	LAUNCH(e, k_fill_u32, 1, 32, 0, e->dir[e->cur].order, 6u, 0u, 1u);
 	e->nlog = 6;
-	for (int b = 0; b < 8; ++b) e->blkBkt[b] = b < 6 ? b : 6;
+	for (int b = 0; b < NBA; ++b) e->blkBkt[b] = b < 6 ? b : 6;
 	e->hctl->poolUsed = 6; e->hctl->poolCap = e->poolCap; e->hctl->err = 0;
 	ctl_push(e);
-	rebuild_directory(e);
+	rebuild_directory(e, false);
 	pull_totals(e);
 	e->stats.pool_blocks = 6;
 }
@@ -1890,6 +2002,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
+	if (e->comm) { delete e->comm; RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
 	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);
 	RB2_CUDA(cudaStreamDestroy(e->st));
@@ -1903,7 +2016,7 @@ static inline void ph_end(rb2_engine *e, int p) { RB2_CUDA(cudaEventRecord(e->ev
 static void ph_collect(rb2_engine *e, uint32_t mask)
 {
 	double *acc[PH_N] = { &e->stats.ms_h2d, &e->stats.ms_transpose, &e->stats.ms_members, &e->stats.ms_groups, &e->stats.ms_merge,
-	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members, &e->stats.ms_merge_general };
+	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members, &e->stats.ms_merge_general, &e->stats.ms_exchange };
 	for (int p = 0; p < PH_N; ++p) if (mask >> p & 1) {
 		float ms = 0;
 		RB2_CUDA(cudaEventElapsedTime(&ms, e->ev[p][0], e->ev[p][1]));
@@ -1963,9 +2076,9 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 		ctl_push(e);
 	}
 	e->nlog = h->nlogNew;
-	for (int b = 0; b < 8; ++b) e->blkBkt[b] = h->blkBktNew[b];
+	for (int b = 0; b < e->nb + 2; ++b) e->blkBkt[b] = h->blkBktNew[b];
 	e->cur ^= 1;
-	rebuild_directory(e);
+	rebuild_directory(e, true);
 	ph_end(e, PH_DIR2);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	ph_collect(e, (1u << PH_MERGE) | (1u << PH_MERGE2) | (1u << PH_DIR) | (1u << PH_DIR2));
@@ -2047,7 +2160,9 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const uint32_t nTile = cdiv(M, MEM_TILE);
 		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
 		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
-		LAUNCH(e, k_member_fetch, nTile, 256, 0, e->T.p + (size_t)col * m, e->sid[cs].p, M, e->asym.p, e->tileB.p);
+		TView tv; memset(&tv, 0, sizeof(tv));
+		tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * m;
+		LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, e->asym.p, e->tileB.p);
 		run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 		ph_end(e, PH_MEMBERS);
 
@@ -2097,7 +2212,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 
 		// ---- advance to the next column ---------------------------------------------
 		for (int b = 0; b < 6; ++b) e->bktLen[b] += mBkt[b + 1] - mBkt[b];
-		for (int b = 0; b < 8; ++b) { gBkt[b] = h->gBktNext[b]; mBkt[b] = h->mBktNext[b]; }
+		for (int b = 0; b < 8; ++b) { gBkt[b] = h->gSymBase[b]; mBkt[b] = h->mSymBase[b]; }
 		G = h->Gnext; M = h->Mnext;
 		cs ^= 1;
 	}
@@ -2174,7 +2289,7 @@ extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6],
 
 extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)
 {
-	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
+	if (bucket < 0 || bucket >= e->nb) RB2_FATAL("bucket out of range");
 	return (int64_t)e->blkBkt[bucket + 1] - e->blkBkt[bucket];
 }
 
@@ -2227,7 +2342,7 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 	e->hctl->poolUsed = used + (uint32_t)n;
 	e->hctl->poolCap = e->poolCap;
 	ctl_push(e);
-	rebuild_directory(e);
+	rebuild_directory(e, false);
 	pull_totals(e);
 	e->stats.pool_blocks = e->hctl->poolUsed;
 	e->stats.pool_capacity = e->poolCap;
@@ -2255,6 +2370,8 @@ extern "C" void rb2_dev_upload(rb2_engine_t *e, void *dst, const void *src, int6
 	RB2_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 }
+
+#include "rb2_shard.inl"
 
 // ---- single-run and bucket-local entry points behind rope.h ---------------------------------
 
