@@ -3,14 +3,16 @@
 
 Workload (BASELINE.json configs[1]): 100 M x 101 bp synthetic uniform reads, forward strand,
 RLO (`ropebwt2 -LRs`), one batch into an empty index, on one B200.  A "step" is one
-mr_insert_multi call over that batch.  Per GPU count N every rank builds the BWT of its own
-read shard of the same size (replicas, weak scaling; see DESIGN.md section "Multi-GPU").
+mr_insert_multi call over that batch.  With N > 1 GPUs the ranks build ONE index of N x 100 M reads
+together (sharded build: 36 sub-buckets spread over the ranks, one count all-gather and one
+string-state exchange per column over NCCL): per-GPU work is fixed, so the
+scaling is "weak".  `--layout replicas` runs N independent indexes instead (no exchange).
 
   value   device-resident input (rb2_insert_multi_dev), timed with CUDA events on the engine's
           stream around the whole call, max over ranks
   e2e     the reference-facing call (mr_insert_multi through the C-ABI) on a pinned HOST buffer:
           H2D copy of the batch and D2H of the symbol counts inside the timed region
-  roofline  k_merge_fast (dominant kernel): algorithmic leaf-block bytes read+written per
+  roofline  k_merge_half (dominant kernel): algorithmic leaf-block bytes read+written per
           launch / its CUDA-event time, against the measured HBM copy bandwidth
   cpu_baseline  the unmodified reference binary (oracle/_ref/ropebwt2 -LRs) on a bounded sample
 
@@ -48,6 +50,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=2)
     ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="reads in the bounded CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1: one index sharded over all GPUs (default) or one independent index per GPU")
     return ap.parse_args()
 
 
@@ -194,11 +198,17 @@ def main():
     hptr = L.rb2_host_alloc(nbytes)
     host = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hptr))
     fill_batch(host, n, ln, shard_seed(args.seed, rank))
-    eng = Engine(local, 1)
+    sharded = world > 1 and args.layout == "sharded"
+    if sharded:
+        # one index over all ranks: the library's own NCCL communicator, unique id handed out through torch.distributed
+        from ropebwt2_b200.binding import ShardedEngine, nccl_unique_id
+        from ropebwt2_b200.dist import broadcast_bytes
+        eng = ShardedEngine(local, 1, rank, world, nccl_uid=broadcast_bytes(nccl_unique_id() if rank == 0 else None))
+    else:
+        eng = Engine(local, 1)
     dptr = eng.dev_alloc(nbytes)
     eng.dev_upload(dptr, host)
     os.environ["RB2_DEVICE"] = str(local)
-    mr = MRope(1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -224,32 +234,49 @@ def main():
     st = eng.stats()
     ms_value = max_over_ranks(st["ms_total"])
     counts = eng.counts()
-    ok = int(counts.sum()) == nbytes and int(counts[:, 0].sum()) == n
+    n_idx = world if sharded else 1  # strings in the index this rank sees
+    ok = int(counts.sum()) == nbytes * n_idx and int(counts[:, 0].sum()) == n * n_idx
     if not ok:
         raise SystemExit("symbol conservation violated: the index does not hold the batch")
     eng.dev_free(dptr)
-    eng.close()
 
-    # ---- e2e leg: mr_insert_multi on the pinned host buffer, counts read back --------------
-    def e2e_step():
-        L.rb2_reset(mr.engine_handle)
-        mr.L.mr_insert_multi(mr.h, nbytes, C.cast(hptr, C.POINTER(C.c_uint8)), 1)
-        return int(mr.counts().sum())
+    # ---- e2e leg: the public host-buffer call on the pinned batch, counts read back ----------
+    if sharded:
+        def e2e_step():
+            eng.reset()
+            eng.insert_multi_ptr(hptr, nbytes)
+            return int(eng.counts().sum())
+        e2e_stats, e2e_reset_stats = eng.stats, eng.reset_stats
+        e2e_api = "rb2_insert_multi_sharded (include/ropebwt2_b200.h) on a pinned host buffer per rank + rb2_counts"
+    else:
+        eng.close()
+        mr = MRope(1)
+
+        def e2e_step():
+            L.rb2_reset(mr.engine_handle)
+            mr.L.mr_insert_multi(mr.h, nbytes, C.cast(hptr, C.POINTER(C.c_uint8)), 1)
+            return int(mr.counts().sum())
+        e2e_stats, e2e_reset_stats = mr.stats, mr.reset_stats
+        e2e_api = "mr_insert_multi (include/mrope.h) on a pinned host buffer + mr_get_c counts"
 
     for _ in range(args.warmup):
         e2e_step()
     barrier()
-    mr.reset_stats()
+    e2e_reset_stats()
     t0 = time.time()
     for _ in range(args.steps):
         tot = e2e_step()
     barrier()
     wall_e2e = time.time() - t0
-    st2 = mr.stats()
+    st2 = e2e_stats()
     ms_e2e = max_over_ranks(st2["ms_total"])
     clocks = sampler.summary()
-    assert tot == nbytes
-    mr.close()
+    assert tot == nbytes * n_idx
+    ms_exch = max_over_ranks(st.get("ms_exchange", 0.0))
+    if sharded:
+        eng.close()
+    else:
+        mr.close()
     L.rb2_host_free(C.c_void_p(hptr))
 
     if rank != 0:
@@ -262,9 +289,9 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # dominant kernel: k_merge_fast.  Its algorithmic bytes: every item it finishes reads one 512-byte
-    # leaf block and writes it back (split pieces are not counted); items it hands to k_merge_general
-    # are excluded together with that kernel's time.
+    # dominant kernel: k_merge_half (two leaf blocks per warp).  Its algorithmic bytes: every item it
+    # finishes reads one 512-byte leaf block and writes it back (split pieces are not counted); items it
+    # hands on to k_merge_fast / k_merge_general are excluded together with those kernels' time.
     fast_items = st["merge_blocks"] - st["general_items"]
     fast_bytes = fast_items * 2 * 512
     merge_gbs = fast_bytes / (st["ms_merge"] * 1e-3) / 1e9 if st["ms_merge"] > 0 else 0.0
@@ -281,23 +308,29 @@ def main():
         "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: {n} x {ln} bp uniform reads per GPU, forward strand, RLO (-LRs), one batch into an empty index",
-                   "reads_per_gpu": n, "read_length": ln, "sorting_order": "RLO", "parallelism": f"replicas x{world}",
+                   "reads_per_gpu": n, "read_length": ln, "sorting_order": "RLO",
+                   "parallelism": (f"sharded x{world}: ONE index of {world * n} reads, 36 sub-buckets over {world} GPUs, "
+                                   "per column one count all-gather + one string-state exchange (NCCL send/recv)") if sharded
+                   else (f"replicas x{world}" if world > 1 else "one GPU"),
                    "l2": "inputs (%.1f GB batch, multi-GB leaf-block pool) far exceed the 126 MB L2" % (nbytes / 1e9),
                    "timing": "CUDA events on the engine stream around each call; wall-clock cross-check %.3f s/step" % (wall_value / args.steps),
                    "parity": "symbol conservation checked in-run; bit-exactness vs the reference is tests/test_parity_gpu.py"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 7 * 48,
                 "ms_per_step": ms_e2e / args.steps, "wall_s_per_step": wall_e2e / args.steps,
-                "api": "mr_insert_multi (include/mrope.h) on a pinned host buffer + mr_get_c counts"},
+                "api": e2e_api},
         "gpu_launches": int(st["n_launches"]),
-        "roofline": {"bound": "hbm", "kernel": "k_merge_fast", "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_merge_half", "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
                      "frac": merge_gbs / peak, "traffic": traffic, "traffic_capture": traffic_info, "peak_source": peak_src,
                      "launches": int(st["n_merge_launches"]), "ms_in_kernel": st["ms_merge"],
                      "algorithmic_bytes": int(fast_bytes), "items": int(fast_items),
-                     "items_left_to_k_merge_general": int(st["general_items"]), "ms_in_k_merge_general": st["ms_merge_general"],
+                     "items_left_to_k_merge_fast_and_general": int(st["general_items"]), "ms_in_k_merge_fast_and_general": st["ms_merge_general"],
                      "share_of_step": st["ms_merge"] / st["ms_total"] if st["ms_total"] else None},
-        "phases_ms_per_step": {k: st[k] / args.steps for k in ("ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_merge_general", "ms_directory")},
+        "phases_ms_per_step": {k: st[k] / args.steps for k in ("ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_merge_general", "ms_directory", "ms_exchange")},
     }
+    if sharded:
+        out["exchange"] = {"ms_per_step_max_over_ranks": ms_exch / args.steps, "bytes_received_per_step_rank0": int(st["exch_bytes"] / args.steps),
+                           "collectives_per_column": "1 all-gather (1.8 KB/rank) + 1 grouped send/recv of the string state"}
     if not args.no_cpu_baseline and ref_binary() is not None:
         g, hot, wall, _ = run_reference_sample(args.cpu_reads, ln, args.seed)
         out["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": 5, "kind": "reference",

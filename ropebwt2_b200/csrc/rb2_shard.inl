@@ -213,7 +213,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	uint64_t Gglob = sorted ? 1 : mAll, Mglob = mAll;
 	const int cs = 0; // current state lives in buffer 0; buffer 1 receives a column's output in source order
 	if (e->owner[0] == me) {
-		e->gL[0].need(mAll); e->gSize[0].need(mAll); e->gOff[0].need(mAll + 1); e->sid[0].need(mAll + 4);
+		e->gL[0].need(Gglob); e->gSize[0].need(Gglob); e->gOff[0].need(Gglob + 1); e->sid[0].need(mAll + 4);
 		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
 		G = (uint32_t)Gglob; M = (uint32_t)mAll;
 	}
@@ -227,9 +227,11 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		if ((uint64_t)col >= ncolAll) RB2_FATAL("internal: live strings beyond the last column");
 		Dir &d = e->dir[e->cur];
 		// ---- per-column capacity (contents of these buffers are dead here) ---------------------
-		e->gL[1].need(M); e->gSize[1].need(M); e->gOff[1].need((size_t)M + 1); e->sid[1].need((size_t)M + 4);
+		// (a group yields at most one next group and one record per symbol, plus records for counts above the run limit)
+		const size_t gnMax = std::min<uint64_t>(M, 6ull * G);
+		e->gL[1].need(gnMax); e->gSize[1].need(useSizes ? gnMax : 0); e->gOff[1].need(gnMax + 1); e->sid[1].need((size_t)M + 4);
 		e->asym.need((size_t)M + 8);
-		const size_t recCap = (size_t)M + M / RB2_MAXRUN + 64;
+		const size_t recCap = gnMax + M / RB2_MAXRUN + 64;
 		e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
 		reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
 		if (useSizes) e->sizes6.need((size_t)G * 6);
@@ -360,7 +362,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const uint32_t Gn = (uint32_t)curG[me], Mn = (uint32_t)curM[me];
 		if (MglobN > 0) {
 			ph_begin(e, PH_EXCH);
-			e->gL[cs].need(Gn); e->gSize[cs].need(Gn); e->gOff[cs].need((size_t)Gn + 1); e->sid[cs].need((size_t)Mn + 4);
+			e->gL[cs].need(Gn); e->gSize[cs].need(useSizes ? Gn : 0); e->gOff[cs].need((size_t)Gn + 1); e->sid[cs].need((size_t)Mn + 4);
 			const bool singles = GglobN == MglobN;
 			cm->group_begin();
 			cm->exchange(e->gL[1].p, e->gL[cs].p, 8, pcG.data(), (int)pcG.size(), e->st);
