@@ -60,6 +60,8 @@ typedef struct {
 	int64_t general_items;              /* work items that went through k_merge_general */
 	double  ms_exchange;                /* sharded build: string-state transfer between ranks */
 	int64_t exch_bytes;                 /* sharded build: bytes of string state this rank received */
+	double  ms_convert;                 /* dense regime: leaf blocks <-> flat symbol array at the ends of a batch */
+	int64_t flat_batches;               /* batches that ran in the dense regime (k_flat_merge instead of the block merges) */
 } rb2_stats_t;
 
 int  rb2_device_count(void);

@@ -403,6 +403,7 @@ struct GroupArgs {
 	int64_t *gSizeNext; uint32_t *gOffNext;
 	int64_t *recP; uint32_t *recSC, *recDst; // recSC = count << 3 | symbol
 	Ctl *ctl;
+	uint32_t *recPre;        // dense regime: members in front of the record = symbols inserted in front of it (or null)
 };
 
 // MODE 0: reduce (per-CTA totals).  MODE 1: emit.  COMP: RCLO insertion order $,T,G,C,A,N.
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 	const bool useSizes = A.sizes6 != 0;
 	const bool nonempty = useSizes && A.gSize[g] > 0;
 	int64_t P = A.gL[g];
-	uint32_t r = v[12];
+	uint32_t r = v[12], mpre = S;
 	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
 #pragma unroll
 	for (int slot = 0; slot < 6; ++slot) {
@@ -526,6 +527,7 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 			while (rem) { // counts above the 4-byte run limit become several records at the same position
 				uint32_t c = rem < RB2_MAXRUN ? rem : RB2_MAXRUN;
 				A.recP[r] = P; A.recSC[r] = (c << 3) | (uint32_t)a; A.recDst[r] = dst;
+				if (A.recPre) { A.recPre[r] = mpre; mpre += c; }
 				dst = NONE32; rem -= c; ++r;
 			}
 		}
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(256) k_group_pass(GroupArgs A)
 }
 
 // one thread: derive the next column's bucket ranges from the scan totals
-__global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
+__global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext, uint32_t *recPre, uint32_t M)
 {
 	uint32_t g = 0, m = 0, bad = 0;
 	ctl->gSymBase[0] = 0; ctl->mSymBase[0] = 0;
@@ -550,6 +552,7 @@ __global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
 		for (uint32_t b = 0; b <= ctl->nb; ++b)
 			for (int a = 0; a < 6; ++a) { ctl->grpPre[b * 6 + a] = ctl->grpTot[a]; ctl->memPre[b * 6 + a] = ctl->grpTot[6 + a]; }
 	gOffNext[g] = m;
+	if (recPre) recPre[ctl->grpTot[12]] = M;
 	if (bad) ctl->err |= RB2_ERR_ORDER;
 }
 
@@ -559,7 +562,7 @@ __global__ void k_col_bases(Ctl *ctl, uint32_t *gOffNext)
 // the next group index of a string is its partition destination.  One kernel then does the work of
 // both group passes, their scans and the partition (mrope.c:195-198 is the reference's own
 // special case for this situation).
-__global__ void k_col_bases_single(Ctl *ctl, uint32_t *gOffNext, uint32_t M)
+__global__ void k_col_bases_single(Ctl *ctl, uint32_t *gOffNext, uint32_t M, uint32_t *recPre)
 {
 	uint32_t m = 0;
 	ctl->gSymBase[0] = 0; ctl->mSymBase[0] = 0;
@@ -574,6 +577,7 @@ __global__ void k_col_bases_single(Ctl *ctl, uint32_t *gOffNext, uint32_t M)
 		for (uint32_t b = 0; b <= ctl->nb; ++b)
 			for (int a = 0; a < 6; ++a) ctl->memPre[b * 6 + a] = ctl->memTot[a];
 	gOffNext[m] = m;
+	if (recPre) recPre[M] = M;
 }
 
 struct SingleArgs {
@@ -581,6 +585,7 @@ struct SingleArgs {
 	const int64_t *gL, *gSize, *sizes6; Ctl *ctl;
 	uint32_t *sidNext; int64_t *gSizeNext; uint32_t *gOffNext;
 	int64_t *recP; uint32_t *recSC, *recDst;
+	uint32_t *recPre;
 };
 
 template <bool COMP>
@@ -645,6 +650,7 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 			if (A.sizes6) A.gSizeNext[d] = sza;
 		}
 		A.recP[g] = P; A.recSC[g] = (1u << 3) | a; A.recDst[g] = d;
+		if (A.recPre) A.recPre[g] = g;
 	}
 }
 
@@ -1728,6 +1734,8 @@ __global__ void k_fill_u32(uint32_t *p, uint32_t n, uint32_t v0, uint32_t step)
 	if (i < n) p[i] = v0 + i * step;
 }
 
+#include "rb2_flat.cuh"
+
 // =====================================================================================
 // Host side
 // =====================================================================================
@@ -1743,7 +1751,15 @@ template <typename T> struct DevBuf {
 	void release() { if (p) RB2_CUDA(cudaFree(p)); p = 0; cap = 0; }
 };
 
-enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_MERGE2, PH_EXCH, PH_N };
+enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, PH_MEMBERS2, PH_MERGE2, PH_EXCH, PH_CONVERT, PH_N };
+
+// dense regime (rb2_flat.cuh): the BWT as a flat array of symbols for the duration of one batch
+struct FlatState {
+	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
+	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0; DevBuf<TileDesc> desc;
+	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
+	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+};
 
 struct rb2_engine {
 	int dev, so, nSM;
@@ -1757,8 +1773,10 @@ struct rb2_engine {
 	// whole-index symbol totals of all sub-buckets (identical on every rank), directory offsets
 	int rank, nranks; Comm *comm; int owner[NBMAX];
 	int64_t gtot[NBMAX][6];
-	int64_t *dDirOff, *hDirOff;
+	int64_t *dDirOff, *hDirOff;       // offsets of the directory (post-column while a column runs)
+	int64_t *dDirOffPre, *hDirOffPre; // the same in front of the column (dense regime: record positions are pre-column)
 	uint32_t *hPlan; DevBuf<uint32_t> plan;
+	FlatState flat; DevBuf<uint32_t> recPre;
 	int64_t tot[6][6]; int64_t bktLen[6];
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
 	int64_t *dRankOut, *hRankOut;
@@ -1929,7 +1947,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	rb2_engine *e = new rb2_engine();
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
-	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->hPlan = 0;
+	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0;
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
 	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
@@ -2002,7 +2020,8 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
-	if (e->comm) { delete e->comm; RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
+	if (e->comm) { delete e->comm; RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
+	e->flat.release(); e->recPre.release();
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
 	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);
 	RB2_CUDA(cudaStreamDestroy(e->st));
@@ -2016,7 +2035,7 @@ static inline void ph_end(rb2_engine *e, int p) { RB2_CUDA(cudaEventRecord(e->ev
 static void ph_collect(rb2_engine *e, uint32_t mask)
 {
 	double *acc[PH_N] = { &e->stats.ms_h2d, &e->stats.ms_transpose, &e->stats.ms_members, &e->stats.ms_groups, &e->stats.ms_merge,
-	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members, &e->stats.ms_merge_general, &e->stats.ms_exchange };
+	                      &e->stats.ms_directory, &e->stats.ms_directory, &e->stats.ms_members, &e->stats.ms_merge_general, &e->stats.ms_exchange, &e->stats.ms_convert };
 	for (int p = 0; p < PH_N; ++p) if (mask >> p & 1) {
 		float ms = 0;
 		RB2_CUDA(cudaEventElapsedTime(&ms, e->ev[p][0], e->ev[p][1]));
@@ -2088,6 +2107,15 @@ static void apply_records(rb2_engine *e, uint32_t nrec, int64_t *gLNext)
 	e->stats.merge_bytes_rw += ((int64_t)nItems * 2 + (int64_t)(h->poolUsed - usedBefore)) * RB2_BLK;
 }
 
+#include "rb2_flat_host.inl"
+
+static FILE *column_log(void)
+{
+	static FILE *f = 0; static int init = 0;
+	if (!init) { init = 1; const char *p = getenv("RB2_COLLOG"); if (p && *p) f = fopen(p, "w"); }
+	return f;
+}
+
 // One sub-batch whose strings already sit in device memory at `s` (len bytes, ends with NUL).
 static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 {
@@ -2126,10 +2154,15 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	e->asym.need((size_t)m + 8);
 	const size_t recCap = (size_t)m + m / RB2_MAXRUN + 64;
 	e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
-	// Reserve leaf blocks for the whole batch up front (2 bytes of pool per new symbol covers random
-	// data at B+-tree fill plus blocks retired by multi-item merges); more is added on demand.
-	reserve_blocks(e, (uint64_t)e->hctl->poolUsed + (uint64_t)len * 2 / RB2_FILL + 4096);
-	reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
+	// dense regime: the whole batch runs on a flat symbol array (rb2_flat.cuh), re-encoded at the end
+	const bool flat = flat_choose(e, m, (uint64_t)len);
+	if (flat) { e->recPre.need(recCap + 1); flat_begin(e, (uint64_t)len); }
+	else {
+		// Reserve leaf blocks for the whole batch up front (2 bytes of pool per new symbol covers random
+		// data at B+-tree fill plus blocks retired by multi-item merges); more is added on demand.
+		reserve_blocks(e, (uint64_t)e->hctl->poolUsed + (uint64_t)len * 2 / RB2_FILL + 4096);
+		reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
+	}
 	const int64_t n0 = e->bktLen[0];
 	const bool useSizes = sorted && n0 > 0;
 	if (useSizes) e->sizes6.need((size_t)m * 6);
@@ -2168,13 +2201,16 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 
 		// ---- groups: interval sizes, histograms, records ------------------------------
 		ph_begin(e, PH_GROUPS);
-		if (useSizes)
-			LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+		if (useSizes) {
+			if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, e->gL[cs].p, e->gSize[cs].p,
+			                 e->sizes6.p, e->dctl, (const int64_t*)0, e->nb);
+			else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+		}
 		if (G == M) {
 			// every group is a singleton: records, next groups and the partition in one kernel
-			LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, M);
+			LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, M, flat ? e->recPre.p : (uint32_t*)0);
 			SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p };
+			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0 };
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 			else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 			ph_end(e, PH_GROUPS);
@@ -2183,11 +2219,11 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			const uint32_t nGC = cdiv(G, 256);
 			e->grpCta.need((size_t)nGC * NGC + NGC);
 			GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
-			                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl };
+			                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl, flat ? e->recPre.p : (uint32_t*)0 };
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 			else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
 			run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
-			LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p);
+			LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, flat ? e->recPre.p : (uint32_t*)0, M);
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
 			else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
 			ph_end(e, PH_GROUPS);
@@ -2197,7 +2233,8 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			ph_end(e, PH_MEMBERS2);
 		}
 		ctl_pull(e);
-		ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2));
+		ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2) | e->flat.pending);
+		e->flat.pending = 0;
 		const uint32_t nrec = h->nrec;
 
 		if (m == 1) { // remember where the string's sentinel goes (mr_insert1's return value)
@@ -2206,15 +2243,27 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			e->lastBkt = 0;
 			for (int b = 0; b < 6; ++b) if (gBkt[b + 1] > gBkt[b]) e->lastBkt = b;
 		}
-		apply_records(e, nrec, e->gL[cs ^ 1].p);
+		const rb2_stats_t before = e->stats;
+		if (flat) flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p);
+		else apply_records(e, nrec, e->gL[cs ^ 1].p);
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
+		if (FILE *cl = column_log()) // developer aid: RB2_COLLOG=<file> gets one line per column
+			fprintf(cl, "col %lld M %u G %u nrec %u nlog %u items %lld deferred %lld ms_half %.3f ms_fast_gen %.3f ms_dir %.3f\n", (long long)col, M, G, nrec, e->nlog,
+			        (long long)(e->stats.merge_blocks - before.merge_blocks), (long long)(e->stats.general_items - before.general_items),
+			        e->stats.ms_merge - before.ms_merge, e->stats.ms_merge_general - before.ms_merge_general, e->stats.ms_directory - before.ms_directory);
 
 		// ---- advance to the next column ---------------------------------------------
 		for (int b = 0; b < 6; ++b) e->bktLen[b] += mBkt[b + 1] - mBkt[b];
 		for (int b = 0; b < 8; ++b) { gBkt[b] = h->gSymBase[b]; mBkt[b] = h->mSymBase[b]; }
 		G = h->Gnext; M = h->Mnext;
 		cs ^= 1;
+	}
+	if (flat) {
+		for (int b = 0; b < 6; ++b) e->bktLen[b] = e->bktLen[b]; // (already advanced column by column)
+		flat_end(e);
+		ph_collect(e, e->flat.pending); e->flat.pending = 0;
+		++e->stats.flat_batches;
 	}
 	pull_totals(e);
 	e->stats.n_strings += m;

@@ -1,0 +1,170 @@
+// rb2_flat_host.inl -- host side of the dense regime (rb2_flat.cuh); included by rb2_engine.cu.
+
+// RB2_FLAT=0 never / 1 always / unset: by cost estimate
+static int flat_pref(void)
+{
+	const char *s = getenv("RB2_FLAT");
+	if (!s || !*s) return -1;
+	return *s != '0';
+}
+
+// local symbol count of the index this engine holds, and (sharded) which buckets it owns
+static bool bucket_mine(const rb2_engine *e, int b) { return !e->comm || e->owner[b] == e->rank; }
+static int64_t bucket_len(const rb2_engine *e, int b)
+{
+	if (!e->comm) return e->bktLen[b];
+	int64_t t = 0;
+	for (int a = 0; a < 6; ++a) t += e->gtot[b][a];
+	return t;
+}
+static uint64_t local_symbols(const rb2_engine *e)
+{
+	uint64_t n = 0;
+	for (int b = 0; b < e->nb; ++b) if (bucket_mine(e, b)) n += (uint64_t)bucket_len(e, b);
+	return n;
+}
+
+// Dense or sparse?  One dense column streams the whole local array (~0.6 ps per symbol); one sparse
+// column costs ~0.22 ns per record (measured, profiles/README.md).  `strings` = records per column at
+// the start of the batch, `addLocal` = symbols this engine expects to receive.
+static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
+{
+	const int pref = flat_pref();
+	if (pref == 0) return false;
+	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
+	size_t freeB = 0, totB = 0;
+	RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+	const uint64_t have = e->flat.s[0].cap + e->flat.s[1].cap;
+	const uint64_t need = 2 * cap + cap / 8 + (cap * 5 / 4) + (64ull << 20); // two arrays, directories, the re-encoded pool
+	if (need > freeB + have + (uint64_t)e->poolCap * RB2_BLK) return false; // does not fit: block-wise updates need far less
+	if (pref == 1) return true;
+	return strings >= 65536 && (double)n0 + 0.5 * (double)addLocal < 256.0 * (double)strings;
+}
+
+static void flat_scan_dir(rb2_engine *e, int which, uint64_t n)
+{
+	FlatState &f = e->flat;
+	const uint64_t nd = n ? (n + FT_DIR - 1) / FT_DIR : 1;
+	FlatDirScan fs = { f.tileCnt.p, nd, f.dir[which].p };
+	run_scan<6, int64_t, FlatDirScan>(e, fs, nd, e->scanCta64, (int64_t*)0, e->midTmp64);
+}
+
+// leaf blocks -> flat array (start of a dense batch)
+static void flat_begin(rb2_engine *e, uint64_t addLocal)
+{
+	FlatState &f = e->flat;
+	ph_begin(e, PH_CONVERT);
+	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
+	for (int k = 0; k < 2; ++k) { f.s[k].need(cap); f.dir[k].need((cap / FT_DIR + 3) * 6); }
+	f.tileCnt.need((cap / FT_DIR + 3) * 6);
+	f.tileR0.need(cap / FT_OUT + 4); f.desc.need(cap / FT_OUT + 4);
+	f.cur = 0; f.n = n0;
+	if (n0 > 0) {
+		Dir &d = e->dir[e->cur];
+		LAUNCH(e, k_blocks_to_flat, cdiv(e->nlog, 4), 128, 0, e->pool, d.order, d.cumLen, e->nlog, e->comm ? e->dDirOff : (const int64_t*)0,
+		       e->dctl->blkBkt, e->nb, f.s[0].p, e->dctl);
+		LAUNCH(e, k_flat_count_tiles, cdiv((n0 + FT_DIR - 1) / FT_DIR, 8), 256, 0, f.s[0].p, n0, f.tileCnt.p);
+	} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 24, e->st));
+	flat_scan_dir(e, 0, n0);
+	ph_end(e, PH_CONVERT);
+	f.pending |= 1u << PH_CONVERT;
+	f.on = true;
+}
+
+// one column: merge nrec records (inserting `inserted` symbols) into the flat array
+static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext)
+{
+	FlatState &f = e->flat;
+	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
+	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
+	f.s[f.cur ^ 1].need(nNew + FT_PAD); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.tileR0.need(nNew / FT_OUT + 4); f.desc.need(nNew / FT_OUT + 4);
+	ph_begin(e, PH_MERGE);
+	LAUNCH(e, k_flat_splits, cdiv((uint64_t)nrec + 1, 256), 256, 0, e->recP.p, e->recPre.p, nrec, nTiles, f.tileR0.p);
+	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, e->recP.p, e->recPre.p, e->recSC.p, f.tileR0.p, nTiles, nNew, f.desc.p);
+	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, e->recP.p, e->recPre.p, e->recSC.p, e->recDst.p, nrec,
+	                f.desc.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
+	LAUNCH(e, k_flat_merge, (uint32_t)nTiles, 256, sizeof(FlatSmem), fa);
+	ph_end(e, PH_MERGE);
+	ph_begin(e, PH_DIR);
+	flat_scan_dir(e, f.cur ^ 1, nNew);
+	ph_end(e, PH_DIR);
+	++e->stats.n_merge_launches;
+	e->stats.merge_blocks += nTiles;
+	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) + (int64_t)nrec * 28; // old array read, new written, records (20 B) read, ranks (8 B) written
+	f.cur ^= 1; f.n = nNew;
+	f.pending |= (1u << PH_MERGE) | (1u << PH_DIR);
+	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096) { // developer aid: dump tiny arrays column by column
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+		std::vector<uint8_t> hs(nNew); std::vector<int64_t> hp(nrec), hd(12); std::vector<uint32_t> hpre(nrec + 1), hsc(nrec), hdst(nrec);
+		RB2_CUDA(cudaMemcpy(hs.data(), f.s[f.cur].p, nNew, cudaMemcpyDeviceToHost));
+		RB2_CUDA(cudaMemcpy(hp.data(), e->recP.p, nrec * 8, cudaMemcpyDeviceToHost));
+		RB2_CUDA(cudaMemcpy(hpre.data(), e->recPre.p, (nrec + 1) * 4, cudaMemcpyDeviceToHost));
+		RB2_CUDA(cudaMemcpy(hsc.data(), e->recSC.p, nrec * 4, cudaMemcpyDeviceToHost));
+		RB2_CUDA(cudaMemcpy(hdst.data(), e->recDst.p, nrec * 4, cudaMemcpyDeviceToHost));
+		RB2_CUDA(cudaMemcpy(hd.data(), f.dir[f.cur].p, 96, cudaMemcpyDeviceToHost));
+		fprintf(stderr, "[flat] n=%llu records:", (unsigned long long)nNew);
+		for (uint32_t r = 0; r < nrec && r < 40; ++r) {
+			int64_t g = -1;
+			if (hdst[r] != NONE32) RB2_CUDA(cudaMemcpy(&g, gLNext + hdst[r], 8, cudaMemcpyDeviceToHost));
+			fprintf(stderr, " (P%lld pre%u %c x%u ->%lld)", (long long)hp[r], hpre[r], "$ACGTN"[hsc[r] & 7], hsc[r] >> 3, (long long)g);
+		}
+		fprintf(stderr, " pre[R]=%u\n[flat] array: ", hpre[nrec]);
+		for (uint64_t i = 0; i < nNew && i < 200; ++i) fputc("$ACGTN??"[hs[i] & 7], stderr);
+		fprintf(stderr, "\n[flat] dir row1:");
+		for (int a = 0; a < 6; ++a) fprintf(stderr, " %lld", (long long)hd[6 + a]);
+		fprintf(stderr, "\n");
+	}
+}
+
+// flat array -> leaf blocks (end of a dense batch): buckets are encoded independently
+static void flat_end(rb2_engine *e)
+{
+	FlatState &f = e->flat;
+	if (f.pending) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, f.pending); f.pending = 0; }
+	ph_begin(e, PH_CONVERT);
+	EncTab T; memset(&T, 0, sizeof(T));
+	T.nb = e->nb;
+	uint64_t sym = 0, ch = 0;
+	for (int b = 0; b < e->nb; ++b) {
+		T.symStart[b] = sym; T.chunkStart[b] = ch;
+		if (bucket_mine(e, b)) { const uint64_t l = (uint64_t)bucket_len(e, b); sym += l; ch += (l + FE_CHUNK - 1) / FE_CHUNK; }
+	}
+	T.symStart[e->nb] = sym; T.chunkStart[e->nb] = ch;
+	if (sym != f.n) RB2_FATAL("internal: flat array holds %llu symbols, the buckets %llu", (unsigned long long)f.n, (unsigned long long)sym);
+	const uint64_t nChunk = ch;
+	f.chunkBytes.need(nChunk + 1); f.chunkPre.need(nChunk + 2);
+	std::vector<uint64_t> edge(2 * (size_t)e->nb, 0);
+	if (nChunk) {
+		LAUNCH(e, k_flat_chunk_bytes, cdiv(nChunk, 256), 256, 0, f.s[f.cur].p, T, nChunk, f.chunkBytes.p);
+		ChunkScan cs = { f.chunkBytes.p, nChunk, f.chunkPre.p };
+		run_scan<1, uint64_t, ChunkScan>(e, cs, nChunk, f.scanU64, (uint64_t*)0, f.midU64);
+		for (int b = 0; b < e->nb; ++b) if (T.chunkStart[b + 1] > T.chunkStart[b]) {
+			RB2_CUDA(cudaMemcpyAsync(&edge[2 * b], f.chunkPre.p + T.chunkStart[b], 8, cudaMemcpyDeviceToHost, e->st));
+			RB2_CUDA(cudaMemcpyAsync(&edge[2 * b + 1], f.chunkPre.p + T.chunkStart[b + 1] - 1, 8, cudaMemcpyDeviceToHost, e->st));
+		}
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+	}
+	uint32_t nBlocks = 0;
+	for (int b = 0; b < e->nb; ++b) {
+		T.blkStart[b] = nBlocks; T.byteStart[b] = edge[2 * b];
+		if (T.chunkStart[b + 1] > T.chunkStart[b]) nBlocks += (uint32_t)((edge[2 * b + 1] - edge[2 * b]) / FE_T) + 1;
+		else if (bucket_mine(e, b)) nBlocks += 1; // an empty bucket keeps one empty block
+	}
+	T.blkStart[e->nb] = nBlocks;
+	e->hctl->poolUsed = 0; // the pool is rewritten from scratch: nothing to carry over when it grows
+	reserve_blocks(e, (uint64_t)nBlocks + nBlocks / 16 + 4096);
+	LAUNCH(e, k_flat_encode, cdiv(nBlocks, 4), 128, 0, f.s[f.cur].p, T, f.chunkPre.p, nBlocks, e->pool, e->blkCnt);
+	LAUNCH(e, k_fill_u32, cdiv(nBlocks, 256), 256, 0, e->dir[e->cur].order, nBlocks, 0u, 1u);
+	e->nlog = nBlocks;
+	for (int b = 0; b < NBA; ++b) e->blkBkt[b] = b <= e->nb ? T.blkStart[b] : nBlocks;
+	Ctl *h = e->hctl;
+	h->poolUsed = nBlocks; h->poolCap = e->poolCap; h->nb = (uint32_t)e->nb;
+	for (int b = 0; b < NBA; ++b) h->blkBkt[b] = e->blkBkt[b];
+	ctl_push(e);
+	rebuild_directory(e, false);
+	ph_end(e, PH_CONVERT);
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	ph_collect(e, 1u << PH_CONVERT);
+	f.on = false;
+}

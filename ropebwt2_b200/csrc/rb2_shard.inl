@@ -66,15 +66,23 @@ extern "C" void rb2_nccl_unique_id(uint8_t out[128])
 }
 
 // symbols / per-symbol counts of the index that other ranks hold in front of each of my sub-buckets
-static void shard_dir_offsets(rb2_engine *e, const int64_t tot[NBMAX][6])
+static void shard_dir_offsets(rb2_engine *e, const int64_t tot[NBMAX][6], bool pre = false)
 {
+	int64_t *hOff = pre ? e->hDirOffPre : e->hDirOff, *dOff = pre ? e->dDirOffPre : e->dDirOff;
 	int64_t acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
 	for (int s = 0; s < NBMAX; ++s) {
-		for (int a = 0; a < 7; ++a) e->hDirOff[s * 7 + a] = acc[a];
+		for (int a = 0; a < 7; ++a) hOff[s * 7 + a] = acc[a];
 		if (e->owner[s] != e->rank)
 			for (int a = 0; a < 6; ++a) { acc[a] += tot[s][a]; acc[6] += tot[s][a]; }
 	}
-	RB2_CUDA(cudaMemcpyAsync(e->dDirOff, e->hDirOff, NBMAX * 7 * sizeof(int64_t), cudaMemcpyHostToDevice, e->st));
+	RB2_CUDA(cudaMemcpyAsync(dOff, hOff, NBMAX * 7 * sizeof(int64_t), cudaMemcpyHostToDevice, e->st));
+}
+
+// dense regime: record positions are whole-index coordinates; my flat array starts at my first symbol
+__global__ void k_flat_localize(int64_t *recP, uint32_t R, const Ctl *ctl, const int64_t *off, int nb)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < R) recP[r] -= off[bucket_of(ctl->recBkt, (uint32_t)nb, r) * 7 + 6];
 }
 
 static void shard_publish_totals(rb2_engine *e)
@@ -124,6 +132,8 @@ extern "C" rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int r
 	shard_owner_map(nranks, e->owner);
 	RB2_CUDA(cudaMalloc(&e->dDirOff, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOff, NBMAX * 7 * sizeof(int64_t)));
+	RB2_CUDA(cudaMalloc(&e->dDirOffPre, NBMAX * 7 * sizeof(int64_t)));
+	RB2_CUDA(cudaMallocHost(&e->hDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t)));
 	if (group) { if (group->n != nranks) RB2_FATAL("group size mismatch"); e->comm = new LocalComm(group, rank); }
 	else e->comm = new NcclComm(rank, nranks, nccl_uid);
@@ -205,7 +215,14 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	// ---- state for column 0 (mrope.c:279-285): everything starts in sub-bucket ($,$) -------------
 	const int64_t n0 = e->bktLen[0];
 	const bool useSizes = sorted && n0 > 0;
-	reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
+	// dense or sparse regime: every rank must take the same path, so the ranks vote
+	const uint64_t addLocal = lenAll / P + lenAll / (4 * P) + 4096;
+	uint32_t myVote = flat_choose(e, mAll / P + 1, addLocal) ? 1u : 0u, votes[RB2_MAX_RANKS];
+	cm->allgather_host(&myVote, 4, votes, e->st);
+	bool flat = true;
+	for (int r = 0; r < P; ++r) flat = flat && votes[r] != 0;
+	if (flat) flat_begin(e, addLocal);
+	else reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
 	uint32_t G = 0, M = 0;
 	uint32_t gBkt[NBA], mBkt[NBA];
 	uint64_t mglob[NBMAX];
@@ -233,7 +250,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		e->asym.need((size_t)M + 8);
 		const size_t recCap = gnMax + M / RB2_MAXRUN + 64;
 		e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
-		reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
+		if (flat) { e->recPre.need(recCap + 1); shard_dir_offsets(e, e->gtot, true); }
+		else reserve_items(e, std::min<uint64_t>(e->poolCap, recCap) + recCap / RMAX + 2);
 		if (useSizes) e->sizes6.need((size_t)G * 6);
 		// ---- control block -------------------------------------------------------------------
 		for (int b = 0; b < NBA; ++b) { h->gBkt[b] = gBkt[b]; h->mBkt[b] = mBkt[b]; h->blkBkt[b] = e->blkBkt[b]; }
@@ -269,12 +287,15 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			ph_end(e, PH_MEMBERS);
 			// ---- groups ---------------------------------------------------------------------
 			ph_begin(e, PH_GROUPS);
-			if (useSizes)
-				LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+			if (useSizes) {
+				if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, e->gL[cs].p, e->gSize[cs].p,
+				                 e->sizes6.p, e->dctl, e->dDirOffPre, e->nb);
+				else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+			}
 			if (G == M) {
-				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M);
+				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M, flat ? e->recPre.p : (uint32_t*)0);
 				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p };
+				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 				else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 				ph_end(e, PH_GROUPS);
@@ -283,11 +304,11 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				const uint32_t nGC = cdiv(G, 256);
 				e->grpCta.need((size_t)nGC * NGC + NGC);
 				GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
-				                 e->grpCta.p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl };
+				                 e->grpCta.p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl, flat ? e->recPre.p : (uint32_t*)0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 				else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
 				run_mid<NGC, uint32_t>(e, e->grpCta.p, (uint64_t)nGC, e->dctl->grpTot, e->midTmp);
-				LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[1].p);
+				LAUNCH(e, k_col_bases, 1, 1, 0, e->dctl, e->gOff[1].p, flat ? e->recPre.p : (uint32_t*)0, M);
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<1, true>), nGC, 256, 0, ga);
 				else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
 				ph_end(e, PH_GROUPS);
@@ -296,8 +317,10 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				ph_end(e, PH_MEMBERS2);
 			}
 			ctl_pull(e);
-			ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2));
+			ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2) | e->flat.pending);
+			e->flat.pending = 0;
 			nrec = h->nrec;
+			if (flat && nrec) LAUNCH(e, k_flat_localize, cdiv(nrec, 256), 256, 0, e->recP.p, nrec, e->dctl, e->dDirOffPre, e->nb);
 		}
 		// ---- gather every rank's tables -----------------------------------------------------------
 		ShardTab mineT;
@@ -353,7 +376,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int r = 0; r < P; ++r) if (curM[r] >= 0xfffffff0ull) RB2_FATAL("too many strings on one rank");
 
 		// ---- merge my records into my blocks ------------------------------------------------------
-		if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
+		if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p); } // (no records: my array does not change)
+		else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
 		else rebuild_directory(e, false);
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
@@ -378,7 +402,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			}
 			ph_end(e, PH_EXCH);
 			RB2_CUDA(cudaStreamSynchronize(e->st)); // hPlan and the piece lists are reused next column
-			ph_collect(e, 1u << PH_EXCH);
+			ph_collect(e, (1u << PH_EXCH) | e->flat.pending);
+			e->flat.pending = 0;
 			e->stats.exch_bytes += ((int64_t)Gn * (8 + (useSizes ? 8 : 0) + (singles ? 0 : 4)) + (int64_t)Mn * 4);
 		}
 		// ---- advance -------------------------------------------------------------------------------
@@ -386,6 +411,12 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int b = 0; b < NBA; ++b) { gBkt[b] = gBktN[b]; mBkt[b] = mBktN[b]; }
 		memcpy(mglob, mglobNext, sizeof(mglob));
 		Gglob = GglobN; Mglob = MglobN;
+	}
+	if (flat) {
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+		ph_collect(e, e->flat.pending); e->flat.pending = 0;
+		flat_end(e);
+		++e->stats.flat_batches;
 	}
 	shard_publish_totals(e);
 	e->stats.n_strings += m;
