@@ -12,8 +12,8 @@ scaling is "weak".  `--layout replicas` runs N independent indexes instead (no e
           stream around the whole call, max over ranks
   e2e     the reference-facing call (mr_insert_multi through the C-ABI) on a pinned HOST buffer:
           H2D copy of the batch and D2H of the symbol counts inside the timed region
-  roofline  k_merge_half (dominant kernel): algorithmic leaf-block bytes read+written per
-          launch / its CUDA-event time, against the measured HBM copy bandwidth
+  roofline  the dominant kernel (k_flat_merge in the dense regime this workload runs in): algorithmic
+          bytes per launch / its CUDA-event time, against the measured HBM copy bandwidth
   cpu_baseline  the unmodified reference binary (oracle/_ref/ropebwt2 -LRs) on a bounded sample
 
 `--impl reference` times the reference's own CPU implementation (all the threads it can use:
@@ -289,15 +289,23 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # dominant kernel: k_merge_half (two leaf blocks per warp).  Its algorithmic bytes: every item it
-    # finishes reads one 512-byte leaf block and writes it back (split pieces are not counted); items it
-    # hands on to k_merge_fast / k_merge_general are excluded together with those kernels' time.
-    fast_items = st["merge_blocks"] - st["general_items"]
-    fast_bytes = fast_items * 2 * 512
+    # dominant kernel.  Dense regime (the headline workload): k_flat_merge, one streaming pass per column
+    # over the flat symbol array -- algorithmic bytes = old array read + new array written + records
+    # (20 B read, 8 B rank written each).  Sparse regime: k_merge_half (two leaf blocks per warp) --
+    # every item it finishes reads one 512-byte leaf block and writes it back.
+    dense = st.get("flat_batches", 0) > 0
+    if dense:
+        kernel = "k_flat_merge"
+        fast_items = st["merge_blocks"]
+        fast_bytes = st["merge_bytes_rw"]
+    else:
+        kernel = "k_merge_half"
+        fast_items = st["merge_blocks"] - st["general_items"]
+        fast_bytes = fast_items * 2 * 512
     merge_gbs = fast_bytes / (st["ms_merge"] * 1e-3) / 1e9 if st["ms_merge"] > 0 else 0.0
     traffic = None
     traffic_info = None
-    ncu_json = os.path.join(ROOT, "profiles", "merge_traffic.json")
+    ncu_json = os.path.join(ROOT, "profiles", "flat_merge_traffic.json" if dense else "merge_traffic.json")
     if os.path.exists(ncu_json):
         traffic_info = {k: v for k, v in json.load(open(ncu_json)).items() if k in ("capture", "items_in_launch", "algorithmic_bytes_same_launch", "note")}
         traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")  # one late launch (column 90) at this workload size
@@ -320,13 +328,13 @@ def main():
                 "ms_per_step": ms_e2e / args.steps, "wall_s_per_step": wall_e2e / args.steps,
                 "api": e2e_api},
         "gpu_launches": int(st["n_launches"]),
-        "roofline": {"bound": "hbm", "kernel": "k_merge_half", "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
                      "frac": merge_gbs / peak, "traffic": traffic, "traffic_capture": traffic_info, "peak_source": peak_src,
                      "launches": int(st["n_merge_launches"]), "ms_in_kernel": st["ms_merge"],
-                     "algorithmic_bytes": int(fast_bytes), "items": int(fast_items),
+                     "algorithmic_bytes": int(fast_bytes), "items": int(fast_items), "regime": "dense (flat symbol array)" if dense else "sparse (leaf blocks)",
                      "items_left_to_k_merge_fast_and_general": int(st["general_items"]), "ms_in_k_merge_fast_and_general": st["ms_merge_general"],
                      "share_of_step": st["ms_merge"] / st["ms_total"] if st["ms_total"] else None},
-        "phases_ms_per_step": {k: st[k] / args.steps for k in ("ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_merge_general", "ms_directory", "ms_exchange")},
+        "phases_ms_per_step": {k: st[k] / args.steps for k in ("ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_merge_general", "ms_directory", "ms_exchange", "ms_convert")},
     }
     if sharded:
         out["exchange"] = {"ms_per_step_max_over_ranks": ms_exch / args.steps, "bytes_received_per_step_rank0": int(st["exch_bytes"] / args.steps),

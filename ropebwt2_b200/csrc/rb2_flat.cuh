@@ -161,7 +161,7 @@ struct FlatSmem {
 	uint4    old4[FT_NCH];               // the old symbols this tile needs, from a directory tile boundary
 	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every 16-byte chunk of old4 (16-bit fields)
 	uint16_t sKey[FT_OUT + 1], sPre[FT_OUT + 1]; // staged records: run start inside the tile, record symbols in front of it
-	uint32_t sLS[FT_OUT + 1];            // (run length inside the tile) << 3 | symbol
+	uint16_t sLS[FT_OUT + 1];            // (run length inside the tile) << 3 | symbol
 	uint16_t sFirst[FT_OUT / 16 + 2];    // first staged record that starts at or behind each 16-symbol output chunk
 	uint32_t warpTot[8][3];
 	uint32_t recCnt[FT_SUB][6];          // symbols the records put into each FT_DIR sub-tile
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 		}
 		if (lane == 31) { S.warpTot[wid][0] = inc[0]; S.warpTot[wid][1] = inc[1]; S.warpTot[wid][2] = inc[2]; }
 	} else {
-		if (tid == NCNT && nCarry) { S.sKey[0] = 0; S.sPre[0] = 0; S.sLS[0] = (carryLen << 3) | carrySym; }
+		if (tid == NCNT && nCarry) { S.sKey[0] = 0; S.sPre[0] = 0; S.sLS[0] = (uint16_t)((carryLen << 3) | carrySym); }
 		if (tid - NCNT < FT_SUB * 6) (&S.recCnt[0][0])[tid - NCNT] = 0;
 		for (uint32_t k = tid - NCNT; k < r1 - r0; k += 256 - NCNT) {
 			const uint32_t r = r0 + k;
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 			const uint32_t key = (uint32_t)((uint64_t)A.recP[r] + pre - o0);
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
-			S.sKey[nCarry + k] = (uint16_t)key; S.sPre[nCarry + k] = (uint16_t)(pre - before); S.sLS[nCarry + k] = (len << 3) | (sc & 7u);
+			S.sKey[nCarry + k] = (uint16_t)key; S.sPre[nCarry + k] = (uint16_t)(pre - before); S.sLS[nCarry + k] = (uint16_t)((len << 3) | (sc & 7u));
 		}
 	}
 	__syncthreads();
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 			const uint32_t cLo = k == 0 ? 0u : ((uint32_t)S.sKey[k - 1] >> 4) + 1, cHi = k == nS ? FT_OUT / 16 : (uint32_t)S.sKey[k] >> 4;
 			for (uint32_t c = cLo; c <= cHi; ++c) S.sFirst[c] = (uint16_t)k;
 			if (k < nS) { // symbols the record puts into each sub-tile
-				uint32_t key = S.sKey[k], len = S.sLS[k] >> 3; const uint32_t a = S.sLS[k] & 7u;
+				uint32_t key = S.sKey[k], len = (uint32_t)S.sLS[k] >> 3; const uint32_t a = S.sLS[k] & 7u;
 				while (len) {
 					const uint32_t sb = key / FT_DIR, room = (sb + 1) * FT_DIR - key, n = len < room ? len : room;
 					atomicAdd(&S.recCnt[sb][a], n);
@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 	const uint32_t rel = tid * 16;
 	const uint32_t k0 = S.sFirst[tid];  // first entry with sKey >= rel
 	uint32_t runRem = 0, runSym = 0, oldIdx;
-	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + (S.sLS[k0 - 1] >> 3) > rel) {
-		runRem = (uint32_t)S.sKey[k0 - 1] + (S.sLS[k0 - 1] >> 3) - rel; runSym = S.sLS[k0 - 1] & 7u;
+	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + ((uint32_t)S.sLS[k0 - 1] >> 3) > rel) {
+		runRem = (uint32_t)S.sKey[k0 - 1] + ((uint32_t)S.sLS[k0 - 1] >> 3) - rel; runSym = S.sLS[k0 - 1] & 7u;
 		oldIdx = (uint32_t)S.sKey[k0 - 1] - S.sPre[k0 - 1] + skip;
 	} else {
 		const uint32_t preAt = k0 < nS ? S.sPre[k0] : recIn;
@@ -283,8 +283,20 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 		ow[0] = __funnelshift_r(x0, x1, sh); ow[1] = __funnelshift_r(x1, x2, sh); ow[2] = __funnelshift_r(x2, x3, sh); ow[3] = __funnelshift_r(x3, x4, sh);
 	}
 	const uint32_t nextKey = k0 < nS ? S.sKey[k0] : 0xffffffffu;
+	const uint32_t nextKey2 = k0 + 1 < nS ? S.sKey[k0 + 1] : 0xffffffffu;
 	if (runRem >= 16) {                             // inside one long run
 		ow[0] = ow[1] = ow[2] = ow[3] = runSym * 0x01010101u;
+	} else if (runRem == 0 && nextKey < rel + 16 && nextKey2 >= rel + 16 && ((uint32_t)S.sLS[k0] >> 3) == 1) {
+		// the common case late in a batch: exactly one single-symbol record among these 16 symbols.
+		// out[j] = V0[j] (j < p), symbol (j == p), V0[j-1] (j > p)
+		const uint32_t pp = nextKey - rel, pw = pp >> 2, pb = (pp & 3) * 8, sy = S.sLS[k0] & 7u;
+		const uint32_t w1[4] = { ow[0] << 8, __funnelshift_l(ow[0], ow[1], 8), __funnelshift_l(ow[1], ow[2], 8), __funnelshift_l(ow[2], ow[3], 8) };
+		const uint32_t lowMask = (1u << pb) - 1u;     // bytes in front of p inside its word
+#pragma unroll
+		for (int w = 0; w < 4; ++w) {
+			const uint32_t mid = (ow[w] & lowMask) | (sy << pb) | (w1[w] & ~((lowMask << 8) | 0xffu));
+			ow[w] = (uint32_t)w < pw ? ow[w] : ((uint32_t)w > pw ? w1[w] : mid);
+		}
 	} else if (runRem || nextKey < rel + 16) {      // records start (or a run ends) inside these 16 symbols
 		typedef unsigned __int128 u128;
 		auto fill = [](uint32_t sy) -> u128 { const uint64_t f = 0x0101010101010101ull * sy; return ((u128)f << 64) | f; };
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 			const uint32_t cnt = nk - pos;            // old symbols in front of the next record (< 16 here)
 			if (cnt) { R |= (O & ((((u128)1) << (8 * cnt)) - 1)) << (8 * pos); O >>= 8 * cnt; pos = nk; }
 			if (pos >= 16) break;
-			uint32_t len = S.sLS[k] >> 3; const uint32_t sy = S.sLS[k] & 7u;
+			uint32_t len = (uint32_t)S.sLS[k] >> 3; const uint32_t sy = S.sLS[k] & 7u;
 			if (len > 16 - pos) len = 16 - pos;
 			if (len == 16) { R = fill(sy); break; }
 			R |= (fill(sy) & ((((u128)1) << (8 * len)) - 1)) << (8 * pos);

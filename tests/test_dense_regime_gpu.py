@@ -1,0 +1,66 @@
+"""GPU parity tests of the DENSE regime (csrc/rb2_flat.cuh): for the duration of a batch the BWT is a
+flat symbol array rewritten by one streaming kernel per column, then re-encoded into leaf blocks.
+The engine picks the regime per batch (RB2_FLAT=1 / 0 forces it); either way the decoded BWT must be
+the oracle's bit for bit, and batches of the two regimes must chain (blocks -> flat -> blocks)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from ropebwt2_b200 import MRope, load
+from ropebwt2_b200.synth import encode_batch, genome_reads, uniform_reads, varlen_reads
+
+pytestmark = pytest.mark.gpu
+
+
+def text(m):
+    return orc.decode_index(load(), m.h, m.total())[0]
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_forced_dense_multi_batch(monkeypatch, so):
+    monkeypatch.setenv("RB2_FLAT", "1")
+    rd = genome_reads(9000, 60, 13 + so, coverage=40.0)
+    o, m = orc.Oracle(so), MRope(so)
+    for part in (rd[:4000], rd[4000:6000], rd[6000:]):
+        buf = encode_batch(part, True, so == 2)
+        o.insert_multi(buf)
+        m.insert_multi(buf)
+        assert np.array_equal(text(m), o.text())
+    assert m.stats()["flat_batches"] == 3
+    assert np.array_equal(m.counts(), o.counts())
+    m.close()
+
+
+@pytest.mark.parametrize("so", [0, 1])
+def test_regimes_alternate(monkeypatch, so):
+    """dense, sparse, dense, sparse on one index: both conversions, non-empty intervals in both regimes"""
+    o, m = orc.Oracle(so), MRope(so)
+    for i, seed in enumerate((1, 2, 3, 4)):
+        monkeypatch.setenv("RB2_FLAT", "1" if i % 2 == 0 else "0")
+        buf = encode_batch(varlen_reads(1500, 70, seed), True, True)
+        o.insert_multi(buf)
+        m.insert_multi(buf)
+        assert np.array_equal(text(m), o.text()), (so, i)
+    assert m.stats()["flat_batches"] == 2
+    # the re-encoded pool is a legal index for the single-string path and for rank queries
+    one = encode_batch(uniform_reads(1, 40, 9))
+    o.insert_multi(one)
+    m.insert1(one)
+    assert np.array_equal(text(m), o.text())
+    for x in (0, 1, o.total() // 3, o.total()):
+        assert np.array_equal(m.rank2a(x)[0], o.rank1a(x))
+    m.close()
+
+
+def test_auto_choice_and_big_counts(monkeypatch):
+    """without RB2_FLAT the engine picks dense for a short-read batch of this size; 300k copies of one
+    read give per-symbol counts above the 4-byte run limit (records split, runs longer than a tile)"""
+    monkeypatch.delenv("RB2_FLAT", raising=False)
+    rd = np.concatenate([uniform_reads(150000, 101, 5), np.tile(uniform_reads(1, 101, 6), (600000, 1))])
+    o, m = orc.Oracle(1), MRope(1)
+    buf = encode_batch(rd)
+    o.insert_multi(buf)
+    m.insert_multi(buf)
+    assert m.stats()["flat_batches"] == 1
+    assert np.array_equal(text(m), o.text())
+    m.close()
