@@ -1756,9 +1756,9 @@ enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, P
 // dense regime (rb2_flat.cuh): the BWT as a flat array of symbols for the duration of one batch
 struct FlatState {
 	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
-	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0; DevBuf<TileDesc> desc;
+	DevBuf<uint8_t> s[2], bytes; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0, ovf; DevBuf<TileDesc> desc;
 	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
-	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+	void release() { bytes.release(); for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
 };
 
 struct rb2_engine {
@@ -1962,6 +1962,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmemT<FT_OUT>)));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);
@@ -2244,8 +2245,10 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			for (int b = 0; b < 6; ++b) if (gBkt[b + 1] > gBkt[b]) e->lastBkt = b;
 		}
 		const rb2_stats_t before = e->stats;
-		if (flat) flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p);
-		else apply_records(e, nrec, e->gL[cs ^ 1].p);
+		if (flat) {
+			flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p);
+			if (column_log()) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, e->flat.pending); e->flat.pending = 0; } // per-column times
+		} else apply_records(e, nrec, e->gL[cs ^ 1].p);
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
 		if (FILE *cl = column_log()) // developer aid: RB2_COLLOG=<file> gets one line per column

@@ -3,9 +3,9 @@
 // When a batch inserts into (nearly) every leaf block in every column -- short reads, the headline
 // workload: 100 M records per column into <= 20 M blocks -- updating run-length coded blocks record
 // by record is instruction bound (profiles/README.md).  For such a batch the engine keeps the BWT,
-// for the duration of the batch only, as ONE flat array of nt6 codes (one byte per symbol, all six
-// buckets concatenated) plus a directory of per-symbol counts in front of every FT_DIR-th symbol,
-// and one column becomes a single streaming pass (k_flat_merge):
+// for the duration of the batch only, as ONE flat array of nt6 codes (4 bits per symbol, two per
+// byte, low nibble first; all six buckets concatenated) plus a directory of per-symbol counts in
+// front of every FT_DIR-th symbol, and one column becomes a single streaming pass (k_flat_merge):
 //
 //   new[P_r + pre_r .. + c_r) = symbol of record r     (pre_r = members in front of record r, i.e. the
 //   old symbol i moves to i + #record symbols with P<=i  symbols this column inserts in front of it)
@@ -13,41 +13,40 @@
 // which is exactly the stable merge rope_insert_run performs one run at a time (rope.c:114-148;
 // new symbols go in FRONT of the old symbol at the same position, mrope.c:206-218), and
 // rank(a, P_r) -- the return value of rope_insert_run / rle_insert_cached (rle.c:10-89) -- is
-// directory[P_r / FT_DIR][a] + a count over < FT_DIR + 4096 symbols held in shared memory.
-// Output-stationary: CTA t produces new[t*4096, (t+1)*4096) with aligned 128-bit stores; the old
+// directory[P_r / FT_DIR][a] + a count over < FT_DIR + FT_OUT symbols held in shared memory.
+// Output-stationary: CTA t produces new[t*FT_OUT, (t+1)*FT_OUT) with aligned 128-bit stores; the old
 // symbols it needs are one contiguous range.  At the end of the batch the array is re-encoded into
 // leaf blocks of the reference's format (k_flat_encode), so everything outside the batch (iterator,
 // dump, rank queries, sparse batches) sees the usual block pool.
 #pragma once
 #include "rb2_codec.cuh"
 
-#define FT_OUT   4096  // output symbols per CTA of k_flat_merge: 256 threads x 16 bytes
-#define FT_DIR   1024  // directory granularity (48 bytes of counts per 1024 symbols)
+#define FT_OUT   8192  // output symbols per CTA of k_flat_merge: 256 threads x 32 symbols (16 bytes)
+#define FT_DIR   2048  // directory granularity (48 bytes of counts per 1024 bytes of symbols)
 #define FT_SUB   (FT_OUT / FT_DIR)
 #define FT_OLDMAX (FT_OUT + FT_DIR) // old symbols one CTA can need: from the directory tile of its first one
-#define FT_PAD   (FT_OLDMAX + 64)   // readable slack behind a flat array
+#define FT_PAD   (FT_OLDMAX + 128)  // readable slack (symbols) behind a flat array
+#define FT_CH    32    // symbols per 16-byte chunk
 #define FE_CHUNK 64    // flat -> blocks: symbols encoded by one thread (<= 64 bytes of runs)
 #define FE_T     (RB2_FILL - FE_CHUNK + 1) // block k of a bucket takes the chunks that start in bytes [k*FE_T, (k+1)*FE_T)
 
+__host__ __device__ __forceinline__ uint64_t flat_bytes(uint64_t symbols) { return (symbols + 1) >> 1; }
+__device__ __forceinline__ uint32_t flat_get(const uint8_t *flat, uint64_t i) { return (flat[i >> 1] >> ((i & 1) * 4)) & 15u; }
+
 // ---- per-symbol counting without per-symbol compares ---------------------------------------------
-// nt6 codes: $=000 A=001 C=010 G=011 T=100 N=101.  For four codes in a word, the bytes of
-//   m0 = bit0, m1 = bit1, m2 = bit2, m01 = bit0&bit1 (G), m02 = bit0&bit2 (N)
-// are 0/1 and can be summed byte-wise over up to 255 words; five horizontal sums then give
-//   N = s02, G = s01, A = s0 - s01 - s02, C = s1 - s01, T = s2 - s02, $ = n - (A+C+G+T+N).
+// nt6 codes: $=000 A=001 C=010 G=011 T=100 N=101 (bit 3 of a nibble is always 0).  For the eight
+// codes of a word, popcounts of
+//   m0 = bit0, m1 = bit1, m2 = bit2, m0&m1 (G), m0&m2 (N)
+// give N = s02, G = s01, A = s0 - s01 - s02, C = s1 - s01, T = s2 - s02, $ = n - (A+C+G+T+N).
 // "Raw" counts (s0, s1, s2, s01, s02, n) are linear, so prefix sums are taken on them and converted
 // only where a symbol count is needed.
 struct Raw6 { uint32_t s0, s1, s2, s01, s02, n; };
 
-__device__ __forceinline__ void raw_add_words(const uint32_t *w, int nw, uint32_t (&acc)[5])
+__device__ __forceinline__ void raw_add_word(uint32_t x, uint32_t (&acc)[5])
 {
-#pragma unroll
-	for (int j = 0; j < nw; ++j) {
-		const uint32_t x = w[j];
-		const uint32_t m0 = x & 0x01010101u, m1 = (x >> 1) & 0x01010101u, m2 = (x >> 2) & 0x01010101u;
-		acc[0] += m0; acc[1] += m1; acc[2] += m2; acc[3] += m0 & m1; acc[4] += m0 & m2;
-	}
+	const uint32_t m0 = x & 0x11111111u, m1 = (x >> 1) & 0x11111111u, m2 = (x >> 2) & 0x11111111u;
+	acc[0] += __popc(m0); acc[1] += __popc(m1); acc[2] += __popc(m2); acc[3] += __popc(m0 & m1); acc[4] += __popc(m0 & m2);
 }
-__device__ __forceinline__ uint32_t hsum4(uint32_t x) { return __dp4a(x, 0x01010101u, 0u); }
 
 __device__ __forceinline__ uint32_t raw_symbol(const Raw6 &r, uint32_t a)
 {
@@ -62,36 +61,28 @@ __device__ __forceinline__ uint32_t raw_symbol(const Raw6 &r, uint32_t a)
 	}
 }
 
-// two 64-bit words hold the six raw counts in 21-bit fields (CTA-level sums stay below 2^21)
-__device__ __forceinline__ void raw_pack(const Raw6 &r, uint64_t (&p)[2])
+// keep the first ns (0..32) symbols of a 16-byte chunk, zero the rest
+__device__ __forceinline__ void chunk_mask(uint32_t (&w)[4], uint32_t ns)
 {
-	p[0] = (uint64_t)r.s0 | (uint64_t)r.s1 << 21 | (uint64_t)r.s2 << 42;
-	p[1] = (uint64_t)r.s01 | (uint64_t)r.s02 << 21 | (uint64_t)r.n << 42;
-}
-__device__ __forceinline__ Raw6 raw_unpack(const uint64_t (&p)[2])
-{
-	Raw6 r;
-	r.s0 = (uint32_t)p[0] & 0x1fffffu; r.s1 = (uint32_t)(p[0] >> 21) & 0x1fffffu; r.s2 = (uint32_t)(p[0] >> 42) & 0x1fffffu;
-	r.s01 = (uint32_t)p[1] & 0x1fffffu; r.s02 = (uint32_t)(p[1] >> 21) & 0x1fffffu; r.n = (uint32_t)(p[1] >> 42) & 0x1fffffu;
-	return r;
-}
-
-// raw counts of the first nb (0..16) bytes of four words
-__device__ __forceinline__ Raw6 raw_count16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t nb)
-{
-	uint32_t w[4] = { w0, w1, w2, w3 };
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
-		const uint32_t kb = nb > (uint32_t)j * 4 ? nb - j * 4 : 0;
-		w[j] = kb >= 4 ? w[j] : (kb ? w[j] & ((1u << (kb * 8)) - 1u) : 0u);
+		const uint32_t k = ns > (uint32_t)j * 8 ? ns - j * 8 : 0;
+		w[j] = k >= 8 ? w[j] : (k ? w[j] & ((1u << (k * 4)) - 1u) : 0u);
 	}
+}
+
+// raw counts of the first ns (0..32) symbols of a 16-byte chunk
+__device__ __forceinline__ Raw6 raw_count_chunk(const uint4 &v, uint32_t ns)
+{
+	uint32_t w[4] = { v.x, v.y, v.z, v.w };
+	if (ns < FT_CH) chunk_mask(w, ns);
 	uint32_t acc[5] = { 0, 0, 0, 0, 0 };
-	raw_add_words(w, 4, acc);
-	Raw6 r;
-	r.s0 = hsum4(acc[0]); r.s1 = hsum4(acc[1]); r.s2 = hsum4(acc[2]); r.s01 = hsum4(acc[3]); r.s02 = hsum4(acc[4]);
-	r.n = nb;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) raw_add_word(w[j], acc);
+	Raw6 r = { acc[0], acc[1], acc[2], acc[3], acc[4], ns };
 	return r;
 }
+__device__ __forceinline__ void raw_addto(Raw6 &a, const Raw6 &b) { a.s0 += b.s0; a.s1 += b.s1; a.s2 += b.s2; a.s01 += b.s01; a.s02 += b.s02; a.n += b.n; }
 
 // ---- tile -> record ranges ---------------------------------------------------------------------------
 // tileR0[t] = first record whose output run starts at or behind t*FT_OUT (key_r = P_r + pre_r); one
@@ -133,22 +124,17 @@ struct FlatArgs {
 	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its raw per-FT_DIR-tile symbol counts
 	const int64_t *recP; const uint32_t *recPre, *recSC, *recDst; uint32_t R;
 	const TileDesc *desc;
+	uint32_t *ovf;           // [0] tiles left to k_flat_merge_dense, [1] its work counter, [2..] the tiles
 	int64_t *gLNext; const Ctl *ctl;
 	// sharded engines: records carry whole-index positions; bucket b of this rank sits recOff[b*7+6]
 	// symbols (recOff[b*7+a] symbols a) further right in the whole index than in the local array
 	const int64_t *recOff; int nb;
 };
 
-// raw counts of 16 bytes, no masking (callers only use prefixes that end inside valid data)
-__device__ __forceinline__ void raw_acc16(const uint4 &x, uint32_t (&acc)[5])
-{
-	const uint32_t w[4] = { x.x, x.y, x.z, x.w };
-	raw_add_words(w, 4, acc);
-}
 // six raw counts as three words of two 16-bit fields (sums stay below 2^16 inside one tile)
 __device__ __forceinline__ void raw_pack16(const uint32_t (&acc)[5], uint32_t n, uint32_t (&p)[3])
 {
-	p[0] = hsum4(acc[0]) | hsum4(acc[1]) << 16; p[1] = hsum4(acc[2]) | hsum4(acc[3]) << 16; p[2] = hsum4(acc[4]) | n << 16;
+	p[0] = acc[0] | acc[1] << 16; p[1] = acc[2] | acc[3] << 16; p[2] = acc[4] | n << 16;
 }
 __device__ __forceinline__ Raw6 raw_unpack16(uint32_t p0, uint32_t p1, uint32_t p2)
 {
@@ -156,26 +142,41 @@ __device__ __forceinline__ Raw6 raw_unpack16(uint32_t p0, uint32_t p1, uint32_t 
 	return r;
 }
 
-#define FT_NCH (FT_OLDMAX / 16 + 2)   // 16-byte chunks of old symbols one tile can hold
-struct FlatSmem {
+#define FT_NCH (FT_OLDMAX / FT_CH + 2)   // 16-byte chunks of old symbols one tile can hold
+#define FT_NOC (FT_OUT / FT_CH)          // 32-symbol output chunks per tile = threads per CTA
+#define FT_CAP_SMALL 2047                // records per tile the main kernel stages (more: overflow kernel, same code)
+template <int CAP> struct FlatSmemT {
 	uint4    old4[FT_NCH];               // the old symbols this tile needs, from a directory tile boundary
 	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every 16-byte chunk of old4 (16-bit fields)
-	uint16_t sKey[FT_OUT + 1], sPre[FT_OUT + 1]; // staged records: run start inside the tile, record symbols in front of it
-	uint16_t sLS[FT_OUT + 1];            // (run length inside the tile) << 3 | symbol
-	uint16_t sFirst[FT_OUT / 16 + 2];    // first staged record that starts at or behind each 16-symbol output chunk
+	uint16_t sKey[CAP + 1];              // staged records: run start inside the tile
+	uint16_t sLS[CAP + 1];               // (run length inside the tile - 1) << 3 | symbol
 	uint32_t warpTot[8][3];
 	uint32_t recCnt[FT_SUB][6];          // symbols the records put into each FT_DIR sub-tile
 	uint32_t subX[FT_SUB + 1];           // old symbols (local index) in front of each sub-tile
+	uint32_t tile;                       // overflow kernel: the tile this CTA works on
 };
 
-__global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
+// insert one symbol at nibble position pp (0..31) of a 32-symbol vector; the last symbol falls out
+__device__ __forceinline__ void insert_symbol(uint32_t (&ow)[4], uint32_t pp, uint32_t sy)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
-	FlatSmem &S = *reinterpret_cast<FlatSmem*>(smraw);
+	const uint32_t pw = pp >> 3, pb = (pp & 7) * 4;
+	const uint32_t w1[4] = { ow[0] << 4, __funnelshift_l(ow[0], ow[1], 4), __funnelshift_l(ow[1], ow[2], 4), __funnelshift_l(ow[2], ow[3], 4) };
+	const uint32_t lowMask = (1u << pb) - 1u;     // symbols in front of pp inside its word
+#pragma unroll
+	for (int w = 0; w < 4; ++w) {
+		const uint32_t mid = (ow[w] & lowMask) | (sy << pb) | (w1[w] & ~((lowMask << 4) | 0xfu));
+		ow[w] = (uint32_t)w < pw ? ow[w] : ((uint32_t)w > pw ? w1[w] : mid);
+	}
+}
+
+// One output tile.  Two barriers: (A) old symbols + their counts | records -> shared memory, (B) every
+// thread assembles its 32 output symbols, (C) ranks of the tile's records | symbol counts of its sub-tiles.
+template <int CAP>
+__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP> &S, const uint32_t tile, const TileDesc d0, const TileDesc d1)
+{
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const uint64_t o0 = (uint64_t)blockIdx.x * FT_OUT;
+	const uint64_t o0 = (uint64_t)tile * FT_OUT;
 	const uint32_t tileLen = A.nNew - o0 < FT_OUT ? (uint32_t)(A.nNew - o0) : FT_OUT;
-	const TileDesc d0 = A.desc[blockIdx.x], d1 = A.desc[blockIdx.x + 1];
 	const uint32_t r0 = d0.r0, r1 = d1.r0;
 	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < tileLen ? (d0.carry >> 3) : tileLen;
 	const uint64_t i0 = d0.i0;                     // old symbols [i0, i1) land in this tile
@@ -183,25 +184,24 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 	const uint32_t loadLen = (uint32_t)(d1.i0 - a0), skip = (uint32_t)(i0 - a0);
 	const uint32_t recIn = tileLen - (loadLen - skip); // record symbols inside the tile
 	const uint64_t before = o0 - i0;               // record symbols in front of the tile
-	const uint32_t nLoad = (loadLen >> 4) + 2;     // chunks that are read (<= FT_NCH)
+	const uint32_t nLoad = loadLen / FT_CH + 2;    // chunks that are read (<= FT_NCH)
 	const uint32_t nCarry = carryLen ? 1u : 0u, nS = nCarry + (r1 - r0);
 	constexpr int NCNT = 160;                      // threads (5 warps) that load + count; the other 3 warps stage records
 
 	// ---- phase A: old symbols -> shared memory + raw counts per chunk pair | records -> shared memory -------
 	uint32_t p[3] = { 0, 0, 0 }, q[3] = { 0, 0, 0 }, inc[3] = { 0, 0, 0 };
 	if (tid < NCNT) {
-		// thread j owns chunks 2j, 2j+1 (bytes behind loadLen are whatever follows in the array: the
+		// thread j owns chunks 2j, 2j+1 (symbols behind loadLen are whatever follows in the array: the
 		// prefixes that include them are never used)
-		const uint4 *src = reinterpret_cast<const uint4*>(A.oldS + a0);
+		const uint4 *src = reinterpret_cast<const uint4*>(A.oldS + (a0 >> 1));
 		if ((uint32_t)tid * 2 < nLoad) {
 			const uint4 x = src[tid * 2], y = src[tid * 2 + 1];
 			S.old4[tid * 2] = x; S.old4[tid * 2 + 1] = y;
-			uint32_t ax[5] = { 0, 0, 0, 0, 0 }, ay[5] = { 0, 0, 0, 0, 0 };
-			raw_acc16(x, ax); raw_acc16(y, ay);
-			raw_pack16(ax, 16, q);
-			raw_pack16(ay, 16, p);
-#pragma unroll
-			for (int k = 0; k < 3; ++k) p[k] += q[k];
+			uint32_t acc[5] = { 0, 0, 0, 0, 0 };
+			raw_add_word(x.x, acc); raw_add_word(x.y, acc); raw_add_word(x.z, acc); raw_add_word(x.w, acc);
+			raw_pack16(acc, FT_CH, q);
+			raw_add_word(y.x, acc); raw_add_word(y.y, acc); raw_add_word(y.z, acc); raw_add_word(y.w, acc);
+			raw_pack16(acc, 2 * FT_CH, p);
 		}
 #pragma unroll
 		for (int k = 0; k < 3; ++k) inc[k] = p[k];
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 		}
 		if (lane == 31) { S.warpTot[wid][0] = inc[0]; S.warpTot[wid][1] = inc[1]; S.warpTot[wid][2] = inc[2]; }
 	} else {
-		if (tid == NCNT && nCarry) { S.sKey[0] = 0; S.sPre[0] = 0; S.sLS[0] = (uint16_t)((carryLen << 3) | carrySym); }
+		if (tid == NCNT && nCarry) { S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym); }
 		if (tid - NCNT < FT_SUB * 6) (&S.recCnt[0][0])[tid - NCNT] = 0;
 		for (uint32_t k = tid - NCNT; k < r1 - r0; k += 256 - NCNT) {
 			const uint32_t r = r0 + k;
@@ -220,138 +220,143 @@ __global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
 			const uint32_t key = (uint32_t)((uint64_t)A.recP[r] + pre - o0);
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
-			S.sKey[nCarry + k] = (uint16_t)key; S.sPre[nCarry + k] = (uint16_t)(pre - before); S.sLS[nCarry + k] = (uint16_t)((len << 3) | (sc & 7u));
+			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
 		}
 	}
 	__syncthreads();
-	// ---- phase B: prefix in front of every chunk | first record per output chunk, record symbols per sub-tile ----
-	if (tid < NCNT) {
-		if ((uint32_t)tid * 2 < nLoad) {
-			uint32_t base[3] = { 0, 0, 0 };
-			for (int w = 0; w < wid; ++w) { base[0] += S.warpTot[w][0]; base[1] += S.warpTot[w][1]; base[2] += S.warpTot[w][2]; }
+	// ---- phase B: prefix in front of every chunk (needed behind the next barrier) ------------------------
+	if (tid < NCNT && (uint32_t)tid * 2 < nLoad) {
+		uint32_t base[3] = { 0, 0, 0 };
+		for (int w = 0; w < wid; ++w) { base[0] += S.warpTot[w][0]; base[1] += S.warpTot[w][1]; base[2] += S.warpTot[w][2]; }
 #pragma unroll
-			for (int k = 0; k < 3; ++k) {
-				const uint32_t ex = base[k] + inc[k] - p[k];
-				S.chunkPre[tid * 2][k] = ex; S.chunkPre[tid * 2 + 1][k] = ex + q[k];
-			}
-		}
-	} else {
-		for (uint32_t k = tid - NCNT; k <= nS; k += 256 - NCNT) {
-			const uint32_t cLo = k == 0 ? 0u : ((uint32_t)S.sKey[k - 1] >> 4) + 1, cHi = k == nS ? FT_OUT / 16 : (uint32_t)S.sKey[k] >> 4;
-			for (uint32_t c = cLo; c <= cHi; ++c) S.sFirst[c] = (uint16_t)k;
-			if (k < nS) { // symbols the record puts into each sub-tile
-				uint32_t key = S.sKey[k], len = (uint32_t)S.sLS[k] >> 3; const uint32_t a = S.sLS[k] & 7u;
-				while (len) {
-					const uint32_t sb = key / FT_DIR, room = (sb + 1) * FT_DIR - key, n = len < room ? len : room;
-					atomicAdd(&S.recCnt[sb][a], n);
-					key += n; len -= n;
-				}
-			}
+		for (int k = 0; k < 3; ++k) {
+			const uint32_t ex = base[k] + inc[k] - p[k];
+			S.chunkPre[tid * 2][k] = ex; S.chunkPre[tid * 2 + 1][k] = ex + q[k];
 		}
 	}
-	__syncthreads();
-	// raw counts in front of local old index x
-	auto prefix_at = [&](uint32_t x) -> Raw6 {
-		const uint32_t c = x >> 4;
-		Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
-		if (x & 15u) {
-			const uint4 v = S.old4[c];
-			const Raw6 part = raw_count16(v.x, v.y, v.z, v.w, x & 15u);
-			rr.s0 += part.s0; rr.s1 += part.s1; rr.s2 += part.s2; rr.s01 += part.s01; rr.s02 += part.s02; rr.n += part.n;
-		}
-		return rr;
-	};
-	// ---- phase C: assemble 16 output symbols per thread ------------------------------------------------
-	const uint32_t rel = tid * 16;
-	const uint32_t k0 = S.sFirst[tid];  // first entry with sKey >= rel
+	// ---- phase B: assemble 32 output symbols per thread ------------------------------------------------
+	// record symbols of this tile in front of staged entry k (the carried run counts from the tile start)
+	auto pre_rel = [&](uint32_t k) -> uint32_t { return k < nCarry ? 0u : (k < nS ? (uint32_t)(A.recPre[r0 + k - nCarry] - before) : recIn); };
+	auto run_len = [&](uint32_t k) -> uint32_t { return ((uint32_t)S.sLS[k] >> 3) + 1; };
+	const uint32_t rel = tid * FT_CH;
+	uint32_t k0;                        // first entry with sKey >= rel
+	{ uint32_t lo = 0, hi = nS; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.sKey[mid] >= rel) hi = mid; else lo = mid + 1; } k0 = lo; }
 	uint32_t runRem = 0, runSym = 0, oldIdx;
-	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + ((uint32_t)S.sLS[k0 - 1] >> 3) > rel) {
-		runRem = (uint32_t)S.sKey[k0 - 1] + ((uint32_t)S.sLS[k0 - 1] >> 3) - rel; runSym = S.sLS[k0 - 1] & 7u;
-		oldIdx = (uint32_t)S.sKey[k0 - 1] - S.sPre[k0 - 1] + skip;
-	} else {
-		const uint32_t preAt = k0 < nS ? S.sPre[k0] : recIn;
-		oldIdx = rel - preAt + skip;
-	}
-	if ((tid & (FT_DIR / 16 - 1)) == 0) S.subX[tid / (FT_DIR / 16)] = oldIdx < loadLen ? oldIdx : loadLen;
+	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) > rel) { // inside the run of entry k0-1
+		runRem = (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) - rel; runSym = S.sLS[k0 - 1] & 7u;
+		oldIdx = (uint32_t)S.sKey[k0 - 1] - pre_rel(k0 - 1) + skip;
+	} else oldIdx = rel - pre_rel(k0) + skip;
+	if ((tid & (FT_DIR / FT_CH - 1)) == 0) S.subX[tid / (FT_DIR / FT_CH)] = oldIdx < loadLen ? oldIdx : loadLen;
 	if (tid == 0) S.subX[FT_SUB] = loadLen;
+	const uint32_t sbMine = rel / FT_DIR;          // the sub-tile this chunk lies in
 	uint32_t ow[4];
 	{
-		// 16 old symbols from oldIdx on (unaligned)
-		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.old4) + (oldIdx >> 2);
-		const uint32_t sh = (oldIdx & 3) * 8;
+		// 32 old symbols from oldIdx on (unaligned)
+		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.old4) + (oldIdx >> 3);
+		const uint32_t sh = (oldIdx & 7) * 4;
 		const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4];
 		ow[0] = __funnelshift_r(x0, x1, sh); ow[1] = __funnelshift_r(x1, x2, sh); ow[2] = __funnelshift_r(x2, x3, sh); ow[3] = __funnelshift_r(x3, x4, sh);
 	}
-	const uint32_t nextKey = k0 < nS ? S.sKey[k0] : 0xffffffffu;
-	const uint32_t nextKey2 = k0 + 1 < nS ? S.sKey[k0 + 1] : 0xffffffffu;
-	if (runRem >= 16) {                             // inside one long run
-		ow[0] = ow[1] = ow[2] = ow[3] = runSym * 0x01010101u;
-	} else if (runRem == 0 && nextKey < rel + 16 && nextKey2 >= rel + 16 && ((uint32_t)S.sLS[k0] >> 3) == 1) {
-		// the common case late in a batch: exactly one single-symbol record among these 16 symbols.
-		// out[j] = V0[j] (j < p), symbol (j == p), V0[j-1] (j > p)
-		const uint32_t pp = nextKey - rel, pw = pp >> 2, pb = (pp & 3) * 8, sy = S.sLS[k0] & 7u;
-		const uint32_t w1[4] = { ow[0] << 8, __funnelshift_l(ow[0], ow[1], 8), __funnelshift_l(ow[1], ow[2], 8), __funnelshift_l(ow[2], ow[3], 8) };
-		const uint32_t lowMask = (1u << pb) - 1u;     // bytes in front of p inside its word
-#pragma unroll
-		for (int w = 0; w < 4; ++w) {
-			const uint32_t mid = (ow[w] & lowMask) | (sy << pb) | (w1[w] & ~((lowMask << 8) | 0xffu));
-			ow[w] = (uint32_t)w < pw ? ow[w] : ((uint32_t)w > pw ? w1[w] : mid);
+	if (runRem >= FT_CH) {                          // inside one long run
+		ow[0] = ow[1] = ow[2] = ow[3] = runSym * 0x11111111u;
+		atomicAdd(&S.recCnt[sbMine][runSym], FT_CH);
+	} else if (runRem || (k0 < nS && S.sKey[k0] < rel + FT_CH)) { // records start (or a run ends) inside these 32 symbols
+		// are all of them single symbols?  (the rule late in a batch)
+		uint32_t k = k0; bool single = runRem == 0;
+		while (single && k < nS && S.sKey[k] < rel + FT_CH) { single = ((uint32_t)S.sLS[k] >> 3) == 0; ++k; }
+		if (single) {
+			for (uint32_t j = k0; j < k; ++j) {
+				const uint32_t sy = S.sLS[j] & 7u;
+				insert_symbol(ow, (uint32_t)S.sKey[j] - rel, sy);
+				atomicAdd(&S.recCnt[sbMine][sy], 1u);
+			}
+		} else {
+			typedef unsigned __int128 u128;
+			auto fill = [](uint32_t sy) -> u128 { const uint64_t f = 0x1111111111111111ull * sy; return ((u128)f << 64) | f; };
+			u128 O = ((u128)(((uint64_t)ow[3] << 32) | ow[2]) << 64) | (((uint64_t)ow[1] << 32) | ow[0]); // nibble 0 = next old symbol
+			u128 R = 0;
+			uint32_t pos = 0;
+			k = k0;
+			if (runRem) { R = fill(runSym) & ((((u128)1) << (4 * runRem)) - 1); pos = runRem; atomicAdd(&S.recCnt[sbMine][runSym], runRem); }
+			while (pos < FT_CH) {
+				uint32_t nk = k < nS ? (uint32_t)S.sKey[k] - rel : (uint32_t)FT_CH;
+				if (nk > FT_CH) nk = FT_CH;
+				const uint32_t cnt = nk - pos;            // old symbols in front of the next record (< 32 here)
+				if (cnt) { R |= (O & ((((u128)1) << (4 * cnt)) - 1)) << (4 * pos); O >>= 4 * cnt; pos = nk; }
+				if (pos >= FT_CH) break;
+				uint32_t len = run_len(k); const uint32_t sy = S.sLS[k] & 7u;
+				if (len > FT_CH - pos) len = FT_CH - pos;
+				atomicAdd(&S.recCnt[sbMine][sy], len);
+				if (len == FT_CH) { R = fill(sy); break; }
+				R |= (fill(sy) & ((((u128)1) << (4 * len)) - 1)) << (4 * pos);
+				pos += len; ++k;
+			}
+			ow[0] = (uint32_t)R; ow[1] = (uint32_t)(R >> 32); ow[2] = (uint32_t)(R >> 64); ow[3] = (uint32_t)(R >> 96);
 		}
-	} else if (runRem || nextKey < rel + 16) {      // records start (or a run ends) inside these 16 symbols
-		typedef unsigned __int128 u128;
-		auto fill = [](uint32_t sy) -> u128 { const uint64_t f = 0x0101010101010101ull * sy; return ((u128)f << 64) | f; };
-		u128 O = ((u128)(((uint64_t)ow[3] << 32) | ow[2]) << 64) | (((uint64_t)ow[1] << 32) | ow[0]); // byte 0 = next old symbol
-		u128 R = 0;
-		uint32_t pos = 0, k = k0;
-		if (runRem) { R = fill(runSym) & ((((u128)1) << (8 * runRem)) - 1); pos = runRem; }
-		while (pos < 16) {
-			uint32_t nk = k < nS ? (uint32_t)S.sKey[k] - rel : 16u;
-			if (nk > 16) nk = 16;
-			const uint32_t cnt = nk - pos;            // old symbols in front of the next record (< 16 here)
-			if (cnt) { R |= (O & ((((u128)1) << (8 * cnt)) - 1)) << (8 * pos); O >>= 8 * cnt; pos = nk; }
-			if (pos >= 16) break;
-			uint32_t len = (uint32_t)S.sLS[k] >> 3; const uint32_t sy = S.sLS[k] & 7u;
-			if (len > 16 - pos) len = 16 - pos;
-			if (len == 16) { R = fill(sy); break; }
-			R |= (fill(sy) & ((((u128)1) << (8 * len)) - 1)) << (8 * pos);
-			pos += len; ++k;
-		}
-		ow[0] = (uint32_t)R; ow[1] = (uint32_t)(R >> 32); ow[2] = (uint32_t)(R >> 64); ow[3] = (uint32_t)(R >> 96);
 	}
 	// symbols behind the end of the array (last tile) are zero
-	if (rel + 16 > tileLen) {
-		const uint32_t nValid = rel >= tileLen ? 0u : tileLen - rel;
-#pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const uint32_t kb = nValid > (uint32_t)j * 4 ? nValid - j * 4 : 0;
-			ow[j] = kb >= 4 ? ow[j] : (kb ? ow[j] & ((1u << (kb * 8)) - 1u) : 0u);
+	if (rel + FT_CH > tileLen) chunk_mask(ow, rel >= tileLen ? 0u : tileLen - rel);
+	reinterpret_cast<uint4*>(A.newS + (o0 >> 1))[tid] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+	__syncthreads();
+	// raw counts in front of local old index x
+	auto prefix_at = [&](uint32_t x) -> Raw6 {
+		const uint32_t c = x / FT_CH;
+		Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
+		if (x & (FT_CH - 1)) raw_addto(rr, raw_count_chunk(S.old4[c], x & (FT_CH - 1)));
+		return rr;
+	};
+	// ---- phase C: symbol counts of the four FT_DIR sub-tiles = old symbols in them + record symbols (warp 0) ----
+	if (tid < FT_SUB * 6) {
+		const uint32_t sb = (uint32_t)tid / 6u, f = (uint32_t)tid % 6u;
+		const uint64_t dt = (uint64_t)tile * FT_SUB + sb;
+		if (dt * FT_DIR < A.nNew || dt == 0) {
+			const Raw6 lo = prefix_at(S.subX[sb]), hi = prefix_at(S.subX[sb + 1]);
+			A.newTileCnt[dt * 6 + f] = raw_symbol(hi, f) - raw_symbol(lo, f) + S.recCnt[sb][f];
 		}
 	}
-	reinterpret_cast<uint4*>(A.newS + o0)[tid] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-	// ---- rank(a, P) for the records that start in this tile (the last warps take them: they had the least to do) ----
+	// ---- phase C: rank(a, P) for the records that start in this tile (taken from the last warp downwards) ----
 	{
 		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
 		for (uint32_t k = 255 - tid; k < r1 - r0; k += 256) {
 			const uint32_t r = r0 + k, dst = A.recDst[r];
 			if (dst == NONE32) continue;
 			const uint32_t a = S.sLS[nCarry + k] & 7u;
-			const uint32_t x = (uint32_t)S.sKey[nCarry + k] - S.sPre[nCarry + k] + skip; // = P - a0
-			const Raw6 rr = prefix_at(x);
+			const Raw6 rr = prefix_at((uint32_t)((uint64_t)A.recP[r] - a0));
 			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a);
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
 				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r) * 7 + a];
 			A.gLNext[dst] = g;
 		}
 	}
-	// ---- symbol counts of the four FT_DIR sub-tiles = old symbols in them + record symbols -----------------
-	__syncthreads();
-	if (tid < FT_SUB * 6) {
-		const uint32_t sb = (uint32_t)tid / 6u, f = (uint32_t)tid % 6u;
-		const uint64_t tile = (uint64_t)blockIdx.x * FT_SUB + sb;
-		if (tile * FT_DIR < A.nNew || tile == 0) {
-			const Raw6 lo = prefix_at(S.subX[sb]), hi = prefix_at(S.subX[sb + 1]);
-			A.newTileCnt[tile * 6 + f] = raw_symbol(hi, f) - raw_symbol(lo, f) + S.recCnt[sb][f];
-		}
+}
+
+// main kernel: one CTA per tile; tiles with more records than it stages go to the overflow list
+__global__ void __launch_bounds__(256) k_flat_merge(FlatArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	FlatSmemT<FT_CAP_SMALL> &S = *reinterpret_cast<FlatSmemT<FT_CAP_SMALL>*>(smraw);
+	const TileDesc d0 = A.desc[blockIdx.x], d1 = A.desc[blockIdx.x + 1];
+	if (d1.r0 - d0.r0 + 1 > FT_CAP_SMALL) { // (+1: a run carried in from the left)
+		if (threadIdx.x == 0) A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = blockIdx.x;
+		return;
+	}
+	flat_merge_tile<FT_CAP_SMALL>(A, S, blockIdx.x, d0, d1);
+}
+
+// overflow kernel (persistent): tiles where records are dense -- small indexes, first columns of an input-order batch
+__global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smraw[];
+	FlatSmemT<FT_OUT> &S = *reinterpret_cast<FlatSmemT<FT_OUT>*>(smraw);
+	const uint32_t n = A.ovf[0];
+	for (;;) {
+		if (threadIdx.x == 0) S.tile = atomicAdd(&A.ovf[1], 1u);
+		__syncthreads();
+		const uint32_t q = S.tile;
+		if (q >= n) break;
+		const uint32_t tile = A.ovf[2 + q];
+		flat_merge_tile<FT_OUT>(A, S, tile, A.desc[tile], A.desc[tile + 1]);
+		__syncthreads();
 	}
 }
 
@@ -374,16 +379,15 @@ struct FlatDirScan { // K=6 (int64): per-tile symbol counts -> counts in front o
 // per-tile symbol counts of a flat array (after blocks -> flat)
 __global__ void __launch_bounds__(256) k_flat_count_tiles(const uint8_t *flat, uint64_t n, uint32_t *tileCnt)
 {
-	// one warp per FT_DIR tile: 32 lanes x 32 bytes
+	// one warp per FT_DIR tile: 32 lanes x 2 chunks
 	const int lane = threadIdx.x & 31;
 	const uint64_t tile = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
 	if (tile * FT_DIR >= n && tile != 0) return;
-	const uint64_t base = tile * FT_DIR + lane * 32;
-	const uint32_t rem = base >= n ? 0u : (n - base < 32 ? (uint32_t)(n - base) : 32u);
-	const uint4 *src = reinterpret_cast<const uint4*>(flat + base);
-	const uint4 x = src[0], y = src[1];
-	const Raw6 c0 = raw_count16(x.x, x.y, x.z, x.w, rem < 16 ? rem : 16), c1 = raw_count16(y.x, y.y, y.z, y.w, rem > 16 ? rem - 16 : 0);
-	Raw6 s = { c0.s0 + c1.s0, c0.s1 + c1.s1, c0.s2 + c1.s2, c0.s01 + c1.s01, c0.s02 + c1.s02, c0.n + c1.n };
+	const uint64_t base = tile * FT_DIR + lane * 2 * FT_CH;
+	const uint32_t rem = base >= n ? 0u : (n - base < 2 * FT_CH ? (uint32_t)(n - base) : 2u * FT_CH);
+	const uint4 *src = reinterpret_cast<const uint4*>(flat + (base >> 1));
+	Raw6 s = raw_count_chunk(src[0], rem < FT_CH ? rem : FT_CH);
+	raw_addto(s, raw_count_chunk(src[1], rem > FT_CH ? rem - FT_CH : 0));
 	s.s0 = warp_sum(s.s0); s.s1 = warp_sum(s.s1); s.s2 = warp_sum(s.s2); s.s01 = warp_sum(s.s01); s.s02 = warp_sum(s.s02); s.n = warp_sum(s.n);
 	if (lane < 6) tileCnt[tile * 6 + lane] = raw_symbol(s, (uint32_t)lane);
 }
@@ -393,13 +397,12 @@ __device__ __forceinline__ void flat_rank6(const uint8_t *flat, const int64_t *d
 {
 	const uint64_t t = (uint64_t)x / FT_DIR;
 	const uint32_t part = (uint32_t)((uint64_t)x - t * FT_DIR);
-	const uint32_t rem = part > (uint32_t)lane * 32 ? (part - lane * 32 < 32 ? part - lane * 32 : 32u) : 0u;
+	const uint32_t rem = part > (uint32_t)lane * 2 * FT_CH ? (part - lane * 2 * FT_CH < 2 * FT_CH ? part - lane * 2 * FT_CH : 2u * FT_CH) : 0u;
 	Raw6 s = { 0, 0, 0, 0, 0, 0 };
 	if (rem) {
-		const uint4 *src = reinterpret_cast<const uint4*>(flat + t * FT_DIR + lane * 32);
-		const uint4 xx = src[0], y = src[1];
-		const Raw6 c0 = raw_count16(xx.x, xx.y, xx.z, xx.w, rem < 16 ? rem : 16), c1 = raw_count16(y.x, y.y, y.z, y.w, rem > 16 ? rem - 16 : 0);
-		s.s0 = c0.s0 + c1.s0; s.s1 = c0.s1 + c1.s1; s.s2 = c0.s2 + c1.s2; s.s01 = c0.s01 + c1.s01; s.s02 = c0.s02 + c1.s02; s.n = c0.n + c1.n;
+		const uint4 *src = reinterpret_cast<const uint4*>(flat + ((t * FT_DIR + lane * 2 * FT_CH) >> 1));
+		s = raw_count_chunk(src[0], rem < FT_CH ? rem : FT_CH);
+		raw_addto(s, raw_count_chunk(src[1], rem > FT_CH ? rem - FT_CH : 0));
 	}
 	s.s0 = warp_sum(s.s0); s.s1 = warp_sum(s.s1); s.s2 = warp_sum(s.s2); s.s01 = warp_sum(s.s01); s.s02 = warp_sum(s.s02); s.n = warp_sum(s.n);
 #pragma unroll
@@ -434,7 +437,8 @@ __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, c
 }
 
 // ---- leaf blocks -> flat --------------------------------------------------------------------------------
-// one warp per logical block: every lane expands the runs that start in its 16 bytes
+// two steps: expand the runs to one byte per symbol (one warp per logical block: every lane expands the
+// runs that start in its 16 bytes), then pack two symbols per byte
 // (sharded engines: off[b*7+6] = symbols of the whole index in front of bucket b that other ranks hold)
 __global__ void __launch_bounds__(128) k_blocks_to_flat(const uint8_t *pool, const uint32_t *order, const int64_t *cumLen, uint32_t nlog,
                                                         const int64_t *off, const uint32_t *bkt, int nb, uint8_t *flat, Ctl *ctl)
@@ -457,6 +461,16 @@ __global__ void __launch_bounds__(128) k_blocks_to_flat(const uint8_t *pool, con
 		dst += l;
 	}
 	if (err && lane == 0) atomicOr(&ctl->err, err);
+}
+
+__global__ void __launch_bounds__(256) k_pack_nibbles(const uint8_t *bytes, uint64_t n, uint8_t *flat)
+{
+	const uint64_t i = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8; // 8 symbols -> one word
+	if (i >= n) return;
+	uint32_t w = 0;
+#pragma unroll
+	for (int j = 0; j < 8; ++j) if (i + j < n) w |= (uint32_t)(bytes[i + j] & 15u) << (4 * j);
+	reinterpret_cast<uint32_t*>(flat)[i >> 3] = w;
 }
 
 // ---- flat -> leaf blocks --------------------------------------------------------------------------------
@@ -482,7 +496,7 @@ __global__ void __launch_bounds__(256) k_flat_chunk_bytes(const uint8_t *flat, E
 	const uint64_t s1 = s0 + FE_CHUNK < T.symStart[b + 1] ? s0 + FE_CHUNK : T.symStart[b + 1];
 	uint32_t bytes = 0, prev = 8, len = 0;
 	for (uint64_t i = s0; i < s1; ++i) {
-		const uint32_t s = flat[i];
+		const uint32_t s = flat_get(flat, i);
 		if (s != prev) { if (len) bytes += len < 16 ? 1 : 2; prev = s; len = 0; }
 		++len;
 	}
@@ -525,7 +539,7 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 		uint8_t *o = img + 2 + (uint32_t)(chunkPre[c] - b0);
 		uint32_t prev = 8, len = 0;
 		for (uint64_t i = s0; i < s1; ++i) {
-			const uint32_t s = flat[i];
+			const uint32_t s = flat_get(flat, i);
 			if (s != prev) { if (len) o += enc_run(o, prev, len); prev = s; len = 0; }
 			++len;
 #pragma unroll

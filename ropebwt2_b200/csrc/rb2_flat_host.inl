@@ -35,7 +35,7 @@ static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
 	size_t freeB = 0, totB = 0;
 	RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
 	const uint64_t have = e->flat.s[0].cap + e->flat.s[1].cap;
-	const uint64_t need = 2 * cap + cap / 8 + (cap * 5 / 4) + (64ull << 20); // two arrays, directories, the re-encoded pool
+	const uint64_t need = cap + cap / 8 + (cap * 5 / 4) + (n0 ? n0 : 0) + (64ull << 20); // two arrays (4 bits per symbol), directories, the re-encoded pool, expansion scratch
 	if (need > freeB + have + (uint64_t)e->poolCap * RB2_BLK) return false; // does not fit: block-wise updates need far less
 	if (pref == 1) return true;
 	return strings >= 65536 && (double)n0 + 0.5 * (double)addLocal < 256.0 * (double)strings;
@@ -55,14 +55,16 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 	FlatState &f = e->flat;
 	ph_begin(e, PH_CONVERT);
 	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
-	for (int k = 0; k < 2; ++k) { f.s[k].need(cap); f.dir[k].need((cap / FT_DIR + 3) * 6); }
+	for (int k = 0; k < 2; ++k) { f.s[k].need(flat_bytes(cap)); f.dir[k].need((cap / FT_DIR + 3) * 6); }
 	f.tileCnt.need((cap / FT_DIR + 3) * 6);
-	f.tileR0.need(cap / FT_OUT + 4); f.desc.need(cap / FT_OUT + 4);
+	f.tileR0.need(cap / FT_OUT + 4); f.desc.need(cap / FT_OUT + 4); f.ovf.need(cap / FT_OUT + 8);
 	f.cur = 0; f.n = n0;
 	if (n0 > 0) {
 		Dir &d = e->dir[e->cur];
+		f.bytes.need(n0 + 64);
 		LAUNCH(e, k_blocks_to_flat, cdiv(e->nlog, 4), 128, 0, e->pool, d.order, d.cumLen, e->nlog, e->comm ? e->dDirOff : (const int64_t*)0,
-		       e->dctl->blkBkt, e->nb, f.s[0].p, e->dctl);
+		       e->dctl->blkBkt, e->nb, f.bytes.p, e->dctl);
+		LAUNCH(e, k_pack_nibbles, cdiv((n0 + 7) / 8, 256), 256, 0, f.bytes.p, n0, f.s[0].p);
 		LAUNCH(e, k_flat_count_tiles, cdiv((n0 + FT_DIR - 1) / FT_DIR, 8), 256, 0, f.s[0].p, n0, f.tileCnt.p);
 	} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 24, e->st));
 	flat_scan_dir(e, 0, n0);
@@ -77,27 +79,30 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	FlatState &f = e->flat;
 	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
 	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
-	f.s[f.cur ^ 1].need(nNew + FT_PAD); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
-	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.tileR0.need(nNew / FT_OUT + 4); f.desc.need(nNew / FT_OUT + 4);
+	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.tileR0.need(nNew / FT_OUT + 4); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
 	ph_begin(e, PH_MERGE);
 	LAUNCH(e, k_flat_splits, cdiv((uint64_t)nrec + 1, 256), 256, 0, e->recP.p, e->recPre.p, nrec, nTiles, f.tileR0.p);
 	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, e->recP.p, e->recPre.p, e->recSC.p, f.tileR0.p, nTiles, nNew, f.desc.p);
+	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, e->recP.p, e->recPre.p, e->recSC.p, e->recDst.p, nrec,
-	                f.desc.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	LAUNCH(e, k_flat_merge, (uint32_t)nTiles, 256, sizeof(FlatSmem), fa);
+	                f.desc.p, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
+	LAUNCH(e, k_flat_merge, (uint32_t)nTiles, 256, sizeof(FlatSmemT<FT_CAP_SMALL>), fa);
+	LAUNCH(e, k_flat_merge_dense, e->nSM * 3, 256, sizeof(FlatSmemT<FT_OUT>), fa);
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);
 	ph_end(e, PH_DIR);
 	++e->stats.n_merge_launches;
 	e->stats.merge_blocks += nTiles;
-	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) + (int64_t)nrec * 28; // old array read, new written, records (20 B) read, ranks (8 B) written
+	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) / 2 + (int64_t)nrec * 28; // old array read, new written (4 bits per symbol), records (20 B) read, ranks (8 B) written
 	f.cur ^= 1; f.n = nNew;
 	f.pending |= (1u << PH_MERGE) | (1u << PH_DIR);
 	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096) { // developer aid: dump tiny arrays column by column
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		std::vector<uint8_t> hs(nNew); std::vector<int64_t> hp(nrec), hd(12); std::vector<uint32_t> hpre(nrec + 1), hsc(nrec), hdst(nrec);
-		RB2_CUDA(cudaMemcpy(hs.data(), f.s[f.cur].p, nNew, cudaMemcpyDeviceToHost));
+		{ std::vector<uint8_t> pk(flat_bytes(nNew)); RB2_CUDA(cudaMemcpy(pk.data(), f.s[f.cur].p, pk.size(), cudaMemcpyDeviceToHost));
+		  for (uint64_t i = 0; i < nNew; ++i) hs[i] = (pk[i >> 1] >> ((i & 1) * 4)) & 15; }
 		RB2_CUDA(cudaMemcpy(hp.data(), e->recP.p, nrec * 8, cudaMemcpyDeviceToHost));
 		RB2_CUDA(cudaMemcpy(hpre.data(), e->recPre.p, (nrec + 1) * 4, cudaMemcpyDeviceToHost));
 		RB2_CUDA(cudaMemcpy(hsc.data(), e->recSC.p, nrec * 4, cudaMemcpyDeviceToHost));
