@@ -586,6 +586,7 @@ struct SingleArgs {
 	uint32_t *sidNext; int64_t *gSizeNext; uint32_t *gOffNext;
 	int64_t *recP; uint32_t *recSC, *recDst;
 	uint32_t *recPre;
+	int lean;   // dense regime, no interval sizes: only sidNext / recDst are written (RecView in rb2_flat.cuh)
 };
 
 template <bool COMP>
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 #pragma unroll
 		for (int x = 1; x < 6; ++x) if (a == x) d = base[x]++;
 		if (a == 0) ++base[0]; // only the bucket-start prefixes of a sharded engine look at it
-		int64_t P = A.gL[g], sza = 0;
+		int64_t P = A.lean ? 0 : A.gL[g], sza = 0;
 		if (A.sizes6 && A.gSize[g] > 0) { // insertion point: behind the old symbols of the earlier slots
 #pragma unroll
 			for (int slot = 0; slot < 6; ++slot) {
@@ -646,11 +647,14 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 		}
 		if (a) {
 			A.sidNext[d] = id[i];
-			A.gOffNext[d] = d;
+			if (!A.lean) A.gOffNext[d] = d;
 			if (A.sizes6) A.gSizeNext[d] = sza;
 		}
-		A.recP[g] = P; A.recSC[g] = (1u << 3) | a; A.recDst[g] = d;
-		if (A.recPre) A.recPre[g] = g;
+		A.recDst[g] = d;
+		if (!A.lean) {
+			A.recP[g] = P; A.recSC[g] = (1u << 3) | a;
+			if (A.recPre) A.recPre[g] = g;
+		}
 	}
 }
 
@@ -2207,11 +2211,12 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			                 e->sizes6.p, e->dctl, (const int64_t*)0, e->nb);
 			else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
 		}
+		const bool lean = flat && !useSizes && G == M && m > 1;
 		if (G == M) {
 			// every group is a singleton: records, next groups and the partition in one kernel
 			LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, M, flat ? e->recPre.p : (uint32_t*)0);
 			SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0 };
+			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 			else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 			ph_end(e, PH_GROUPS);
@@ -2246,7 +2251,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		}
 		const rb2_stats_t before = e->stats;
 		if (flat) {
-			flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p);
+			flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p, lean ? e->gL[cs].p : (const int64_t*)0);
 			if (column_log()) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, e->flat.pending); e->flat.pending = 0; } // per-column times
 		} else apply_records(e, nrec, e->gL[cs ^ 1].p);
 		e->stats.n_records += nrec;

@@ -84,15 +84,26 @@ __device__ __forceinline__ Raw6 raw_count_chunk(const uint4 &v, uint32_t ns)
 }
 __device__ __forceinline__ void raw_addto(Raw6 &a, const Raw6 &b) { a.s0 += b.s0; a.s1 += b.s1; a.s2 += b.s2; a.s01 += b.s01; a.s02 += b.s02; a.n += b.n; }
 
+// The records of a column.  In the all-singleton regime without interval sizes (the bulk of a short-read
+// batch) a record is fully described by the state arrays themselves -- position = the group's interval
+// start, symbol = the member's next symbol, count 1, members in front = its own index -- so the column
+// kernel writes none of recP / recSC / recPre and the pointers below are the state arrays / null.
+struct RecView {
+	const int64_t *P; const uint32_t *pre, *sc; const uint8_t *asym;
+	__device__ __forceinline__ uint32_t Pre(uint32_t r) const { return pre ? pre[r] : r; }
+	__device__ __forceinline__ uint32_t SC(uint32_t r) const { return sc ? sc[r] : (8u | asym[r]); }
+	__device__ __forceinline__ uint64_t Key(uint32_t r) const { return (uint64_t)P[r] + Pre(r); }
+};
+
 // ---- tile -> record ranges ---------------------------------------------------------------------------
 // tileR0[t] = first record whose output run starts at or behind t*FT_OUT (key_r = P_r + pre_r); one
 // thread per record (plus a virtual one behind the last) fills the tiles between its predecessor and itself.
-__global__ void __launch_bounds__(256) k_flat_splits(const int64_t *recP, const uint32_t *recPre, uint32_t R, uint64_t nTiles, uint32_t *tileR0)
+__global__ void __launch_bounds__(256) k_flat_splits(const RecView V, uint32_t R, uint64_t nTiles, uint32_t *tileR0)
 {
 	const uint64_t r = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (r > R) return;
-	const int64_t tPrev = r == 0 ? -1 : (int64_t)((uint64_t)(recP[r - 1] + recPre[r - 1]) / FT_OUT);
-	const int64_t t = r == R ? (int64_t)nTiles : (int64_t)((uint64_t)(recP[r] + recPre[r]) / FT_OUT);
+	const int64_t tPrev = r == 0 ? -1 : (int64_t)(V.Key((uint32_t)r - 1) / FT_OUT);
+	const int64_t t = r == R ? (int64_t)nTiles : (int64_t)(V.Key((uint32_t)r) / FT_OUT);
 	for (int64_t tt = tPrev + 1; tt <= t; ++tt) tileR0[tt] = (uint32_t)r;
 }
 
@@ -101,8 +112,7 @@ __global__ void __launch_bounds__(256) k_flat_splits(const int64_t *recP, const 
 // across it from the left.  Computed ahead of k_flat_merge so that its CTAs start with two independent loads.
 struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FT_OUT) << 3 | symbol
 
-__global__ void __launch_bounds__(256) k_flat_geo(const int64_t *recP, const uint32_t *recPre, const uint32_t *recSC, const uint32_t *tileR0,
-                                                  uint64_t nTiles, uint64_t nNew, TileDesc *desc)
+__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, const uint32_t *tileR0, uint64_t nTiles, uint64_t nNew, TileDesc *desc)
 {
 	const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (t > nTiles) return;
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(256) k_flat_geo(const int64_t *recP, const uin
 	const uint32_t r0 = tileR0[t];
 	uint64_t before = 0; uint32_t carry = 0;
 	if (r0 > 0) {
-		const uint64_t pre = recPre[r0 - 1], key = (uint64_t)recP[r0 - 1] + pre; const uint32_t sc = recSC[r0 - 1];
+		const uint64_t pre = V.Pre(r0 - 1), key = (uint64_t)V.P[r0 - 1] + pre; const uint32_t sc = V.SC(r0 - 1);
 		const uint64_t end = key + (sc >> 3);
 		if (end > o0) { before = pre + (o0 - key); const uint64_t rem = end - o0; carry = (uint32_t)(rem < FT_OUT ? rem : FT_OUT) << 3 | (sc & 7u); }
 		else before = pre + (sc >> 3);
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(256) k_flat_geo(const int64_t *recP, const uin
 struct FlatArgs {
 	const uint8_t *oldS; const int64_t *oldDir;   // old array, counts in front of every FT_DIR-th old symbol
 	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its raw per-FT_DIR-tile symbol counts
-	const int64_t *recP; const uint32_t *recPre, *recSC, *recDst; uint32_t R;
+	RecView V; const uint32_t *recDst; uint32_t R;
 	const TileDesc *desc;
 	uint32_t *ovf;           // [0] tiles left to k_flat_merge_dense, [1] its work counter, [2..] the tiles
 	int64_t *gLNext; const Ctl *ctl;
@@ -216,8 +226,8 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		if (tid - NCNT < FT_SUB * 6) (&S.recCnt[0][0])[tid - NCNT] = 0;
 		for (uint32_t k = tid - NCNT; k < r1 - r0; k += 256 - NCNT) {
 			const uint32_t r = r0 + k;
-			const uint32_t pre = A.recPre[r], sc = A.recSC[r];
-			const uint32_t key = (uint32_t)((uint64_t)A.recP[r] + pre - o0);
+			const uint32_t pre = A.V.Pre(r), sc = A.V.SC(r);
+			const uint32_t key = (uint32_t)((uint64_t)A.V.P[r] + pre - o0);
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
 			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
@@ -236,7 +246,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	}
 	// ---- phase B: assemble 32 output symbols per thread ------------------------------------------------
 	// record symbols of this tile in front of staged entry k (the carried run counts from the tile start)
-	auto pre_rel = [&](uint32_t k) -> uint32_t { return k < nCarry ? 0u : (k < nS ? (uint32_t)(A.recPre[r0 + k - nCarry] - before) : recIn); };
+	auto pre_rel = [&](uint32_t k) -> uint32_t { return k < nCarry ? 0u : (k < nS ? (uint32_t)(A.V.Pre(r0 + k - nCarry) - before) : recIn); };
 	auto run_len = [&](uint32_t k) -> uint32_t { return ((uint32_t)S.sLS[k] >> 3) + 1; };
 	const uint32_t rel = tid * FT_CH;
 	uint32_t k0;                        // first entry with sKey >= rel
@@ -321,7 +331,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			const uint32_t r = r0 + k, dst = A.recDst[r];
 			if (dst == NONE32) continue;
 			const uint32_t a = S.sLS[nCarry + k] & 7u;
-			const Raw6 rr = prefix_at((uint32_t)((uint64_t)A.recP[r] - a0));
+			const Raw6 rr = prefix_at((uint32_t)((uint64_t)A.V.P[r] - a0));
 			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a);
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
 				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r) * 7 + a];
@@ -486,6 +496,18 @@ __device__ __forceinline__ int enc_bucket_of_chunk(const EncTab &T, uint64_t c)
 	return b;
 }
 
+// the FE_CHUNK symbols that start at symbol s0, as eight words (low nibble first)
+__device__ __forceinline__ void load_chunk64(const uint8_t *flat, uint64_t s0, uint32_t (&w)[8])
+{
+	const uint32_t *wp = reinterpret_cast<const uint32_t*>(flat) + (s0 >> 3);
+	const uint32_t sh = (uint32_t)(s0 & 7) * 4;
+	uint32_t x[9];
+#pragma unroll
+	for (int j = 0; j < 9; ++j) x[j] = wp[j];
+#pragma unroll
+	for (int j = 0; j < 8; ++j) w[j] = __funnelshift_r(x[j], x[j + 1], sh);
+}
+
 // bytes of the encoded chunk
 __global__ void __launch_bounds__(256) k_flat_chunk_bytes(const uint8_t *flat, EncTab T, uint64_t nChunk, uint8_t *chunkBytes)
 {
@@ -493,14 +515,17 @@ __global__ void __launch_bounds__(256) k_flat_chunk_bytes(const uint8_t *flat, E
 	if (c >= nChunk) return;
 	const int b = enc_bucket_of_chunk(T, c);
 	const uint64_t s0 = T.symStart[b] + (c - T.chunkStart[b]) * FE_CHUNK;
-	const uint64_t s1 = s0 + FE_CHUNK < T.symStart[b + 1] ? s0 + FE_CHUNK : T.symStart[b + 1];
+	const uint32_t n = (uint32_t)(s0 + FE_CHUNK < T.symStart[b + 1] ? FE_CHUNK : T.symStart[b + 1] - s0);
+	uint32_t w[8];
+	load_chunk64(flat, s0, w);
 	uint32_t bytes = 0, prev = 8, len = 0;
-	for (uint64_t i = s0; i < s1; ++i) {
-		const uint32_t s = flat_get(flat, i);
-		if (s != prev) { if (len) bytes += len < 16 ? 1 : 2; prev = s; len = 0; }
+#pragma unroll
+	for (int i = 0; i < FE_CHUNK; ++i) if ((uint32_t)i < n) {
+		const uint32_t sy = (w[i >> 3] >> ((i & 7) * 4)) & 15u;
+		if (sy != prev) { bytes += len == 0 ? 0 : (len < 16 ? 1 : 2); prev = sy; len = 0; }
 		++len;
 	}
-	if (len) bytes += len < 16 ? 1 : 2;
+	bytes += len == 0 ? 0 : (len < 16 ? 1 : 2);
 	chunkBytes[c] = (uint8_t)bytes;
 }
 
@@ -532,27 +557,39 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 	uint8_t *img = sImg[wid];
 	for (int j = lane; j < (RB2_BLK + 64) / 4; j += 32) reinterpret_cast<uint32_t*>(img)[j] = 0;
 	__syncwarp();
-	uint32_t cnt[6] = { 0, 0, 0, 0, 0, 0 };
+	uint32_t acc[5] = { 0, 0, 0, 0, 0 }, nsym = 0;
 	for (uint64_t c = c0 + lane; c < c1; c += 32) {
 		const uint64_t s0 = T.symStart[b] + (c - cLo) * FE_CHUNK;
-		const uint64_t s1 = s0 + FE_CHUNK < T.symStart[b + 1] ? s0 + FE_CHUNK : T.symStart[b + 1];
+		const uint32_t n = (uint32_t)(s0 + FE_CHUNK < T.symStart[b + 1] ? FE_CHUNK : T.symStart[b + 1] - s0);
+		uint32_t w[8];
+		load_chunk64(flat, s0, w);
 		uint8_t *o = img + 2 + (uint32_t)(chunkPre[c] - b0);
 		uint32_t prev = 8, len = 0;
-		for (uint64_t i = s0; i < s1; ++i) {
-			const uint32_t s = flat_get(flat, i);
-			if (s != prev) { if (len) o += enc_run(o, prev, len); prev = s; len = 0; }
-			++len;
 #pragma unroll
-			for (int a = 0; a < 6; ++a) cnt[a] += s == (uint32_t)a;
+		for (int i = 0; i < FE_CHUNK; ++i) if ((uint32_t)i < n) {
+			const uint32_t sy = (w[i >> 3] >> ((i & 7) * 4)) & 15u;
+			if (sy != prev) { if (len) o += enc_run(o, prev, len); prev = sy; len = 0; }
+			++len;
 		}
 		if (len) o += enc_run(o, prev, len);
+		// symbol counts of the chunk (symbols behind n masked away)
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t kv = n > (uint32_t)j * 8 ? n - j * 8 : 0;
+			raw_add_word(kv >= 8 ? w[j] : (kv ? w[j] & ((1u << (kv * 4)) - 1u) : 0u), acc);
+		}
+		nsym += n;
+	}
+	uint32_t cnt[6];
+	{
+		Raw6 r = { warp_sum(acc[0]), warp_sum(acc[1]), warp_sum(acc[2]), warp_sum(acc[3]), warp_sum(acc[4]), warp_sum(nsym) };
+#pragma unroll
+		for (int a = 0; a < 6; ++a) cnt[a] = raw_symbol(r, (uint32_t)a);
 	}
 	__syncwarp();
 	if (lane == 0) { img[0] = (uint8_t)(nbytes & 0xff); img[1] = (uint8_t)(nbytes >> 8); }
 	__syncwarp();
 	reinterpret_cast<uint4*>(pool + (size_t)k * RB2_BLK)[lane] = reinterpret_cast<const uint4*>(img)[lane];
-#pragma unroll
-	for (int a = 0; a < 6; ++a) cnt[a] = warp_sum(cnt[a]);
 	if (lane < 6) {
 		uint32_t v = 0;
 #pragma unroll

@@ -74,7 +74,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 }
 
 // one column: merge nrec records (inserting `inserted` symbols) into the flat array
-static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext)
+static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0)
 {
 	FlatState &f = e->flat;
 	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
@@ -82,10 +82,12 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
 	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.tileR0.need(nNew / FT_OUT + 4); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
 	ph_begin(e, PH_MERGE);
-	LAUNCH(e, k_flat_splits, cdiv((uint64_t)nrec + 1, 256), 256, 0, e->recP.p, e->recPre.p, nrec, nTiles, f.tileR0.p);
-	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, e->recP.p, e->recPre.p, e->recSC.p, f.tileR0.p, nTiles, nNew, f.desc.p);
+	// leanP: all-singleton column without interval sizes -- the records are the state arrays themselves
+	const RecView V = leanP ? RecView{ leanP, 0, 0, e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
+	LAUNCH(e, k_flat_splits, cdiv((uint64_t)nrec + 1, 256), 256, 0, V, nrec, nTiles, f.tileR0.p);
+	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, f.tileR0.p, nTiles, nNew, f.desc.p);
 	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
-	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, e->recP.p, e->recPre.p, e->recSC.p, e->recDst.p, nrec,
+	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
 	                f.desc.p, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
 	LAUNCH(e, k_flat_merge, (uint32_t)nTiles, 256, sizeof(FlatSmemT<FT_CAP_SMALL>), fa);
 	LAUNCH(e, k_flat_merge_dense, e->nSM * 3, 256, sizeof(FlatSmemT<FT_OUT>), fa);
@@ -95,10 +97,10 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	ph_end(e, PH_DIR);
 	++e->stats.n_merge_launches;
 	e->stats.merge_blocks += nTiles;
-	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) / 2 + (int64_t)nrec * 28; // old array read, new written (4 bits per symbol), records (20 B) read, ranks (8 B) written
+	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) / 2 + (int64_t)nrec * (leanP ? 21 : 28); // old array read, new written (4 bits per symbol), records (20 B) read, ranks (8 B) written
 	f.cur ^= 1; f.n = nNew;
 	f.pending |= (1u << PH_MERGE) | (1u << PH_DIR);
-	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096) { // developer aid: dump tiny arrays column by column
+	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096 && !leanP) { // developer aid: dump tiny arrays column by column
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		std::vector<uint8_t> hs(nNew); std::vector<int64_t> hp(nrec), hd(12); std::vector<uint32_t> hpre(nrec + 1), hsc(nrec), hdst(nrec);
 		{ std::vector<uint8_t> pk(flat_bytes(nNew)); RB2_CUDA(cudaMemcpy(pk.data(), f.s[f.cur].p, pk.size(), cudaMemcpyDeviceToHost));

@@ -295,7 +295,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			if (G == M) {
 				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M, flat ? e->recPre.p : (uint32_t*)0);
 				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0 };
+				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, 0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 				else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 				ph_end(e, PH_GROUPS);
