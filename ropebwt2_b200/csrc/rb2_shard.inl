@@ -132,6 +132,8 @@ extern "C" rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int r
 	shard_owner_map(nranks, e->owner);
 	RB2_CUDA(cudaMalloc(&e->dDirOff, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOff, NBMAX * 7 * sizeof(int64_t)));
+	RB2_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+	RB2_CUDA(cudaEventCreateWithFlags(&e->evEarly, cudaEventDisableTiming));
 	RB2_CUDA(cudaMalloc(&e->dDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t)));
@@ -375,25 +377,38 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int r = 0; r < P; ++r) { GglobN += curG[r]; MglobN += curM[r]; }
 		for (int r = 0; r < P; ++r) if (curM[r] >= 0xfffffff0ull) RB2_FATAL("too many strings on one rank");
 
-		// ---- merge my records into my blocks ------------------------------------------------------
-		if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p); } // (no records: my array does not change)
-		else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
-		else rebuild_directory(e, false);
+		// ---- merge my records | move the string state to the owners of the next sub-buckets --------------
+		// Member ids, member ranges and interval sizes are final before the merge: they travel on a second
+		// stream while the merge runs; the interval starts (ranks) follow behind the merge.
+		const uint32_t Gn = (uint32_t)curG[me], Mn = (uint32_t)curM[me];
+		const bool singles = GglobN == MglobN;
+		auto exchange_early = [&]() {
+			e->gSize[cs].need(useSizes ? Gn : 0); e->gOff[cs].need((size_t)Gn + 1); e->sid[cs].need((size_t)Mn + 4);
+			cm->group_begin();
+			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), e->st2);
+			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), e->st2);
+			cm->exchange(e->sid[1].p, e->sid[cs].p, 4, pcM.data(), (int)pcM.size(), e->st2);
+			cm->group_end(e->st2);
+			RB2_CUDA(cudaEventRecord(e->evEarly, e->st2));
+		};
+		auto merge = [&]() {
+			if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p); } // (no records: my array does not change)
+			else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
+			else rebuild_directory(e, false);
+		};
+		// the dense merge is fully asynchronous, so it is queued first; the block merge synchronises with the host
+		if (MglobN > 0 && !flat) exchange_early();
+		merge();
+		if (MglobN > 0 && flat) exchange_early();
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
-
-		// ---- move the string state to the owners of the next sub-buckets --------------------------------
-		const uint32_t Gn = (uint32_t)curG[me], Mn = (uint32_t)curM[me];
 		if (MglobN > 0) {
 			ph_begin(e, PH_EXCH);
-			e->gL[cs].need(Gn); e->gSize[cs].need(useSizes ? Gn : 0); e->gOff[cs].need((size_t)Gn + 1); e->sid[cs].need((size_t)Mn + 4);
-			const bool singles = GglobN == MglobN;
+			e->gL[cs].need(Gn);
 			cm->group_begin();
 			cm->exchange(e->gL[1].p, e->gL[cs].p, 8, pcG.data(), (int)pcG.size(), e->st);
-			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), e->st);
-			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), e->st);
-			cm->exchange(e->sid[1].p, e->sid[cs].p, 4, pcM.data(), (int)pcM.size(), e->st);
 			cm->group_end(e->st);
+			RB2_CUDA(cudaStreamWaitEvent(e->st, e->evEarly, 0));
 			if (singles) { if (Gn + 1 > 0) LAUNCH(e, k_fill_u32, cdiv((uint64_t)Gn + 1, 256), 256, 0, e->gOff[cs].p, Gn + 1, 0u, 1u); }
 			else if (Gn > 0) {
 				e->plan.need(2 * (NBMAX * 6 + 8));
