@@ -173,9 +173,16 @@ def reference_arm(args):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         reference_arm(args)
         return
+    # NCCL reads these once per process: the sharded build moves a few large point-to-point messages per column
+    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     import torch
     import torch.distributed as dist
     from ropebwt2_b200.dist import Reducer, rank_info, shard_seed

@@ -132,7 +132,12 @@ struct NcclComm : Comm {
 	uint8_t *hSend, *hRecv, *dSend, *dRecv; // staging of the small all-gather
 	enum { SMALL = 4096 };
 	NcclComm(int rank_, int n_, const void *uid) {
-		rank = rank_; n = n_; api = nccl_api();
+		rank = rank_; n = n_;
+		// the exchange is a handful of large point-to-point transfers per column: let NCCL spread each over
+		// many channels (its default for send/recv is tuned for many small peers); the caller's setting wins
+		setenv("NCCL_MIN_P2P_NCHANNELS", "16", 0);
+		setenv("NCCL_MAX_P2P_NCHANNELS", "32", 0);
+		api = nccl_api();
 		ncclUniqueId id; memcpy(&id, uid, sizeof(id));
 		RB2_NCCL(api->CommInitRank(&comm, n, id, rank));
 		RB2_CUDA(cudaMallocHost(&hSend, SMALL)); RB2_CUDA(cudaMallocHost(&hRecv, SMALL * RB2_MAX_RANKS));

@@ -1780,7 +1780,7 @@ struct rb2_engine {
 	int64_t *dDirOff, *hDirOff;       // offsets of the directory (post-column while a column runs)
 	int64_t *dDirOffPre, *hDirOffPre; // the same in front of the column (dense regime: record positions are pre-column)
 	uint32_t *hPlan; DevBuf<uint32_t> plan;
-	cudaStream_t st2; cudaEvent_t evEarly; // second stream: the part of the exchange that overlaps the merge
+	cudaStream_t st2; cudaEvent_t evEarly, evMerge; // second stream: the part of the exchange that overlaps the merge
 	FlatState flat; DevBuf<uint32_t> recPre;
 	int64_t tot[6][6]; int64_t bktLen[6];
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
@@ -2026,7 +2026,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
-	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
+	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
 	e->flat.release(); e->recPre.release();
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
 	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);

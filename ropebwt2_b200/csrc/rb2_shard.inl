@@ -132,8 +132,13 @@ extern "C" rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int r
 	shard_owner_map(nranks, e->owner);
 	RB2_CUDA(cudaMalloc(&e->dDirOff, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOff, NBMAX * 7 * sizeof(int64_t)));
-	RB2_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
+	{ // the overlapped part of the exchange must get SM / copy slots while the merge grid is still draining
+		int lo = 0, hi = 0;
+		RB2_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+		RB2_CUDA(cudaStreamCreateWithPriority(&e->st2, cudaStreamNonBlocking, hi));
+	}
 	RB2_CUDA(cudaEventCreateWithFlags(&e->evEarly, cudaEventDisableTiming));
+	RB2_CUDA(cudaEventCreateWithFlags(&e->evMerge, cudaEventDisableTiming));
 	RB2_CUDA(cudaMalloc(&e->dDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t)));
@@ -242,6 +247,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 
 	std::vector<ShardTab> tabs(P);
 	std::vector<Piece> pcG, pcM;
+	bool latePending = false;
 	for (int64_t col = 0; Mglob > 0; ++col) {
 		if ((uint64_t)col >= ncolAll) RB2_FATAL("internal: live strings beyond the last column");
 		Dir &d = e->dir[e->cur];
@@ -274,6 +280,14 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		ctl_push(e);
 
 		uint32_t nrec = 0;
+		const bool lean = flat && !useSizes && M > 0 && G == M && Gglob == Mglob; // records = the state arrays (RecView)
+		// the interval starts of this column are still arriving (second stream) while its first kernels run
+		auto wait_late = [&]() {
+			if (!latePending) return;
+			RB2_CUDA(cudaEventSynchronize(e->ev[PH_EXCH][1]));
+			ph_collect(e, 1u << PH_EXCH);
+			latePending = false;
+		};
 		if (M > 0) {
 			// ---- members: next symbol + tile histograms -------------------------------------
 			ph_begin(e, PH_MEMBERS);
@@ -288,6 +302,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 			ph_end(e, PH_MEMBERS);
 			// ---- groups ---------------------------------------------------------------------
+			if (!lean) wait_late(); // the group kernels read the interval starts
 			ph_begin(e, PH_GROUPS);
 			if (useSizes) {
 				if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, e->gL[cs].p, e->gSize[cs].p,
@@ -297,7 +312,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			if (G == M) {
 				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M, flat ? e->recPre.p : (uint32_t*)0);
 				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, 0 };
+				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 				else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 				ph_end(e, PH_GROUPS);
@@ -322,7 +337,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2) | e->flat.pending);
 			e->flat.pending = 0;
 			nrec = h->nrec;
-			if (flat && nrec) LAUNCH(e, k_flat_localize, cdiv(nrec, 256), 256, 0, e->recP.p, nrec, e->dctl, e->dDirOffPre, e->nb);
+			wait_late();
+			if (flat && nrec) LAUNCH(e, k_flat_localize, cdiv(nrec, 256), 256, 0, lean ? e->gL[cs].p : e->recP.p, nrec, e->dctl, e->dDirOffPre, e->nb);
 		}
 		// ---- gather every rank's tables -----------------------------------------------------------
 		ShardTab mineT;
@@ -363,11 +379,18 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				if (nm == 0) continue;
 				Piece pg = { src, dst, (uint64_t)gSym[src][a] + tabs[src].grp[sb * 6 + a], curG[dst], ng };
 				Piece pm = { src, dst, (uint64_t)mSym[src][a] + tabs[src].mem[sb * 6 + a], curM[dst], nm };
-				pcG.push_back(pg); pcM.push_back(pm);
-				if (dst == me) { // rebase table of the member ranges I receive
-					e->hPlan[nMyPieces] = (uint32_t)pg.dof;
-					e->hPlan[NBMAX * 6 + 8 + nMyPieces] = (uint32_t)pm.dof - (uint32_t)pm.so;
-					++nMyPieces;
+				// neighbouring pieces of one (source, target) pair that are contiguous on both sides travel as one
+				// message (NCCL's point-to-point bandwidth collapses with many small messages per peer)
+				if (!pcG.empty() && pcG.back().src == src && pcG.back().dst == dst && pcG.back().so + pcG.back().n == pg.so &&
+				    pcG.back().dof + pcG.back().n == pg.dof && pcM.back().so + pcM.back().n == pm.so && pcM.back().dof + pcM.back().n == pm.dof) {
+					pcG.back().n += ng; pcM.back().n += nm;
+				} else {
+					pcG.push_back(pg); pcM.push_back(pm);
+					if (dst == me) { // rebase table of the member ranges I receive
+						e->hPlan[nMyPieces] = (uint32_t)pg.dof;
+						e->hPlan[NBMAX * 6 + 8 + nMyPieces] = (uint32_t)pm.dof - (uint32_t)pm.so;
+						++nMyPieces;
+					}
 				}
 				curG[dst] += ng; curM[dst] += nm; mglobNext[t] += nm;
 			}
@@ -392,22 +415,30 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			RB2_CUDA(cudaEventRecord(e->evEarly, e->st2));
 		};
 		auto merge = [&]() {
-			if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p); } // (no records: my array does not change)
+			if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p, lean ? e->gL[cs].p : (const int64_t*)0); } // (no records: my array does not change)
 			else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
 			else rebuild_directory(e, false);
 		};
 		// the dense merge is fully asynchronous, so it is queued first; the block merge synchronises with the host
+		wait_late(); // (ranks without members get here with the previous column's transfer possibly still in flight)
 		if (MglobN > 0 && !flat) exchange_early();
 		merge();
 		if (MglobN > 0 && flat) exchange_early();
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
 		if (MglobN > 0) {
-			ph_begin(e, PH_EXCH);
+			// interval starts: behind the merge, on the second stream -- the next column only needs them when its
+			// records are merged (all-singleton columns) or its groups are scanned
+			RB2_CUDA(cudaEventRecord(e->evMerge, e->st));
 			e->gL[cs].need(Gn);
+			RB2_CUDA(cudaStreamWaitEvent(e->st2, e->evMerge, 0));
+			RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][0], e->st2));
 			cm->group_begin();
-			cm->exchange(e->gL[1].p, e->gL[cs].p, 8, pcG.data(), (int)pcG.size(), e->st);
-			cm->group_end(e->st);
+			cm->exchange(e->gL[1].p, e->gL[cs].p, 8, pcG.data(), (int)pcG.size(), e->st2);
+			cm->group_end(e->st2);
+			RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][1], e->st2));
+			latePending = true;
+			// member ids / ranges arrived on the second stream: finish the member ranges on the main one
 			RB2_CUDA(cudaStreamWaitEvent(e->st, e->evEarly, 0));
 			if (singles) { if (Gn + 1 > 0) LAUNCH(e, k_fill_u32, cdiv((uint64_t)Gn + 1, 256), 256, 0, e->gOff[cs].p, Gn + 1, 0u, 1u); }
 			else if (Gn > 0) {
@@ -415,9 +446,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				RB2_CUDA(cudaMemcpyAsync(e->plan.p, e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
 				LAUNCH(e, k_rebase_goff, cdiv(Gn, 256), 256, 0, e->gOff[cs].p, Gn, Mn, e->plan.p, e->plan.p + NBMAX * 6 + 8, nMyPieces);
 			}
-			ph_end(e, PH_EXCH);
 			RB2_CUDA(cudaStreamSynchronize(e->st)); // hPlan and the piece lists are reused next column
-			ph_collect(e, (1u << PH_EXCH) | e->flat.pending);
+			ph_collect(e, e->flat.pending);
 			e->flat.pending = 0;
 			e->stats.exch_bytes += ((int64_t)Gn * (8 + (useSizes ? 8 : 0) + (singles ? 0 : 4)) + (int64_t)Mn * 4);
 		}
