@@ -66,3 +66,55 @@ def test_single_process_defaults():
     assert rank_info() == (0, 1, 0)
     red = Reducer(1)
     assert whole_job_throughput(5.0, 2.0, red) == (5.0, 2.0, 2500.0)
+
+
+# ---- host logic of the sharded build (one index over all ranks) -----------------------------------
+
+def _shard_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ropebwt2_b200.dist import broadcast_bytes, gather_index_blocks, owner_map, split_batch_bytes
+        # the NCCL unique id travels from rank 0 to everybody (128 opaque bytes)
+        uid = broadcast_bytes(bytes(range(128)) if rank == 0 else None)
+        own = owner_map(world)
+        # every rank contributes fake leaf blocks for the sub-buckets it owns: block byte 0 = sub-bucket id
+        mine = {s: np.full((2 if s % 5 == 0 else 1, 512), s, dtype=np.uint8) for s in range(36) if own[s] == rank}
+        blocks = gather_index_blocks(mine, world, rank)
+        out.put((rank, uid, split_batch_bytes(1001, world)[rank], None if blocks is None else blocks[:, 0].tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_sharded_host_logic():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1] == bytes(range(128))
+    # contiguous shares in rank order that cover the batch
+    assert res[0][2][0] == 0 and res[0][2][1] == res[1][2][0] and res[1][2][1] == 1001
+    # rank 0 sees all sub-buckets in BWT order (sub-bucket ids ascending), nothing on the other rank
+    assert res[1][3] is None
+    ids = res[0][3]
+    assert ids == sorted(ids) and sorted(set(ids)) == list(range(36))
+
+
+def test_owner_map_is_a_partition_into_contiguous_ranges():
+    from ropebwt2_b200.dist import owner_map
+    for world in range(1, 9):
+        own = owner_map(world)
+        assert len(own) == 36 and own == sorted(own) and set(own) == set(range(world))
+        # the 16 ACGT x ACGT sub-buckets (the ones that carry the data) are spread evenly
+        main = [own[x * 6 + y] for x in range(1, 5) for y in range(1, 5)]
+        counts = [main.count(r) for r in range(world)]
+        assert max(counts) - min(counts) <= 1
+    from ropebwt2_b200 import load
+    assert load().rb2_shard_owner(9, 0) == -1 and load().rb2_shard_owner(2, 36) == -1
