@@ -128,34 +128,65 @@ __global__ void k_maxlen(const int64_t *strEnd, uint32_t m, unsigned long long *
 	if ((threadIdx.x & 31) == 0 && l) atomicMax(maxlen, l);
 }
 
-// T[j*m + k] = j-th symbol of (reversed) string k, including its terminating NUL.
-// 32x32 tiles through shared memory: rows of a tile are strings, columns are symbol
-// indices; reads walk along strings, writes are coalesced along the string index.
+// T[j*mstride + k] = j-th symbol of (reversed) string k, including its terminating NUL (mstride = m
+// rounded up to 16 so that every column starts 16-byte aligned).  One CTA transposes 128 strings, 32
+// symbols at a time: reads walk along the strings (aligned words + funnel shift, 16 bytes per thread),
+// shared memory holds the slab as [4 symbols][string] words, and every warp store writes the same
+// symbol of 128 consecutive strings (128 bytes).
+#define TR_S 128
+__host__ __device__ __forceinline__ uint64_t t_stride(uint64_t m) { return (m + 15) & ~(uint64_t)15; }
 __global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64_t *strEnd, uint32_t m, int64_t ncol, uint8_t *T)
 {
-	__shared__ uint8_t tile[32][33];
-	__shared__ int64_t sStart[32];
-	__shared__ int32_t sLen[32];
-	const uint32_t k0 = blockIdx.x * 32;
-	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 8 rows of 32
-	if (threadIdx.x < 32) {
-		uint32_t k = k0 + threadIdx.x;
+	__shared__ __align__(16) uint32_t tile[8][TR_S + 4];
+	__shared__ int64_t sStart[TR_S];
+	__shared__ int32_t sLen[TR_S];
+	__shared__ int32_t sMax;
+	const uint64_t mstride = t_stride(m);
+	const uint32_t k0 = blockIdx.x * TR_S;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) sMax = -1;
+	__syncthreads();
+	if (tid < TR_S) {
+		const uint32_t k = k0 + tid;
 		int64_t st = 0; int32_t ln = -1;
 		if (k < m) { st = k ? strEnd[k-1] + 1 : 0; ln = (int32_t)(strEnd[k] - st); }
-		sStart[threadIdx.x] = st; sLen[threadIdx.x] = ln;
+		sStart[tid] = st; sLen[tid] = ln;
+		atomicMax(&sMax, ln);
 	}
 	__syncthreads();
-	int32_t maxl = -1;
-	for (int i = 0; i < 32; ++i) maxl = sLen[i] > maxl ? sLen[i] : maxl;
+	const int32_t maxl = sMax;
+	const int r = tid >> 1, half = tid & 1;
 	for (int64_t j0 = 0; j0 <= maxl; j0 += 32) {
-		for (int r = ty; r < 32; r += 8) { // string r of the tile, symbol j0+tx
-			int64_t j = j0 + tx;
-			tile[r][tx] = j <= sLen[r] ? s[sStart[r] + j] : 0;
+		{ // 16 symbols of string r from index j0 + 16*half on (zero behind the terminating NUL)
+			const int64_t jb = j0 + half * 16;
+			const int64_t left = (int64_t)sLen[r] + 1 - jb;
+			uint32_t w[4] = { 0, 0, 0, 0 };
+			if (left > 0) {
+				const int64_t a = sStart[r] + jb;
+				const uint32_t *wp = reinterpret_cast<const uint32_t*>(s + (a & ~(int64_t)3));
+				const uint32_t sh = (uint32_t)(a & 3) * 8;
+				const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4];
+				w[0] = __funnelshift_r(x0, x1, sh); w[1] = __funnelshift_r(x1, x2, sh); w[2] = __funnelshift_r(x2, x3, sh); w[3] = __funnelshift_r(x3, x4, sh);
+				if (left < 16) {
+#pragma unroll
+					for (int i = 0; i < 4; ++i) {
+						const int64_t kb = left - i * 4;
+						w[i] = kb >= 4 ? w[i] : (kb > 0 ? w[i] & ((1u << (kb * 8)) - 1u) : 0u);
+					}
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i) tile[half * 4 + i][r] = w[i];
 		}
 		__syncthreads();
-		for (int c = ty; c < 32; c += 8) { // column j0+c, string k0+tx
-			int64_t j = j0 + c;
-			if (k0 + tx < m && j <= sLen[tx] && j < ncol) T[j * m + k0 + tx] = tile[tx][c];
+		for (int c = wid; c < 32; c += 8) { // symbol j0+c of strings k0 + 4*lane .. +3
+			const int64_t j = j0 + c;
+			if (j < ncol && (uint64_t)k0 + 4 * lane < mstride) {
+				const uint4 v = *reinterpret_cast<const uint4*>(&tile[c >> 2][4 * lane]);
+				const uint32_t sel = 0x0040 + (c & 3) * 0x0011; // result bytes 0,1 = byte (c&3) of the first / second operand
+				const uint32_t lo = __byte_perm(v.x, v.y, sel), hi = __byte_perm(v.z, v.w, sel);
+				*reinterpret_cast<uint32_t*>(T + j * mstride + k0 + 4 * lane) = (lo & 0xffffu) | (hi << 16);
+			}
 		}
 		__syncthreads();
 	}
@@ -2148,11 +2179,11 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	{
 		size_t freeB = 0, totB = 0;
 		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-		if ((size_t)ncol * m > e->T.cap && (size_t)ncol * m > freeB + e->T.cap)
+		if ((size_t)ncol * t_stride(m) > e->T.cap && (size_t)ncol * t_stride(m) > freeB + e->T.cap)
 			RB2_FATAL("column-major symbol matrix (%lld columns x %u strings) does not fit in HBM", (long long)ncol, m);
 	}
-	e->T.need((size_t)ncol * m);
-	LAUNCH(e, k_transpose, cdiv(m, 32), 256, 0, s, e->strEnd.p, m, ncol, e->T.p);
+	e->T.need((size_t)ncol * t_stride(m) + 16);
+	LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, m, ncol, e->T.p);
 	ph_end(e, PH_TRANSPOSE);
 
 	// ---- state for column 0 (mrope.c:279-285) -------------------------------------------
@@ -2200,7 +2231,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
 		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
 		TView tv; memset(&tv, 0, sizeof(tv));
-		tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * m;
+		tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * t_stride(m);
 		LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, e->asym.p, e->tileB.p);
 		run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 		ph_end(e, PH_MEMBERS);

@@ -198,7 +198,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	for (int r = 0; r < P; ++r) {
 		strOff[r] = mAll; tOff[r] = tBytes;
 		mAll += all[r].m; lenAll += all[r].len;
-		tBytes += (all[r].m * all[r].ncol + 15) & ~15ull;
+		tBytes += t_stride(all[r].m) * all[r].ncol;
 		ncolAll = std::max(ncolAll, all[r].ncol);
 	}
 	strOff[P] = mAll; tOff[P] = tBytes;
@@ -211,10 +211,10 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			RB2_FATAL("replicated symbol matrices (%.1f GB) do not fit in HBM", tBytes * 1e-9);
 	}
 	e->T.need(tBytes + 16);
-	if (m) LAUNCH(e, k_transpose, cdiv(m, 32), 256, 0, s, e->strEnd.p, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
+	if (m) LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
 	{
 		uint8_t *dst[RB2_MAX_RANKS]; size_t bytes[RB2_MAX_RANKS];
-		for (int r = 0; r < P; ++r) { dst[r] = e->T.p + tOff[r]; bytes[r] = all[r].m * all[r].ncol; }
+		for (int r = 0; r < P; ++r) { dst[r] = e->T.p + tOff[r]; bytes[r] = t_stride(all[r].m) * all[r].ncol; }
 		cm->gather_blocks(dst, bytes, e->st);
 	}
 	ph_end(e, PH_TRANSPOSE);
@@ -297,7 +297,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			TView tv; memset(&tv, 0, sizeof(tv));
 			tv.n = P;
 			for (int r = 0; r <= P; ++r) tv.off[r] = (uint32_t)strOff[r];
-			for (int r = 0; r < P; ++r) tv.col[r] = (uint64_t)col < all[r].ncol ? e->T.p + tOff[r] + (size_t)col * all[r].m : (const uint8_t*)0;
+			for (int r = 0; r < P; ++r) tv.col[r] = (uint64_t)col < all[r].ncol ? e->T.p + tOff[r] + (size_t)col * t_stride(all[r].m) : (const uint8_t*)0;
 			LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, e->asym.p, e->tileB.p);
 			run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 			ph_end(e, PH_MEMBERS);
