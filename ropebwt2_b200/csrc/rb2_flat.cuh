@@ -554,12 +554,14 @@ struct ChunkScan { // K=1 (uint64): exclusive prefix of the chunk sizes
 	}
 };
 
-// one warp per output block: find its chunks, encode them into a shared-memory image, store it
+// eight lanes per output block (four blocks per warp; a block holds ~9 chunks of random reads): find its
+// chunks, encode them into a shared-memory image, store it
 __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab T, const uint64_t *chunkPre, uint32_t nBlocks, uint8_t *pool, uint32_t *blkCnt)
 {
-	__shared__ __align__(16) uint8_t sImg[4][RB2_BLK + 64];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t k = blockIdx.x * 4 + wid;
+	__shared__ __align__(16) uint8_t sImg[16][RB2_BLK + 64];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = lane >> 3, gl = lane & 7;
+	const uint32_t gmask = 0xffu << (grp * 8);
+	const uint32_t k = (blockIdx.x * 4 + wid) * 4 + grp;
 	if (k >= nBlocks) return;
 	int b = 0;
 	for (int x = 1; x < T.nb; ++x) b += k >= T.blkStart[x];
@@ -570,11 +572,11 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 	const uint64_t c0 = lower((uint64_t)kk * FE_T), c1 = lower((uint64_t)(kk + 1) * FE_T);
 	const uint64_t b0 = c0 < cHi ? chunkPre[c0] : chunkPre[cHi];
 	const uint32_t nbytes = (uint32_t)((c1 < cHi ? chunkPre[c1] : chunkPre[cHi]) - b0);
-	uint8_t *img = sImg[wid];
-	for (int j = lane; j < (RB2_BLK + 64) / 4; j += 32) reinterpret_cast<uint32_t*>(img)[j] = 0;
-	__syncwarp();
+	uint8_t *img = sImg[wid * 4 + grp];
+	for (int j = gl; j < (RB2_BLK + 64) / 4; j += 8) reinterpret_cast<uint32_t*>(img)[j] = 0;
+	__syncwarp(gmask);
 	uint32_t acc[5] = { 0, 0, 0, 0, 0 }, nsym = 0;
-	for (uint64_t c = c0 + lane; c < c1; c += 32) {
+	for (uint64_t c = c0 + gl; c < c1; c += 8) {
 		const uint64_t s0 = T.symStart[b] + (c - cLo) * FE_CHUNK;
 		const uint32_t n = (uint32_t)(s0 + FE_CHUNK < T.symStart[b + 1] ? FE_CHUNK : T.symStart[b + 1] - s0);
 		uint32_t w[8];
@@ -596,20 +598,21 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 		}
 		nsym += n;
 	}
-	uint32_t cnt[6];
-	{
-		Raw6 r = { warp_sum(acc[0]), warp_sum(acc[1]), warp_sum(acc[2]), warp_sum(acc[3]), warp_sum(acc[4]), warp_sum(nsym) };
+	// sums over the eight lanes of the group
 #pragma unroll
-		for (int a = 0; a < 6; ++a) cnt[a] = raw_symbol(r, (uint32_t)a);
+	for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+		for (int q = 0; q < 5; ++q) acc[q] += __shfl_xor_sync(gmask, acc[q], o);
+		nsym += __shfl_xor_sync(gmask, nsym, o);
 	}
-	__syncwarp();
-	if (lane == 0) { img[0] = (uint8_t)(nbytes & 0xff); img[1] = (uint8_t)(nbytes >> 8); }
-	__syncwarp();
-	reinterpret_cast<uint4*>(pool + (size_t)k * RB2_BLK)[lane] = reinterpret_cast<const uint4*>(img)[lane];
-	if (lane < 6) {
-		uint32_t v = 0;
+	if (gl == 0) { img[0] = (uint8_t)(nbytes & 0xff); img[1] = (uint8_t)(nbytes >> 8); }
+	__syncwarp(gmask);
+	uint4 *dst = reinterpret_cast<uint4*>(pool + (size_t)k * RB2_BLK);
+	const uint4 *src = reinterpret_cast<const uint4*>(img);
 #pragma unroll
-		for (int a = 0; a < 6; ++a) if (lane == a) v = cnt[a];
-		blkCnt[(size_t)k * 6 + lane] = v;
+	for (int j = 0; j < 4; ++j) dst[j * 8 + gl] = src[j * 8 + gl];
+	if (gl < 6) {
+		const Raw6 r = { acc[0], acc[1], acc[2], acc[3], acc[4], nsym };
+		blkCnt[(size_t)k * 6 + gl] = raw_symbol(r, (uint32_t)gl);
 	}
 }

@@ -161,7 +161,7 @@ static void flat_end(rb2_engine *e)
 	T.blkStart[e->nb] = nBlocks;
 	e->hctl->poolUsed = 0; // the pool is rewritten from scratch: nothing to carry over when it grows
 	reserve_blocks(e, (uint64_t)nBlocks + nBlocks / 16 + 4096);
-	LAUNCH(e, k_flat_encode, cdiv(nBlocks, 4), 128, 0, f.s[f.cur].p, T, f.chunkPre.p, nBlocks, e->pool, e->blkCnt);
+	LAUNCH(e, k_flat_encode, cdiv(nBlocks, 16), 128, 0, f.s[f.cur].p, T, f.chunkPre.p, nBlocks, e->pool, e->blkCnt);
 	LAUNCH(e, k_fill_u32, cdiv(nBlocks, 256), 256, 0, e->dir[e->cur].order, nBlocks, 0u, 1u);
 	e->nlog = nBlocks;
 	for (int b = 0; b < NBA; ++b) e->blkBkt[b] = b <= e->nb ? T.blkStart[b] : nBlocks;
