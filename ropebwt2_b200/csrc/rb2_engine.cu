@@ -128,13 +128,13 @@ __global__ void k_maxlen(const int64_t *strEnd, uint32_t m, unsigned long long *
 	if ((threadIdx.x & 31) == 0 && l) atomicMax(maxlen, l);
 }
 
-// T[j*mstride + k] = j-th symbol of (reversed) string k, including its terminating NUL (mstride = m
-// rounded up to 16 so that every column starts 16-byte aligned).  One CTA transposes 128 strings, 32
-// symbols at a time: reads walk along the strings (aligned words + funnel shift, 16 bytes per thread),
-// shared memory holds the slab as [4 symbols][string] words, and every warp store writes the same
-// symbol of 128 consecutive strings (128 bytes).
+// Column-major symbol matrix of a batch, 4 bits per symbol: byte T[j*tstride + (k >> 1)], nibble k & 1,
+// holds the j-th symbol of (reversed) string k, including its terminating NUL (tstride = bytes per
+// column, rounded up to 16).  One CTA transposes 128 strings, 32 symbols at a time: reads walk along the
+// strings (aligned words + funnel shift, 16 bytes per thread), shared memory holds the slab as
+// [4 symbols][string] words, and half a warp stores the same symbol of 128 consecutive strings (64 bytes).
 #define TR_S 128
-__host__ __device__ __forceinline__ uint64_t t_stride(uint64_t m) { return (m + 15) & ~(uint64_t)15; }
+__host__ __device__ __forceinline__ uint64_t t_stride(uint64_t m) { return (((m + 1) >> 1) + 15) & ~(uint64_t)15; }
 __global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64_t *strEnd, uint32_t m, int64_t ncol, uint8_t *T)
 {
 	__shared__ __align__(16) uint32_t tile[8][TR_S + 4];
@@ -179,13 +179,17 @@ __global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64
 			for (int i = 0; i < 4; ++i) tile[half * 4 + i][r] = w[i];
 		}
 		__syncthreads();
-		for (int c = wid; c < 32; c += 8) { // symbol j0+c of strings k0 + 4*lane .. +3
+		for (int cp = wid; cp < 16; cp += 8) { // two columns per warp pass: lanes 0-15 / 16-31; a lane packs 8 strings
+			const int c = cp * 2 + (lane >> 4), hl = lane & 15;
 			const int64_t j = j0 + c;
-			if (j < ncol && (uint64_t)k0 + 4 * lane < mstride) {
-				const uint4 v = *reinterpret_cast<const uint4*>(&tile[c >> 2][4 * lane]);
+			if (j < ncol && (uint64_t)(k0 >> 1) + 4 * hl < mstride) {
+				const uint4 v0 = *reinterpret_cast<const uint4*>(&tile[c >> 2][8 * hl]), v1 = *reinterpret_cast<const uint4*>(&tile[c >> 2][8 * hl + 4]);
 				const uint32_t sel = 0x0040 + (c & 3) * 0x0011; // result bytes 0,1 = byte (c&3) of the first / second operand
-				const uint32_t lo = __byte_perm(v.x, v.y, sel), hi = __byte_perm(v.z, v.w, sel);
-				*reinterpret_cast<uint32_t*>(T + j * mstride + k0 + 4 * lane) = (lo & 0xffffu) | (hi << 16);
+				uint32_t a = (__byte_perm(v0.x, v0.y, sel) & 0xffffu) | (__byte_perm(v0.z, v0.w, sel) << 16); // symbols of strings 0..3, one per byte
+				uint32_t b = (__byte_perm(v1.x, v1.y, sel) & 0xffffu) | (__byte_perm(v1.z, v1.w, sel) << 16); // strings 4..7
+				a = (a | (a >> 4)) & 0x00ff00ffu; a = (a | (a >> 8)) & 0xffffu;   // four nibbles
+				b = (b | (b >> 4)) & 0x00ff00ffu; b = (b | (b >> 8)) & 0xffffu;
+				*reinterpret_cast<uint32_t*>(T + j * mstride + (k0 >> 1) + 4 * hl) = a | (b << 16);
 			}
 		}
 		__syncthreads();
@@ -223,7 +227,7 @@ __device__ __forceinline__ uint32_t tview_fetch(const TView &tv, uint32_t id)
 	const uint8_t *c = tv.col[0]; uint32_t o = tv.off[0];
 #pragma unroll
 	for (int x = 1; x < TV_MAX; ++x) if (r == x) { c = tv.col[x]; o = tv.off[x]; }
-	return c[id - o];
+	return (c[(id - o) >> 1] >> (((id - o) & 1) * 4)) & 15u;
 }
 
 __global__ void __launch_bounds__(256) k_member_fetch(const TView tv, const uint32_t *sid, uint32_t M, uint8_t *asym, uint32_t *tileTot)
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(256) k_member_fetch(const TView tv, const uint
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			if (k + i < M) {
-				uint32_t a = tv.n == 1 ? tv.col[0][id[i]] : tview_fetch(tv, id[i]);
+				uint32_t a = tv.n == 1 ? (tv.col[0][id[i] >> 1] >> ((id[i] & 1) * 4)) & 15u : tview_fetch(tv, id[i]);
 				packed |= a << (8 * i);
 #pragma unroll
 				for (int x = 0; x < 6; ++x) c[x] += a == x;
