@@ -141,7 +141,7 @@ extern "C" rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int r
 	RB2_CUDA(cudaEventCreateWithFlags(&e->evMerge, cudaEventDisableTiming));
 	RB2_CUDA(cudaMalloc(&e->dDirOffPre, NBMAX * 7 * sizeof(int64_t)));
 	RB2_CUDA(cudaMallocHost(&e->hDirOffPre, NBMAX * 7 * sizeof(int64_t)));
-	RB2_CUDA(cudaMallocHost(&e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t)));
+	RB2_CUDA(cudaMallocHost(&e->hPlan, 2 * 2 * (NBMAX * 6 + 8) * sizeof(uint32_t))); // two columns in flight
 	if (group) { if (group->n != nranks) RB2_FATAL("group size mismatch"); e->comm = new LocalComm(group, rank); }
 	else e->comm = new NcclComm(rank, nranks, nccl_uid);
 	shard_reset_index(e);
@@ -368,6 +368,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		uint32_t gBktN[NBA], mBktN[NBA];
 		memset(curG, 0, sizeof(curG)); memset(curM, 0, sizeof(curM)); memset(mglobNext, 0, sizeof(mglobNext));
 		int nMyPieces = 0;
+		uint32_t *hPlan = e->hPlan + (col & 1) * 2 * (NBMAX * 6 + 8); // the copy of the previous column may still be queued
 		for (int t = 0; t < NBMAX; ++t) {
 			const int a = t / 6, x = t % 6, dst = e->owner[t];
 			gBktN[t] = (uint32_t)curG[me]; mBktN[t] = (uint32_t)curM[me];
@@ -387,8 +388,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				} else {
 					pcG.push_back(pg); pcM.push_back(pm);
 					if (dst == me) { // rebase table of the member ranges I receive
-						e->hPlan[nMyPieces] = (uint32_t)pg.dof;
-						e->hPlan[NBMAX * 6 + 8 + nMyPieces] = (uint32_t)pm.dof - (uint32_t)pm.so;
+						hPlan[nMyPieces] = (uint32_t)pg.dof;
+						hPlan[NBMAX * 6 + 8 + nMyPieces] = (uint32_t)pm.dof - (uint32_t)pm.so;
 						++nMyPieces;
 					}
 				}
@@ -443,12 +444,14 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			if (singles) { if (Gn + 1 > 0) LAUNCH(e, k_fill_u32, cdiv((uint64_t)Gn + 1, 256), 256, 0, e->gOff[cs].p, Gn + 1, 0u, 1u); }
 			else if (Gn > 0) {
 				e->plan.need(2 * (NBMAX * 6 + 8));
-				RB2_CUDA(cudaMemcpyAsync(e->plan.p, e->hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
+				RB2_CUDA(cudaMemcpyAsync(e->plan.p, hPlan, 2 * (NBMAX * 6 + 8) * sizeof(uint32_t), cudaMemcpyHostToDevice, e->st));
 				LAUNCH(e, k_rebase_goff, cdiv(Gn, 256), 256, 0, e->gOff[cs].p, Gn, Mn, e->plan.p, e->plan.p + NBMAX * 6 + 8, nMyPieces);
 			}
-			RB2_CUDA(cudaStreamSynchronize(e->st)); // hPlan and the piece lists are reused next column
-			ph_collect(e, e->flat.pending);
-			e->flat.pending = 0;
+			if (!flat) { // (the dense regime keeps the host running ahead: its events are collected at the next control-block read)
+				RB2_CUDA(cudaStreamSynchronize(e->st));
+				ph_collect(e, e->flat.pending);
+				e->flat.pending = 0;
+			}
 			e->stats.exch_bytes += ((int64_t)Gn * (8 + (useSizes ? 8 : 0) + (singles ? 0 : 4)) + (int64_t)Mn * 4);
 		}
 		// ---- advance -------------------------------------------------------------------------------
