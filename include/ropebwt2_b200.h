@@ -13,6 +13,8 @@
  *                                rope_insert_run / rope_rank2a     rope.c:114-194
  *                                rle_insert_cached / rle_rank2a    rle.c:10-89,134-191
  *   rb2_insert_multi_dev         same, input already resident in HBM (bench "value" leg)
+ *   rb2_create_sharded / rb2_insert_multi_sharded   the same path on ONE index spread over several GPUs
+ *                                (the reference's per-bucket worker threads, mrope.c:287-325, across devices)
  *   rb2_rank2a                   mr_rank2a                         mrope.c:70-105
  *   rb2_counts                   the rope_t::c[6] marginals        rope.h:19, mrope.h:86-116
  *   rb2_num_blocks/fetch_blocks  rope_itr_first/next_block         rope.c:200-219
@@ -44,9 +46,9 @@ typedef struct {
 	int64_t n_strings, n_symbols;       /* inserted strings / symbols (sentinels included) */
 	int64_t n_columns;                  /* BCR columns executed */
 	int64_t n_launches;                 /* kernels launched by this library */
-	int64_t n_merge_launches;           /* launches of the dominant kernel (k_merge_fast) */
-	int64_t merge_blocks;               /* work items (leaf blocks read) of the merge kernels, all launches */
-	int64_t merge_bytes_rw;             /* algorithmic HBM bytes of the merge kernels: blocks read + written, x512 */
+	int64_t n_merge_launches;           /* launches of the dominant kernel (k_flat_merge in the dense regime, k_merge_half in the sparse one) */
+	int64_t merge_blocks;               /* work items of the merge kernels, all launches: 8192-symbol tiles (dense) / leaf blocks read (sparse) */
+	int64_t merge_bytes_rw;             /* algorithmic HBM bytes of the merge kernels: arrays read + written + records (dense) / blocks read + written, x512 (sparse) */
 	int64_t n_records;                  /* (position, symbol, count) insertion records merged */
 	int64_t pool_blocks, pool_capacity; /* leaf blocks in use / allocated */
 	double  ms_total;                   /* device time of whole rb2_insert_multi* calls (CUDA events) */
@@ -54,10 +56,10 @@ typedef struct {
 	double  ms_transpose;               /* string split + column-major transpose */
 	double  ms_members;                 /* symbol fetch, radix partition of the string set */
 	double  ms_groups;                  /* group scan, record emission, rank pre-pass */
-	double  ms_merge;                   /* k_merge_fast (the dominant kernel) */
+	double  ms_merge;                   /* the dominant kernel: k_flat_merge with its two planning kernels (dense) / k_merge_half (sparse) */
 	double  ms_directory;               /* item planning + directory rebuild */
-	double  ms_merge_general;           /* k_merge_general: over-full / multi-item / empty blocks */
-	int64_t general_items;              /* work items that went through k_merge_general */
+	double  ms_merge_general;           /* sparse regime: k_merge_fast + k_merge_general (over-full / multi-item / empty blocks) */
+	int64_t general_items;              /* sparse regime: work items k_merge_half handed on */
 	double  ms_exchange;                /* sharded build: string-state transfer between ranks */
 	int64_t exch_bytes;                 /* sharded build: bytes of string state this rank received */
 	double  ms_convert;                 /* dense regime: leaf blocks <-> flat symbol array at the ends of a batch */
