@@ -250,20 +250,8 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	auto run_len = [&](uint32_t k) -> uint32_t { return ((uint32_t)S.sLS[k] >> 3) + 1; };
 	const uint32_t rel = tid * FT_CH;
 	uint32_t k0;                        // first entry with sKey >= rel
-	{
-		// records are spread almost evenly late in a batch: start from the proportional guess, walk a few
-		// steps, and only bisect what is left if that was not enough
-		uint32_t lo = 0, hi = nS, g = (uint32_t)(((uint64_t)rel * nS) / FT_OUT);
-		g = g < nS ? g : nS;
-#pragma unroll 1
-		for (int step = 0; step < 6; ++step) {
-			if (g > 0 && S.sKey[g - 1] >= rel) { hi = g - 1; --g; }
-			else if (g < nS && S.sKey[g] < rel) { lo = g + 1; ++g; }
-			else { lo = hi = g; break; }
-		}
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.sKey[mid] >= rel) hi = mid; else lo = mid + 1; }
-		k0 = lo;
-	}
+	// (plain bisection: a proportional first guess plus a short walk was measured to cost twice the instructions)
+	{ uint32_t lo = 0, hi = nS; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.sKey[mid] >= rel) hi = mid; else lo = mid + 1; } k0 = lo; }
 	uint32_t runRem = 0, runSym = 0, oldIdx;
 	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) > rel) { // inside the run of entry k0-1
 		runRem = (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) - rel; runSym = S.sLS[k0 - 1] & 7u;
