@@ -160,6 +160,9 @@ template <int CAP> struct FlatSmemT {
 	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every 16-byte chunk of old4 (16-bit fields)
 	uint16_t sKey[CAP + 1];              // staged records: run start inside the tile
 	uint16_t sLS[CAP + 1];               // (run length inside the tile - 1) << 3 | symbol
+	uint32_t cntC[FT_NOC + 1];           // staged records that start in each 32-symbol output chunk
+	uint16_t k0C[FT_NOC + 2];            // ... and their exclusive prefix = the first record at or behind each chunk
+	uint32_t anyLong;                    // some staged record is longer than one symbol
 	uint32_t warpTot[8][3];
 	uint32_t recCnt[FT_SUB][6];          // symbols the records put into each FT_DIR sub-tile
 	uint32_t subX[FT_SUB + 1];           // old symbols (local index) in front of each sub-tile
@@ -222,15 +225,37 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		}
 		if (lane == 31) { S.warpTot[wid][0] = inc[0]; S.warpTot[wid][1] = inc[1]; S.warpTot[wid][2] = inc[2]; }
 	} else {
-		if (tid == NCNT && nCarry) { S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym); }
-		if (tid - NCNT < FT_SUB * 6) (&S.recCnt[0][0])[tid - NCNT] = 0;
-		for (uint32_t k = tid - NCNT; k < r1 - r0; k += 256 - NCNT) {
+		// the three staging warps also index the records by output chunk (they would otherwise wait for the
+		// counting warps): histogram of chunk ids, then one warp scans it.  Barrier 1 is private to them.
+		const int st = tid - NCNT;
+		for (int c = st; c <= FT_NOC; c += 256 - NCNT) S.cntC[c] = 0;
+		if (st == 0) S.anyLong = 0;
+		if (st < FT_SUB * 6) (&S.recCnt[0][0])[st] = 0;
+		asm volatile("bar.sync 1, 96;" ::: "memory");
+		if (st == 0 && nCarry) {
+			S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym);
+			atomicAdd(&S.cntC[0], 1u);
+			if (carryLen > 1) S.anyLong = 1;
+		}
+		for (uint32_t k = st; k < r1 - r0; k += 256 - NCNT) {
 			const uint32_t r = r0 + k;
 			const uint32_t pre = A.V.Pre(r), sc = A.V.SC(r);
 			const uint32_t key = (uint32_t)((uint64_t)A.V.P[r] + pre - o0);
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
 			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
+			atomicAdd(&S.cntC[key / FT_CH], 1u);
+			if (len > 1) S.anyLong = 1;
+		}
+		asm volatile("bar.sync 1, 96;" ::: "memory");
+		if (wid == NCNT / 32) { // eight chunks per lane
+			uint32_t v[8], sum = 0;
+#pragma unroll
+			for (int i = 0; i < 8; ++i) { v[i] = S.cntC[lane * 8 + i]; sum += v[i]; }
+			uint32_t ex = warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+			for (int i = 0; i < 8; ++i) { S.k0C[lane * 8 + i] = (uint16_t)ex; ex += v[i]; }
+			if (lane == 31) S.k0C[FT_NOC] = (uint16_t)ex;
 		}
 	}
 	__syncthreads();
@@ -250,8 +275,8 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	auto run_len = [&](uint32_t k) -> uint32_t { return ((uint32_t)S.sLS[k] >> 3) + 1; };
 	const uint32_t rel = tid * FT_CH;
 	uint32_t k0;                        // first entry with sKey >= rel
-	// (plain bisection: a proportional first guess plus a short walk was measured to cost twice the instructions)
-	{ uint32_t lo = 0, hi = nS; while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.sKey[mid] >= rel) hi = mid; else lo = mid + 1; } k0 = lo; }
+	k0 = S.k0C[tid];                    // (a bisection over sKey costs 70 instructions per warp; a proportional guess + walk twice that)
+	const uint32_t kEnd = S.k0C[tid + 1]; // one past the last entry that starts in this chunk
 	uint32_t runRem = 0, runSym = 0, oldIdx;
 	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) > rel) { // inside the run of entry k0-1
 		runRem = (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) - rel; runSym = S.sLS[k0 - 1] & 7u;
@@ -271,10 +296,10 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	if (runRem >= FT_CH) {                          // inside one long run
 		ow[0] = ow[1] = ow[2] = ow[3] = runSym * 0x11111111u;
 		atomicAdd(&S.recCnt[sbMine][runSym], FT_CH);
-	} else if (runRem || (k0 < nS && S.sKey[k0] < rel + FT_CH)) { // records start (or a run ends) inside these 32 symbols
-		// are all of them single symbols?  (the rule late in a batch)
-		uint32_t k = k0; bool single = runRem == 0;
-		while (single && k < nS && S.sKey[k] < rel + FT_CH) { single = ((uint32_t)S.sLS[k] >> 3) == 0; ++k; }
+	} else if (runRem || kEnd > k0) {               // records start (or a run ends) inside these 32 symbols
+		// are all of them single symbols?  (the rule late in a batch: then no record of the tile is longer)
+		uint32_t k = kEnd; bool single = runRem == 0;
+		if (single && S.anyLong) { k = k0; while (single && k < kEnd) { single = ((uint32_t)S.sLS[k] >> 3) == 0; ++k; } }
 		if (single) {
 			for (uint32_t j = k0; j < k; ++j) {
 				const uint32_t sy = S.sLS[j] & 7u;
