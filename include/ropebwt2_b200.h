@@ -90,6 +90,9 @@ void rb2_counts(rb2_engine_t *e, int64_t c[36]);
  * cy == NULL skips the second query (mr_rank1a) */
 void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6]);
 
+/* n rank queries in one call (one warp per position): out[i*6+a] = #a in BWT[0, x[i]) */
+void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int64_t *out);
+
 /* Leaf blocks of one bucket in logical (left-to-right) order. */
 int64_t rb2_num_blocks(rb2_engine_t *e, int bucket);
 /* Copy blocks [first, first+n) of `bucket` to host: dst gets n*512 bytes, cnt (optional)

@@ -24,7 +24,8 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_destroy", "rb2_sorting_ord
                "rb2_dev_free", "rb2_dev_upload", "rb2_reset", "rb2_host_alloc", "rb2_host_free", "rb2_insert_run",
                "rb2_bucket_rank2a", "rb2_last_sentinel_rank",
                "rb2_group_create", "rb2_group_destroy", "rb2_nccl_unique_id", "rb2_create_sharded",
-               "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets"]
+               "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets",
+               "rb2_rank_batch"]
 
 
 class Stats(C.Structure):
@@ -122,6 +123,7 @@ def load(rebuild: bool = False) -> C.CDLL:
     L.rb2_insert_multi_sharded_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.rb2_shard_owner.restype = C.c_int
     L.rb2_shard_owner.argtypes = [C.c_int, C.c_int]
+    L.rb2_rank_batch.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
     L.rb2_num_buckets.restype = C.c_int
     L.rb2_num_buckets.argtypes = [C.c_void_p]
     _lib = L
@@ -174,6 +176,13 @@ class MRope:
         cy = np.zeros(6, dtype=np.int64)
         self.L.mr_rank2a(self.h, x, y, cx.ctypes.data_as(_i64p), cy.ctypes.data_as(_i64p) if y >= 0 else None)
         return cx, cy
+
+    def rank_batch(self, xs) -> np.ndarray:
+        """occ(a, x) for every position in xs at once -> int64 [n, 6] (rb2_rank_batch)."""
+        x = np.ascontiguousarray(xs, dtype=np.int64)
+        out = np.zeros((x.size, 6), dtype=np.int64)
+        self.L.rb2_rank_batch(self.engine_handle, x.size, x.ctypes.data_as(_i64p), out.ctypes.data_as(_i64p))
+        return out
 
     def stats(self) -> dict:
         st = Stats()

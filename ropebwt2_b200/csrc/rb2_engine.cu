@@ -398,6 +398,27 @@ __global__ void __launch_bounds__(32) k_rank_query(const uint8_t *pool, Dir dir,
 	if (err && lane == 0) atomicOr(&ctl->err, err);
 }
 
+// batched API rank (a query service on top of mr_rank1a, mrope.c:70-105): one warp per position
+__global__ void __launch_bounds__(128) k_rank_batch(const uint8_t *pool, Dir dir, uint32_t nlog, uint32_t n, const int64_t *x, int64_t *out, Ctl *ctl)
+{
+	__shared__ __align__(16) uint8_t sRuns[4][RB2_IMG_BYTES];
+	__shared__ uint32_t sCnt[4][32 * 7];
+	__shared__ int64_t sRes[4][6];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t err = 0;
+	for (uint32_t q = blockIdx.x * 4 + wid; q < n; q += gridDim.x * 4) {
+		int64_t c[6];
+		warp_rank6(pool, dir, nlog, x[q], lane, sRuns[wid], sCnt[wid], sRes[wid], c, err);
+		if (lane < 6) {
+			int64_t v = 0;
+#pragma unroll
+			for (int a = 0; a < 6; ++a) if (lane == a) v = c[a];
+			out[(size_t)q * 6 + lane] = v;
+		}
+	}
+	if (err && lane == 0) atomicOr(&ctl->err, err);
+}
+
 // =====================================================================================
 // Groups: per-group histogram of next symbols, scan, record + next-group emission
 // =====================================================================================
@@ -2378,6 +2399,27 @@ extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6],
 	RB2_CUDA(cudaMemcpyAsync(e->hRankOut, e->dRankOut, 12 * 8, cudaMemcpyDeviceToHost, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	for (int a = 0; a < 6; ++a) { cx[a] = e->hRankOut[a]; if (y >= 0) cy[a] = e->hRankOut[6 + a]; }
+}
+
+// n rank queries in one call: out[i*6+a] = #a in BWT[0, x[i]) (the batched form of mr_rank1a)
+extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int64_t *out)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	if (e->comm) RB2_FATAL("rb2_rank_batch: not available on a sharded engine yet");
+	int64_t total = 0;
+	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
+	const int64_t CH = 1 << 20;
+	DevBuf<int64_t> dx, dout;
+	dx.need(CH < n ? CH : n); dout.need((size_t)(CH < n ? CH : n) * 6);
+	for (int64_t o = 0; o < n; o += CH) {
+		const int64_t m = n - o < CH ? n - o : CH;
+		for (int64_t i = 0; i < m; ++i) if (x[o + i] < 0 || x[o + i] > total) RB2_FATAL("rank position out of range");
+		RB2_CUDA(cudaMemcpyAsync(dx.p, x + o, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
+		LAUNCH(e, k_rank_batch, std::min<uint32_t>(cdiv(m, 4), (uint32_t)e->nSM * 16), 128, 0, e->pool, e->dir[e->cur], e->nlog, (uint32_t)m, dx.p, dout.p, e->dctl);
+		RB2_CUDA(cudaMemcpyAsync(out + o * 6, dout.p, (size_t)m * 48, cudaMemcpyDeviceToHost, e->st));
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+	}
+	dx.release(); dout.release();
 }
 
 extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)

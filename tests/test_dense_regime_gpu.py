@@ -64,3 +64,25 @@ def test_auto_choice_and_big_counts(monkeypatch):
     assert m.stats()["flat_batches"] == 1
     assert np.array_equal(text(m), o.text())
     m.close()
+
+
+def test_batched_rank_queries(monkeypatch):
+    """rb2_rank_batch (one warp per position) against the oracle's occ() on a re-encoded and on an
+    in-place updated index"""
+    rng = np.random.default_rng(5)
+    for regime in ("1", "0"):
+        monkeypatch.setenv("RB2_FLAT", regime)
+        o, m = orc.Oracle(1), MRope(1)
+        for seed in (3, 4):
+            buf = encode_batch(genome_reads(3000, 70, seed, coverage=30.0))
+            o.insert_multi(buf)
+            m.insert_multi(buf)
+        xs = np.concatenate([[0, 1, o.total() - 1, o.total()], rng.integers(0, o.total() + 1, size=3000)])
+        got = m.rank_batch(xs)
+        for x, g in zip(xs[:300], got[:300]):
+            assert np.array_equal(g, o.rank1a(int(x))), (regime, int(x))
+        # consistency of the whole batch: occ is monotone and occ(total) are the marginals
+        order = np.argsort(xs, kind="stable")
+        assert (np.diff(got[order], axis=0) >= 0).all()
+        assert np.array_equal(got[3], o.counts().sum(0))
+        m.close()
