@@ -2325,7 +2325,6 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		cs ^= 1;
 	}
 	if (flat) {
-		for (int b = 0; b < 6; ++b) e->bktLen[b] = e->bktLen[b]; // (already advanced column by column)
 		flat_end(e);
 		ph_collect(e, e->flat.pending); e->flat.pending = 0;
 		++e->stats.flat_batches;
