@@ -68,3 +68,14 @@ def test_mrope_struct_layout():
     assert binding._MRopeStruct.r.offset == 8
     assert binding._MRopeStruct.priv.offset == 56  # the reference's mrope_t ends here (mrope.h:10-14)
     assert C.sizeof(binding._MRopeStruct) == 64
+
+
+@pytest.mark.parametrize("header", ["mrope.h", "rope.h", "rle.h", "ropebwt2_b200.h"])
+def test_headers_are_plain_c(header, tmp_path):
+    """A maintainer of the reference includes these from C99 sources (main.c): they must compile as C,
+    on their own, without warnings."""
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(void) { return 0; }\n' % header)
+    r = subprocess.run(["gcc", "-std=gnu99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
