@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -118,3 +119,88 @@ def test_owner_map_is_a_partition_into_contiguous_ranges():
         assert max(counts) - min(counts) <= 1
     from ropebwt2_b200 import load
     assert load().rb2_shard_owner(9, 0) == -1 and load().rb2_shard_owner(2, 36) == -1
+
+
+# ---- the sharded algorithm itself, modelled on the CPU (oracle/shard_model.py) -------------------------
+
+def _batches(so):
+    from ropebwt2_b200.synth import genome_reads, varlen_reads
+    rd = genome_reads(160, 14, 31 + so, coverage=25.0)       # duplicates -> non-empty intervals in later batches
+    return [list(rd[:70]), list(rd[70:110]), varlen_reads(40, 12, 5 + so)]
+
+
+def _reversed(reads):
+    return [[int(c) for c in r[::-1]] for r in reads]
+
+
+def _oracle_text(so, batches):
+    from oracle import oracle as orc
+    from ropebwt2_b200.synth import encode_batch
+    o = orc.Oracle(so)
+    for b in batches:
+        o.insert_multi(encode_batch(b))
+    return o.text().tolist()
+
+
+def test_shard_model_world1_matches_the_oracle():
+    from oracle.shard_model import LocalComm, ShardModel, owner_map
+    from ropebwt2_b200 import load
+    for world in range(1, 9):   # the model partitions exactly like the library
+        assert owner_map(world) == [load().rb2_shard_owner(world, s) for s in range(36)]
+    for so in (0, 1, 2):
+        batches = _batches(so)
+        m = ShardModel(LocalComm(), so)
+        for b in batches:
+            m.insert_multi(_reversed(b))
+        assert m.text() == _oracle_text(so, batches), so
+
+
+def _model_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.shard_model import ShardModel
+        from ropebwt2_b200.dist import split_batch_bytes
+
+        class GlooComm:
+            def __init__(self):
+                self.rank, self.world = rank, world
+
+            def allgather(self, obj):
+                box = [None] * world
+                dist.all_gather_object(box, obj)
+                return box
+        ok = True
+        for so in (0, 1, 2):
+            batches = _batches(so)
+            m = ShardModel(GlooComm(), so)
+            for b in batches:
+                a, e = split_batch_bytes(len(b), world)[rank]
+                m.insert_multi(_reversed(b[a:e]))
+            text = m.text()
+            # every rank holds only its own sub-buckets, and together they are the oracle's BWT
+            assert set(m.seg) == {s for s in range(36) if m.own[s] == rank}
+            if rank == 0:
+                ok = ok and text == _oracle_text(so, batches)
+        out.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_model_over_gloo_matches_the_oracle(world):
+    """The N > 1 algorithm on CPU: sub-bucket ownership, per-column table all-gather, whole-index ranks
+    from local counts + gathered totals, routing (x,y)+a -> (a,x), target order -- over a real process
+    group.  The CUDA engine implements the same steps (tests/test_sharded_gpu.py checks it on the GPU)."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
