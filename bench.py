@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (BASELINE config 2: 100M)")
     ap.add_argument("--length", type=int, default=101)
     ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--cpu-reads", type=int, default=1_000_000, help="reads in the bounded CPU-reference sample")
+    ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-reference sample (about 15 s of reference time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layout", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one index sharded over all GPUs (default) or one independent index per GPU")
