@@ -1837,6 +1837,8 @@ struct rb2_engine {
 	int64_t *dDirOffPre, *hDirOffPre; // the same in front of the column (dense regime: record positions are pre-column)
 	uint32_t *hPlan; DevBuf<uint32_t> plan;
 	cudaStream_t st2; cudaEvent_t evEarly, evMerge; // second stream: the part of the exchange that overlaps the merge
+	// RB2_GPUS > 1 (rb2_cluster.inl): this engine is a proxy in front of nChild sharded engines
+	int nChild; rb2_engine *child[RB2_MAX_RANKS]; rb2_group *grp;
 	FlatState flat; DevBuf<uint32_t> recPre;
 	int64_t tot[6][6]; int64_t bktLen[6];
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
@@ -1998,6 +2000,15 @@ extern "C" int rb2_device_count(void)
 	return n;
 }
 
+static void cluster_attach(rb2_engine *e, int device, int sorting_order);
+static void cluster_destroy(rb2_engine *e);
+static void cluster_reset(rb2_engine *e);
+static void cluster_insert_multi(rb2_engine *e, int64_t len, const uint8_t *s);
+static int64_t cluster_num_blocks(rb2_engine *e, int bucket);
+static int64_t cluster_fetch_blocks(rb2_engine *e, int bucket, int64_t first, int64_t n, uint8_t *dst, int64_t *cnt);
+static void cluster_rank1(rb2_engine *e, int64_t x, int64_t c[6]);
+#define RB2_NO_CLUSTER(e, what) do { if ((e)->nChild) RB2_FATAL(what " is not available with RB2_GPUS > 1"); } while (0)
+
 extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 {
 	if (sorting_order < 0 || sorting_order > 2) RB2_FATAL("sorting order must be 0, 1 or 2 (mrope.c:18)");
@@ -2008,6 +2019,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	rb2_engine *e = new rb2_engine();
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
+	e->nChild = 0; e->grp = 0;
 	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0;
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
@@ -2037,6 +2049,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	ctl_push(e);
 	rebuild_directory(e, false);
 	pull_totals(e);
+	cluster_attach(e, device, sorting_order);
 	return e;
 }
 
@@ -2044,6 +2057,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 static void shard_reset_index(rb2_engine *e);
 extern "C" void rb2_reset(rb2_engine_t *e)
 {
+	if (e->nChild) { cluster_reset(e); return; }
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (e->comm) { shard_reset_index(e); return; }
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
@@ -2069,6 +2083,7 @@ extern "C" void rb2_host_free(void *p) { RB2_CUDA(cudaFreeHost(p)); }
 extern "C" void rb2_destroy(rb2_engine_t *e)
 {
 	if (!e) return;
+	if (e->nChild) cluster_destroy(e);
 	RB2_CUDA(cudaSetDevice(e->dev));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
@@ -2343,6 +2358,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 extern "C" void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev)
 {
 	if (len <= 0) RB2_FATAL("mr_insert_multi: empty batch (mrope.c:268)");
+	RB2_NO_CLUSTER(e, "rb2_insert_multi_dev");
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (((uintptr_t)s_dev & 15) != 0) RB2_FATAL("device batch must be 16-byte aligned");
 	if (len > RB2_MAX_BATCH_BYTES) RB2_FATAL("device-resident batches are limited to %lld bytes; use the host entry point", (long long)RB2_MAX_BATCH_BYTES);
@@ -2357,6 +2373,7 @@ extern "C" void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t
 extern "C" void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s)
 {
 	if (len <= 0 || s[len - 1] != 0) RB2_FATAL("mr_insert_multi: batch must be non-empty and end with NUL (mrope.c:268)");
+	if (e->nChild) { cluster_insert_multi(e, len, s); return; }
 	RB2_CUDA(cudaSetDevice(e->dev));
 	RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
 	int64_t off = 0;
@@ -2389,6 +2406,12 @@ extern "C" void rb2_counts(rb2_engine_t *e, int64_t c[36])
 
 extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6])
 {
+	if (e->nChild) {
+		cluster_rank1(e, x, cx);
+		if (cy && y >= 0) cluster_rank1(e, y, cy);
+		RB2_CUDA(cudaSetDevice(e->dev));
+		return;
+	}
 	RB2_CUDA(cudaSetDevice(e->dev));
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
@@ -2404,6 +2427,7 @@ extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6],
 extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int64_t *out)
 {
 	RB2_CUDA(cudaSetDevice(e->dev));
+	RB2_NO_CLUSTER(e, "rb2_rank_batch");
 	if (e->comm) RB2_FATAL("rb2_rank_batch: not available on a sharded engine yet");
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
@@ -2424,11 +2448,13 @@ extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int
 extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)
 {
 	if (bucket < 0 || bucket >= e->nb) RB2_FATAL("bucket out of range");
+	if (e->nChild) return cluster_num_blocks(e, bucket);
 	return (int64_t)e->blkBkt[bucket + 1] - e->blkBkt[bucket];
 }
 
 extern "C" int64_t rb2_fetch_blocks(rb2_engine_t *e, int bucket, int64_t first, int64_t n, uint8_t *dst, int64_t *cnt)
 {
+	if (e->nChild) return cluster_fetch_blocks(e, bucket, first, n, dst, cnt);
 	RB2_CUDA(cudaSetDevice(e->dev));
 	int64_t nb = rb2_num_blocks(e, bucket);
 	if (first < 0 || first > nb) RB2_FATAL("block index out of range");
@@ -2446,6 +2472,7 @@ extern "C" int64_t rb2_fetch_blocks(rb2_engine_t *e, int bucket, int64_t first, 
 
 extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const uint8_t *src, const int64_t *cnt)
 {
+	RB2_NO_CLUSTER(e, "restoring an index (rb2_load_blocks)");
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
 	if (n <= 0) return;
@@ -2485,6 +2512,7 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 extern "C" void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st) { *st = e->stats; }
 extern "C" void rb2_reset_stats(rb2_engine_t *e)
 {
+	for (int r = 0; r < e->nChild; ++r) rb2_reset_stats(e->child[r]);
 	int64_t pb = e->stats.pool_blocks, pc = e->stats.pool_capacity;
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->stats.pool_blocks = pb; e->stats.pool_capacity = pc;
@@ -2506,6 +2534,7 @@ extern "C" void rb2_dev_upload(rb2_engine_t *e, void *dst, const void *src, int6
 }
 
 #include "rb2_shard.inl"
+#include "rb2_cluster.inl"
 
 // ---- single-run and bucket-local entry points behind rope.h ---------------------------------
 
@@ -2521,6 +2550,7 @@ static int64_t bucket_start(const rb2_engine *e, int b)
 // `bucket`; returns the bucket-local rank(a, x) before the insertion.
 extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a, int64_t rl)
 {
+	RB2_NO_CLUSTER(e, "rope_insert_run");
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5 || a < 0 || a > 5 || rl <= 0) RB2_FATAL("rb2_insert_run: bad argument");
 	if (x < 0 || x > e->bktLen[bucket]) RB2_FATAL("rb2_insert_run: position out of range");
@@ -2568,6 +2598,7 @@ extern "C" void rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_
 // inserted last as a single-string batch, local to the bucket it went into.
 extern "C" int64_t rb2_last_sentinel_rank(rb2_engine_t *e)
 {
+	RB2_NO_CLUSTER(e, "mr_insert1's return value");
 	int64_t cx[6];
 	rb2_rank2a(e, e->lastP, -1, cx, 0);
 	int64_t z = cx[0];
