@@ -50,13 +50,20 @@ def lib_path() -> str:
     return _build.LIB
 
 
-def load(rebuild: bool = False) -> C.CDLL:
+def load(rebuild: bool = False, path: str = None) -> C.CDLL:
     """Build (if stale) and load the shared library.  Raises if it cannot be built/loaded:
-    there is deliberately no fallback."""
+    there is deliberately no fallback.  `path` is for the test suite only: tests/emu loads the
+    engine compiled against its CPU emulator of the CUDA execution model that way (kernel-logic
+    checks on machines without a GPU); nothing in this package ever passes it."""
     global _lib
-    if _lib is not None and not rebuild:
+    if _lib is not None and not rebuild and path is None:
         return _lib
-    path = _build.build() if (rebuild or not os.path.exists(_build.LIB) or os.environ.get("RB2_REBUILD")) else _build.LIB
+    if path is None:
+        # build() returns at once when the library is newer than every source; a prebuilt library
+        # on a machine without nvcc (the GPU box) is used as it is
+        import shutil
+        have_nvcc = shutil.which(os.environ.get("NVCC", "nvcc")) is not None
+        path = _build.build(force=rebuild) if (have_nvcc or not os.path.exists(_build.LIB)) else _build.LIB
     L = C.CDLL(path)
     L.mr_init.restype = C.c_void_p
     L.mr_init.argtypes = [C.c_int, C.c_int, C.c_int]

@@ -14,6 +14,18 @@
 
 #define FULLMASK 0xffffffffu
 
+// Three constructs have no plain-C++ spelling.  The product build (nvcc, sm_100a) uses the CUDA forms;
+// RB2_EMU is defined only by the CPU kernel-logic emulator of the test suite (tests/emu/cuda_emu.h).
+#ifdef RB2_EMU
+#define RB2_DYN_SMEM(name) uint8_t *name = RB2_EMU_DYN_SMEM
+#define RB2_NAMED_BAR(id, nthreads) rb2emu::named_barrier((id), (nthreads))
+#define RB2_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) rb2emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define RB2_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#define RB2_NAMED_BAR(id, nthreads) asm volatile("bar.sync %0, %1;" :: "n"(id), "n"(nthreads) : "memory")
+#define RB2_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 // device-side error codes (Ctl::err)
 enum { RB2_ERR_NONE = 0, RB2_ERR_POOL = 1, RB2_ERR_RUN8 = 2, RB2_ERR_STAGE = 4, RB2_ERR_ORDER = 8, RB2_ERR_PIECES = 16 };
 

@@ -1310,7 +1310,7 @@ __device__ __forceinline__ T half_incl_scan(T v, int hl, uint32_t hmask)
 
 __global__ void __launch_bounds__(MERGE_WARPS * 32, HALF_MINCTA) k_merge_half(MergeArgs A)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
+	RB2_DYN_SMEM(smraw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
 	const uint32_t hmask = half ? 0xffff0000u : 0x0000ffffu;
 	const uint32_t w = (blockIdx.x * MERGE_WARPS + wid) * 2 + half;
@@ -1656,7 +1656,7 @@ __device__ __forceinline__ void item_prologue(const MergeArgs &A, ItemCtx &C, in
 __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(MergeArgs A)
 {
 	// persistent: warps pull the items k_merge_half deferred
-	extern __shared__ __align__(16) uint8_t smraw[];
+	RB2_DYN_SMEM(smraw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	FastSmem &S = reinterpret_cast<FastSmem*>(smraw)[wid];
 	const uint32_t nTodoA = A.ctl->nTodoA;
@@ -1688,7 +1688,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32, MERGE_MINCTA) k_merge_fast(M
 // Persistent kernel: warps pull queued items until the queue is empty.
 __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_general(MergeArgs A)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
+	RB2_DYN_SMEM(smraw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	GenSmem &S = reinterpret_cast<GenSmem*>(smraw)[wid];
 	const uint32_t nTodo = A.ctl->nTodo;
@@ -1881,7 +1881,7 @@ struct TraceT {
 static inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
 #define LAUNCH(e, kernel, grid, block, smem, ...) do { \
-	kernel<<<(grid), (block), (smem), (e)->st>>>(__VA_ARGS__); ++(e)->stats.n_launches; \
+	RB2_KERNEL_LAUNCH(kernel, (grid), (block), (smem), (e)->st, __VA_ARGS__); ++(e)->stats.n_launches; \
 	cudaError_t le_ = cudaGetLastError(); if (le_ != cudaSuccess) RB2_FATAL("launch of %s failed: %s", #kernel, cudaGetErrorString(le_)); } while (0)
 
 TraceT::TraceT(rb2_engine *e_, const char *n) : e(e_), name(n) { if (rb2_trace_on()) { cudaStreamSynchronize(e->st); t0 = std::chrono::steady_clock::now(); } }

@@ -231,7 +231,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		for (int c = st; c <= FT_NOC; c += 256 - NCNT) S.cntC[c] = 0;
 		if (st == 0) S.anyLong = 0;
 		if (st < FT_SUB * 6) (&S.recCnt[0][0])[st] = 0;
-		asm volatile("bar.sync 1, 96;" ::: "memory");
+		RB2_NAMED_BAR(1, 96);
 		if (st == 0 && nCarry) {
 			S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym);
 			atomicAdd(&S.cntC[0], 1u);
@@ -247,7 +247,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			atomicAdd(&S.cntC[key / FT_CH], 1u);
 			if (len > 1) S.anyLong = 1;
 		}
-		asm volatile("bar.sync 1, 96;" ::: "memory");
+		RB2_NAMED_BAR(1, 96);
 		if (wid == NCNT / 32) { // eight chunks per lane
 			uint32_t v[8], sum = 0;
 #pragma unroll
@@ -372,7 +372,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 // main kernel: one CTA per tile; tiles with more records than it stages go to the overflow list
 __global__ void __launch_bounds__(256, FT_MINCTA) k_flat_merge(FlatArgs A)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
+	RB2_DYN_SMEM(smraw);
 	FlatSmemT<FT_CAP_SMALL> &S = *reinterpret_cast<FlatSmemT<FT_CAP_SMALL>*>(smraw);
 	const TileDesc d0 = A.desc[blockIdx.x], d1 = A.desc[blockIdx.x + 1];
 	if (d1.r0 - d0.r0 + 1 > FT_CAP_SMALL) { // (+1: a run carried in from the left)
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256, FT_MINCTA) k_flat_merge(FlatArgs A)
 // overflow kernel (persistent): tiles where records are dense -- small indexes, first columns of an input-order batch
 __global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
 {
-	extern __shared__ __align__(16) uint8_t smraw[];
+	RB2_DYN_SMEM(smraw);
 	FlatSmemT<FT_OUT> &S = *reinterpret_cast<FlatSmemT<FT_OUT>*>(smraw);
 	const uint32_t n = A.ovf[0];
 	for (;;) {
