@@ -26,6 +26,57 @@
 #define RB2_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// ---- TMA (1-D bulk copies, cp.async.bulk) + mbarrier ------------------------------------------------
+// One elected thread arms the mbarrier with the byte count and issues the copy; whoever needs the
+// data waits on the barrier's phase parity.  Addresses and sizes are multiples of 16 bytes.
+#ifdef RB2_EMU
+static inline void rb2_emu_check16(const void *a, const void *b, uint32_t n) { if ((((uintptr_t)a | (uintptr_t)b | n) & 15) != 0) { fprintf(stderr, "[cuda_emu] bulk copy not 16-byte aligned\n"); abort(); } }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { rb2_emu_check16(dst, src, bytes); memcpy(dst, src, bytes); *bar += 1; }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { while (((uint32_t)*bar & 1u) == parity) rb2emu::yield(); }
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) { rb2_emu_check16(dst, src, bytes); memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_commit() {}
+__device__ __forceinline__ void bulk_wait_read() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ uint32_t warp_redux_add(uint32_t v) { return __reduce_add_sync(FULLMASK, v); }
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared; completes `bytes` transaction bytes on the mbarrier when the data has landed
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while (!ok);
+}
+// shared -> global (bulk group); the source must stay untouched until bulk_wait_read()
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (the bulk store that follows)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t warp_redux_add(uint32_t v) { return __reduce_add_sync(FULLMASK, v); }
+#endif
+
 // device-side error codes (Ctl::err)
 enum { RB2_ERR_NONE = 0, RB2_ERR_POOL = 1, RB2_ERR_RUN8 = 2, RB2_ERR_STAGE = 4, RB2_ERR_ORDER = 8, RB2_ERR_PIECES = 16 };
 

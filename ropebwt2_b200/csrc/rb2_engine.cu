@@ -1816,9 +1816,10 @@ enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, P
 // dense regime (rb2_flat.cuh): the BWT as a flat array of symbols for the duration of one batch
 struct FlatState {
 	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
-	DevBuf<uint8_t> s[2], bytes; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0, ovf; DevBuf<TileDesc> desc;
+	bool valid = false, blocksStale = false; // the array holds the current index (resident between dense batches) / the leaf blocks do not
+	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0, ovf; DevBuf<TileDesc> desc;
 	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
-	void release() { bytes.release(); for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
 };
 
 struct rb2_engine {
@@ -2000,6 +2001,8 @@ extern "C" int rb2_device_count(void)
 	return n;
 }
 
+static void ensure_blocks(rb2_engine *e);  // rb2_flat_host.inl: rebuild the leaf blocks from the resident flat array if they are stale
+static void blocks_edited(rb2_engine *e);  // ... and drop the array when the blocks change underneath it
 static void cluster_attach(rb2_engine *e, int device, int sorting_order);
 static void cluster_destroy(rb2_engine *e);
 static void cluster_reset(rb2_engine *e);
@@ -2059,6 +2062,7 @@ extern "C" void rb2_reset(rb2_engine_t *e)
 {
 	if (e->nChild) { cluster_reset(e); return; }
 	RB2_CUDA(cudaSetDevice(e->dev));
+	e->flat.valid = false; e->flat.blocksStale = false;
 	if (e->comm) { shard_reset_index(e); return; }
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
 	RB2_CUDA(cudaMemsetAsync(e->blkCnt, 0, 6 * 24, e->st));
@@ -2235,6 +2239,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	const bool flat = flat_choose(e, m, (uint64_t)len);
 	if (flat) { e->recPre.need(recCap + 1); flat_begin(e, (uint64_t)len); }
 	else {
+		ensure_blocks(e); blocks_edited(e); // a sparse batch edits the leaf blocks
 		// Reserve leaf blocks for the whole batch up front (2 bytes of pool per new symbol covers random
 		// data at B+-tree fill plus blocks retired by multi-item merges); more is added on demand.
 		reserve_blocks(e, (uint64_t)e->hctl->poolUsed + (uint64_t)len * 2 / RB2_FILL + 4096);
@@ -2339,12 +2344,10 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		G = h->Gnext; M = h->Mnext;
 		cs ^= 1;
 	}
-	if (flat) {
-		flat_end(e);
-		ph_collect(e, e->flat.pending); e->flat.pending = 0;
+	if (flat) { // the array stays resident; leaf blocks are rebuilt when something asks for them (ensure_blocks)
+		flat_finish(e);
 		++e->stats.flat_batches;
-	}
-	pull_totals(e);
+	} else pull_totals(e);
 	e->stats.n_strings += m;
 	e->stats.n_symbols += len;
 	e->stats.pool_blocks = e->hctl->poolUsed;
@@ -2417,6 +2420,7 @@ extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6],
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
 	if (x < 0 || x > total || y > total) RB2_FATAL("rank position out of range");
 	if (!cy) y = -1;
+	ensure_blocks(e);
 	LAUNCH(e, k_rank_query, 1, 32, 0, e->pool, e->dir[e->cur], e->nlog, x, y, e->dRankOut, e->dctl);
 	RB2_CUDA(cudaMemcpyAsync(e->hRankOut, e->dRankOut, 12 * 8, cudaMemcpyDeviceToHost, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
@@ -2429,6 +2433,7 @@ extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int
 	RB2_CUDA(cudaSetDevice(e->dev));
 	RB2_NO_CLUSTER(e, "rb2_rank_batch");
 	if (e->comm) RB2_FATAL("rb2_rank_batch: not available on a sharded engine yet");
+	ensure_blocks(e);
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
 	const int64_t CH = 1 << 20;
@@ -2449,6 +2454,8 @@ extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)
 {
 	if (bucket < 0 || bucket >= e->nb) RB2_FATAL("bucket out of range");
 	if (e->nChild) return cluster_num_blocks(e, bucket);
+	RB2_CUDA(cudaSetDevice(e->dev));
+	ensure_blocks(e);
 	return (int64_t)e->blkBkt[bucket + 1] - e->blkBkt[bucket];
 }
 
@@ -2476,6 +2483,7 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
 	if (n <= 0) return;
+	ensure_blocks(e); blocks_edited(e);
 	// the bucket's blocks are [blkBkt[b], blkBkt[b+1]); new blocks are inserted at its right end.
 	// An initially empty bucket consists of one empty block, which is replaced.
 	const uint32_t used = e->hctl->poolUsed;
@@ -2554,6 +2562,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5 || a < 0 || a > 5 || rl <= 0) RB2_FATAL("rb2_insert_run: bad argument");
 	if (x < 0 || x > e->bktLen[bucket]) RB2_FATAL("rb2_insert_run: position out of range");
+	ensure_blocks(e); blocks_edited(e);
 	const uint32_t k = (uint32_t)((rl + RB2_MAXRUN - 1) / RB2_MAXRUN);
 	e->recP.need(k); e->recSC.need(k); e->recDst.need(k);
 	std::vector<int64_t> P(k, bucket_start(e, bucket) + x);

@@ -2,10 +2,11 @@
 //
 // When a batch inserts into (nearly) every leaf block in every column -- short reads, the headline
 // workload: 100 M records per column into <= 20 M blocks -- updating run-length coded blocks record
-// by record is instruction bound (profiles/README.md).  For such a batch the engine keeps the BWT,
-// for the duration of the batch only, as ONE flat array of nt6 codes (4 bits per symbol, two per
-// byte, low nibble first; all six buckets concatenated) plus a directory of per-symbol counts in
-// front of every FT_DIR-th symbol, and one column becomes a single streaming pass (k_flat_merge):
+// by record is instruction bound (profiles/README.md).  For such batches the engine keeps the BWT as
+// ONE flat array of nt6 codes, 3 bits per symbol in BIT PLANES: the array is a sequence of cells of 32
+// symbols, a cell is three 32-bit words (bit 0, bit 1, bit 2 of the 32 codes; all six buckets
+// concatenated), plus a directory of per-symbol counts in front of every FT_DIR-th symbol.  One column
+// is a single streaming pass (k_flat_merge):
 //
 //   new[P_r + pre_r .. + c_r) = symbol of record r     (pre_r = members in front of record r, i.e. the
 //   old symbol i moves to i + #record symbols with P<=i  symbols this column inserts in front of it)
@@ -14,39 +15,62 @@
 // new symbols go in FRONT of the old symbol at the same position, mrope.c:206-218), and
 // rank(a, P_r) -- the return value of rope_insert_run / rle_insert_cached (rle.c:10-89) -- is
 // directory[P_r / FT_DIR][a] + a count over < FT_DIR + FT_OUT symbols held in shared memory.
-// Output-stationary: CTA t produces new[t*FT_OUT, (t+1)*FT_OUT) with aligned 128-bit stores; the old
-// symbols it needs are one contiguous range.  At the end of the batch the array is re-encoded into
-// leaf blocks of the reference's format (k_flat_encode), so everything outside the batch (iterator,
-// dump, rank queries, sparse batches) sees the usual block pool.
+// Why planes: counting a symbol over 32 codes is one AND/ANDN pair + one POPC (nibbles needed ~50
+// instructions), inserting a run at a bit position is shift/mask work on three words, and the array
+// is 25 % smaller than at 4 bits per symbol -- the kernel is bound by HBM, not by instruction issue.
+// Output-stationary: CTA t produces new[t*FT_OUT, (t+1)*FT_OUT): the old symbols it needs are one
+// contiguous range, fetched into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), and
+// the finished tile leaves through one TMA bulk store.  The array stays resident between batches; it
+// is re-encoded into leaf blocks of the reference's format (k_flat_encode) only when something needs
+// blocks (iterator, dump, rank queries, a sparse batch).
 #pragma once
 #include "rb2_codec.cuh"
 
-#define FT_OUT   8192  // output symbols per CTA of k_flat_merge: 256 threads x 32 symbols (16 bytes)
-#define FT_DIR   2048  // directory granularity (48 bytes of counts per 1024 bytes of symbols)
+#define FT_OUT   8192  // output symbols per CTA of k_flat_merge: 256 threads x one cell
+#define FT_DIR   2048  // directory granularity (48 bytes of counts per 768 bytes of symbols)
 #define FT_SUB   (FT_OUT / FT_DIR)
 #define FT_OLDMAX (FT_OUT + FT_DIR) // old symbols one CTA can need: from the directory tile of its first one
-#define FT_PAD   (FT_OLDMAX + 128)  // readable slack (symbols) behind a flat array
-#define FT_CH    32    // symbols per 16-byte chunk
+#define FT_PAD   (FT_OLDMAX + 256)  // readable / writable slack (symbols) behind a flat array
+#define FT_CH    32    // symbols per cell (three words)
 #define FE_CHUNK 64    // flat -> blocks: symbols encoded by one thread (<= 64 bytes of runs)
 #define FE_T     (RB2_FILL - FE_CHUNK + 1) // block k of a bucket takes the chunks that start in bytes [k*FE_T, (k+1)*FE_T)
 
-__host__ __device__ __forceinline__ uint64_t flat_bytes(uint64_t symbols) { return (symbols + 1) >> 1; }
-__device__ __forceinline__ uint32_t flat_get(const uint8_t *flat, uint64_t i) { return (flat[i >> 1] >> ((i & 1) * 4)) & 15u; }
-
-// ---- per-symbol counting without per-symbol compares ---------------------------------------------
-// nt6 codes: $=000 A=001 C=010 G=011 T=100 N=101 (bit 3 of a nibble is always 0).  For the eight
-// codes of a word, popcounts of
-//   m0 = bit0, m1 = bit1, m2 = bit2, m0&m1 (G), m0&m2 (N)
-// give N = s02, G = s01, A = s0 - s01 - s02, C = s1 - s01, T = s2 - s02, $ = n - (A+C+G+T+N).
-// "Raw" counts (s0, s1, s2, s01, s02, n) are linear, so prefix sums are taken on them and converted
-// only where a symbol count is needed.
-struct Raw6 { uint32_t s0, s1, s2, s01, s02, n; };
-
-__device__ __forceinline__ void raw_add_word(uint32_t x, uint32_t (&acc)[5])
+__host__ __device__ __forceinline__ uint64_t flat_bytes(uint64_t symbols) { return ((symbols + FT_CH - 1) / FT_CH) * 12; }
+__host__ __device__ __forceinline__ uint32_t flat_get(const uint8_t *flat, uint64_t i)
 {
-	const uint32_t m0 = x & 0x11111111u, m1 = (x >> 1) & 0x11111111u, m2 = (x >> 2) & 0x11111111u;
-	acc[0] += __popc(m0); acc[1] += __popc(m1); acc[2] += __popc(m2); acc[3] += __popc(m0 & m1); acc[4] += __popc(m0 & m2);
+	const uint32_t *w = reinterpret_cast<const uint32_t*>(flat) + (i >> 5) * 3; const uint32_t b = (uint32_t)(i & 31);
+	return ((w[0] >> b) & 1u) | ((w[1] >> b) & 1u) << 1 | ((w[2] >> b) & 1u) << 2;
 }
+
+// ---- per-symbol counting ----------------------------------------------------------------------------
+// nt6 codes: $=000 A=001 C=010 G=011 T=100 N=101 (110 and 111 never occur).  With the three planes
+// b0, b1, b2 of a cell the positions of a symbol are one or two bitwise operations (cell_match), and the
+// five popcounts s0 = |b0|, s1 = |b1|, s2 = |b2|, s01 = |b0&b1| (G), s02 = |b0&b2| (N) give all six
+// counts: A = s0 - s01 - s02, C = s1 - s01, T = s2 - s02, $ = n - (A+C+G+T+N).  These "raw" counts are
+// linear, so prefix sums are taken on them and converted only where a symbol count is needed.
+struct Raw6 { uint32_t s0, s1, s2, s01, s02, n; };
+struct Cell { uint32_t b0, b1, b2; };
+
+__device__ __forceinline__ Cell cell_load(const uint32_t *w) { Cell c = { w[0], w[1], w[2] }; return c; }
+__device__ __forceinline__ uint32_t cell_match(const Cell &c, uint32_t a)
+{
+	switch (a) {
+	case 0: return ~(c.b0 | c.b1 | c.b2);
+	case 1: return c.b0 & ~(c.b1 | c.b2);
+	case 2: return c.b1 & ~c.b0;
+	case 3: return c.b0 & c.b1;
+	case 4: return c.b2 & ~c.b0;
+	default: return c.b0 & c.b2;
+	}
+}
+// raw counts of the symbols selected by mask m (n = number of selected positions)
+__device__ __forceinline__ Raw6 raw_of_cell(const Cell &c, uint32_t m, uint32_t n)
+{
+	const uint32_t x0 = c.b0 & m, x1 = c.b1 & m, x2 = c.b2 & m;
+	Raw6 r = { (uint32_t)__popc(x0), (uint32_t)__popc(x1), (uint32_t)__popc(x2), (uint32_t)__popc(x0 & x1), (uint32_t)__popc(x0 & x2), n };
+	return r;
+}
+__device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? 0xffffffffu : (1u << n) - 1u; } // the n lowest bits, 0 <= n <= 32
 
 __device__ __forceinline__ uint32_t raw_symbol(const Raw6 &r, uint32_t a)
 {
@@ -60,29 +84,14 @@ __device__ __forceinline__ uint32_t raw_symbol(const Raw6 &r, uint32_t a)
 	default: return N;
 	}
 }
-
-// keep the first ns (0..32) symbols of a 16-byte chunk, zero the rest
-__device__ __forceinline__ void chunk_mask(uint32_t (&w)[4], uint32_t ns)
+__device__ __forceinline__ void raw_addto(Raw6 &a, const Raw6 &b) { a.s0 += b.s0; a.s1 += b.s1; a.s2 += b.s2; a.s01 += b.s01; a.s02 += b.s02; a.n += b.n; }
+// six raw counts as three words of two 16-bit fields (sums stay below 2^16 inside one tile)
+__device__ __forceinline__ void raw_pack16(const Raw6 &r, uint32_t (&p)[3]) { p[0] = r.s0 | r.s1 << 16; p[1] = r.s2 | r.s01 << 16; p[2] = r.s02 | r.n << 16; }
+__device__ __forceinline__ Raw6 raw_unpack16(uint32_t p0, uint32_t p1, uint32_t p2)
 {
-#pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		const uint32_t k = ns > (uint32_t)j * 8 ? ns - j * 8 : 0;
-		w[j] = k >= 8 ? w[j] : (k ? w[j] & ((1u << (k * 4)) - 1u) : 0u);
-	}
-}
-
-// raw counts of the first ns (0..32) symbols of a 16-byte chunk
-__device__ __forceinline__ Raw6 raw_count_chunk(const uint4 &v, uint32_t ns)
-{
-	uint32_t w[4] = { v.x, v.y, v.z, v.w };
-	if (ns < FT_CH) chunk_mask(w, ns);
-	uint32_t acc[5] = { 0, 0, 0, 0, 0 };
-#pragma unroll
-	for (int j = 0; j < 4; ++j) raw_add_word(w[j], acc);
-	Raw6 r = { acc[0], acc[1], acc[2], acc[3], acc[4], ns };
+	Raw6 r = { p0 & 0xffffu, p0 >> 16, p1 & 0xffffu, p1 >> 16, p2 & 0xffffu, p2 >> 16 };
 	return r;
 }
-__device__ __forceinline__ void raw_addto(Raw6 &a, const Raw6 &b) { a.s0 += b.s0; a.s1 += b.s1; a.s2 += b.s2; a.s01 += b.s01; a.s02 += b.s02; a.n += b.n; }
 
 // The records of a column.  In the all-singleton regime without interval sizes (the bulk of a short-read
 // batch) a record is fully described by the state arrays themselves -- position = the group's interval
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, const uint32_
 
 struct FlatArgs {
 	const uint8_t *oldS; const int64_t *oldDir;   // old array, counts in front of every FT_DIR-th old symbol
-	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its raw per-FT_DIR-tile symbol counts
+	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its per-FT_DIR-tile symbol counts
 	RecView V; const uint32_t *recDst; uint32_t R;
 	const TileDesc *desc;
 	uint32_t *ovf;           // [0] tiles left to k_flat_merge_dense, [1] its work counter, [2..] the tiles
@@ -141,51 +150,43 @@ struct FlatArgs {
 	const int64_t *recOff; int nb;
 };
 
-// six raw counts as three words of two 16-bit fields (sums stay below 2^16 inside one tile)
-__device__ __forceinline__ void raw_pack16(const uint32_t (&acc)[5], uint32_t n, uint32_t (&p)[3])
-{
-	p[0] = acc[0] | acc[1] << 16; p[1] = acc[2] | acc[3] << 16; p[2] = acc[4] | n << 16;
-}
-__device__ __forceinline__ Raw6 raw_unpack16(uint32_t p0, uint32_t p1, uint32_t p2)
-{
-	Raw6 r = { p0 & 0xffffu, p0 >> 16, p1 & 0xffffu, p1 >> 16, p2 & 0xffffu, p2 >> 16 };
-	return r;
-}
-
-#define FT_NCH (FT_OLDMAX / FT_CH + 2)   // 16-byte chunks of old symbols one tile can hold
-#define FT_NOC (FT_OUT / FT_CH)          // 32-symbol output chunks per tile = threads per CTA
+#define FT_NCH (FT_OLDMAX / FT_CH + 2)   // cells of old symbols one tile can hold (one more than it counts: funnel-shift partner)
+#define FT_OLDW ((FT_NCH * 3 + 3) & ~3)  // ... as words, a multiple of 16 bytes (TMA destination)
+#define FT_NOC (FT_OUT / FT_CH)          // output cells per tile = threads per CTA
+#define FT_TILEW (FT_NOC * 3)            // words of one output tile
 #define FT_CAP_SMALL 2047                // records per tile the main kernel stages (more: overflow kernel, same code)
 template <int CAP> struct FlatSmemT {
-	uint4    old4[FT_NCH];               // the old symbols this tile needs, from a directory tile boundary
-	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every 16-byte chunk of old4 (16-bit fields)
+	alignas(16) uint32_t old[FT_OLDW];   // the old symbols this tile needs, from a directory tile boundary (TMA bulk load)
+	alignas(16) uint32_t out[FT_TILEW];  // the finished tile (TMA bulk store)
+	alignas(8) uint64_t mbar;            // completion of the bulk load
+	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every cell of old (16-bit fields)
 	uint16_t sKey[CAP + 1];              // staged records: run start inside the tile
 	uint16_t sLS[CAP + 1];               // (run length inside the tile - 1) << 3 | symbol
-	uint32_t cntC[FT_NOC + 1];           // staged records that start in each 32-symbol output chunk
-	uint16_t k0C[FT_NOC + 2];            // ... and their exclusive prefix = the first record at or behind each chunk
-	uint32_t anyLong;                    // some staged record is longer than one symbol
+	uint16_t sPre[CAP + 1];              // record symbols of this tile in front of the record
+	uint32_t cntC[FT_NOC + 1];           // staged records that start in each output cell
+	uint16_t k0C[FT_NOC + 2];            // ... and their exclusive prefix = the first record at or behind each cell
 	uint32_t warpTot[8][3];
-	uint32_t recCnt[FT_SUB][6];          // symbols the records put into each FT_DIR sub-tile
-	uint32_t subX[FT_SUB + 1];           // old symbols (local index) in front of each sub-tile
+	uint32_t warpCnt[8][3];              // raw counts of the 32 output cells of each warp
 	uint32_t tile;                       // overflow kernel: the tile this CTA works on
 };
 
-// insert one symbol at nibble position pp (0..31) of a 32-symbol vector; the last symbol falls out
-__device__ __forceinline__ void insert_symbol(uint32_t (&ow)[4], uint32_t pp, uint32_t sy)
+// insert c copies (1 <= c, q + c <= 32) of symbol sy at bit position q of a cell; what is pushed past bit 31 falls out
+__device__ __forceinline__ void cell_insert(Cell &x, uint32_t q, uint32_t c, uint32_t sy)
 {
-	const uint32_t pw = pp >> 3, pb = (pp & 7) * 4;
-	const uint32_t w1[4] = { ow[0] << 4, __funnelshift_l(ow[0], ow[1], 4), __funnelshift_l(ow[1], ow[2], 4), __funnelshift_l(ow[2], ow[3], 4) };
-	const uint32_t lowMask = (1u << pb) - 1u;     // symbols in front of pp inside its word
-#pragma unroll
-	for (int w = 0; w < 4; ++w) {
-		const uint32_t mid = (ow[w] & lowMask) | (sy << pb) | (w1[w] & ~((lowMask << 4) | 0xfu));
-		ow[w] = (uint32_t)w < pw ? ow[w] : ((uint32_t)w > pw ? w1[w] : mid);
-	}
+	const uint32_t low = (1u << q) - 1u;                 // q <= 31
+	const uint32_t fill = low_mask(c) << q;
+	const uint32_t sh = c & 31u;                          // c == 32 only with q == 0: everything is replaced
+	const uint32_t keepHi = c >= 32 ? 0u : 0xffffffffu;
+	x.b0 = (x.b0 & low) | (((x.b0 & ~low) << sh) & keepHi) | ((sy & 1u) ? fill : 0u);
+	x.b1 = (x.b1 & low) | (((x.b1 & ~low) << sh) & keepHi) | ((sy & 2u) ? fill : 0u);
+	x.b2 = (x.b2 & low) | (((x.b2 & ~low) << sh) & keepHi) | ((sy & 4u) ? fill : 0u);
 }
 
-// One output tile.  Two barriers: (A) old symbols + their counts | records -> shared memory, (B) every
-// thread assembles its 32 output symbols, (C) ranks of the tile's records | symbol counts of its sub-tiles.
+// One output tile.  (A) TMA bulk load of the old symbols, their counts per cell | records -> shared memory,
+// (B) every thread assembles one output cell, (C) TMA bulk store | ranks of the tile's records | symbol
+// counts of its sub-tiles.  `parity`: phase of S.mbar this call waits for (S.mbar is initialised by the caller).
 template <int CAP>
-__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP> &S, const uint32_t tile, const TileDesc d0, const TileDesc d1)
+__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP> &S, const uint32_t tile, const TileDesc d0, const TileDesc d1, const uint32_t parity)
 {
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const uint64_t o0 = (uint64_t)tile * FT_OUT;
@@ -197,24 +198,27 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	const uint32_t loadLen = (uint32_t)(d1.i0 - a0), skip = (uint32_t)(i0 - a0);
 	const uint32_t recIn = tileLen - (loadLen - skip); // record symbols inside the tile
 	const uint64_t before = o0 - i0;               // record symbols in front of the tile
-	const uint32_t nLoad = loadLen / FT_CH + 2;    // chunks that are read (<= FT_NCH)
+	const uint32_t nLoad = loadLen / FT_CH + 2;    // cells that are read (<= FT_NCH); the last one only as a funnel-shift partner
 	const uint32_t nCarry = carryLen ? 1u : 0u, nS = nCarry + (r1 - r0);
-	constexpr int NCNT = 160;                      // threads (5 warps) that load + count; the other 3 warps stage records
+	constexpr int NCNT = 160;                      // threads (5 warps) that count; the other 3 warps stage records
 
-	// ---- phase A: old symbols -> shared memory + raw counts per chunk pair | records -> shared memory -------
+	// ---- phase A: old symbols -> shared memory (TMA) + raw counts per cell pair | records -> shared memory -----
+	if (tid == 0) {
+		const uint32_t bytes = (nLoad * 12u + 15u) & ~15u;
+		mbar_expect_tx(&S.mbar, bytes);
+		bulk_g2s(S.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.mbar);
+	}
 	uint32_t p[3] = { 0, 0, 0 }, q[3] = { 0, 0, 0 }, inc[3] = { 0, 0, 0 };
 	if (tid < NCNT) {
-		// thread j owns chunks 2j, 2j+1 (symbols behind loadLen are whatever follows in the array: the
+		// thread j owns cells 2j, 2j+1 (symbols behind loadLen are whatever follows in the array: the
 		// prefixes that include them are never used)
-		const uint4 *src = reinterpret_cast<const uint4*>(A.oldS + (a0 >> 1));
+		mbar_wait(&S.mbar, parity);
 		if ((uint32_t)tid * 2 < nLoad) {
-			const uint4 x = src[tid * 2], y = src[tid * 2 + 1];
-			S.old4[tid * 2] = x; S.old4[tid * 2 + 1] = y;
-			uint32_t acc[5] = { 0, 0, 0, 0, 0 };
-			raw_add_word(x.x, acc); raw_add_word(x.y, acc); raw_add_word(x.z, acc); raw_add_word(x.w, acc);
-			raw_pack16(acc, FT_CH, q);
-			raw_add_word(y.x, acc); raw_add_word(y.y, acc); raw_add_word(y.z, acc); raw_add_word(y.w, acc);
-			raw_pack16(acc, 2 * FT_CH, p);
+			const Cell x = cell_load(S.old + tid * 6), y = cell_load(S.old + tid * 6 + 3);
+			Raw6 r = raw_of_cell(x, 0xffffffffu, FT_CH);
+			raw_pack16(r, q);
+			raw_addto(r, raw_of_cell(y, 0xffffffffu, FT_CH));
+			raw_pack16(r, p);
 		}
 #pragma unroll
 		for (int k = 0; k < 3; ++k) inc[k] = p[k];
@@ -225,17 +229,14 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		}
 		if (lane == 31) { S.warpTot[wid][0] = inc[0]; S.warpTot[wid][1] = inc[1]; S.warpTot[wid][2] = inc[2]; }
 	} else {
-		// the three staging warps also index the records by output chunk (they would otherwise wait for the
-		// counting warps): histogram of chunk ids, then one warp scans it.  Barrier 1 is private to them.
+		// the three staging warps also index the records by output cell: histogram of cell ids, then one
+		// warp scans it.  Barrier 1 is private to them.
 		const int st = tid - NCNT;
 		for (int c = st; c <= FT_NOC; c += 256 - NCNT) S.cntC[c] = 0;
-		if (st == 0) S.anyLong = 0;
-		if (st < FT_SUB * 6) (&S.recCnt[0][0])[st] = 0;
 		RB2_NAMED_BAR(1, 96);
 		if (st == 0 && nCarry) {
-			S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym);
+			S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym); S.sPre[0] = 0;
 			atomicAdd(&S.cntC[0], 1u);
-			if (carryLen > 1) S.anyLong = 1;
 		}
 		for (uint32_t k = st; k < r1 - r0; k += 256 - NCNT) {
 			const uint32_t r = r0 + k;
@@ -244,11 +245,11 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
 			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
+			S.sPre[nCarry + k] = (uint16_t)(pre - (uint32_t)before);
 			atomicAdd(&S.cntC[key / FT_CH], 1u);
-			if (len > 1) S.anyLong = 1;
 		}
 		RB2_NAMED_BAR(1, 96);
-		if (wid == NCNT / 32) { // eight chunks per lane
+		if (wid == NCNT / 32) { // eight cells per lane
 			uint32_t v[8], sum = 0;
 #pragma unroll
 			for (int i = 0; i < 8; ++i) { v[i] = S.cntC[lane * 8 + i]; sum += v[i]; }
@@ -259,7 +260,8 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		}
 	}
 	__syncthreads();
-	// ---- phase B: prefix in front of every chunk (needed behind the next barrier) ------------------------
+	if (tid >= NCNT) mbar_wait(&S.mbar, parity); // (complete by now: every thread that reads S.old has observed the phase itself)
+	// prefix in front of every cell (needed behind the next barrier)
 	if (tid < NCNT && (uint32_t)tid * 2 < nLoad) {
 		uint32_t base[3] = { 0, 0, 0 };
 		for (int w = 0; w < wid; ++w) { base[0] += S.warpTot[w][0]; base[1] += S.warpTot[w][1]; base[2] += S.warpTot[w][2]; }
@@ -269,101 +271,70 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			S.chunkPre[tid * 2][k] = ex; S.chunkPre[tid * 2 + 1][k] = ex + q[k];
 		}
 	}
-	// ---- phase B: assemble 32 output symbols per thread ------------------------------------------------
-	// record symbols of this tile in front of staged entry k (the carried run counts from the tile start)
-	auto pre_rel = [&](uint32_t k) -> uint32_t { return k < nCarry ? 0u : (k < nS ? (uint32_t)(A.V.Pre(r0 + k - nCarry) - before) : recIn); };
-	auto run_len = [&](uint32_t k) -> uint32_t { return ((uint32_t)S.sLS[k] >> 3) + 1; };
-	const uint32_t rel = tid * FT_CH;
-	uint32_t k0;                        // first entry with sKey >= rel
-	k0 = S.k0C[tid];                    // (a bisection over sKey costs 70 instructions per warp; a proportional guess + walk twice that)
-	const uint32_t kEnd = S.k0C[tid + 1]; // one past the last entry that starts in this chunk
-	uint32_t runRem = 0, runSym = 0, oldIdx;
-	if (k0 > 0 && (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) > rel) { // inside the run of entry k0-1
-		runRem = (uint32_t)S.sKey[k0 - 1] + run_len(k0 - 1) - rel; runSym = S.sLS[k0 - 1] & 7u;
-		oldIdx = (uint32_t)S.sKey[k0 - 1] - pre_rel(k0 - 1) + skip;
-	} else oldIdx = rel - pre_rel(k0) + skip;
-	if ((tid & (FT_DIR / FT_CH - 1)) == 0) S.subX[tid / (FT_DIR / FT_CH)] = oldIdx < loadLen ? oldIdx : loadLen;
-	if (tid == 0) S.subX[FT_SUB] = loadLen;
-	const uint32_t sbMine = rel / FT_DIR;          // the sub-tile this chunk lies in
-	uint32_t ow[4];
+	// ---- phase B: one output cell per thread ------------------------------------------------------------
 	{
-		// 32 old symbols from oldIdx on (unaligned)
-		const uint32_t *wp = reinterpret_cast<const uint32_t*>(S.old4) + (oldIdx >> 3);
-		const uint32_t sh = (oldIdx & 7) * 4;
-		const uint32_t x0 = wp[0], x1 = wp[1], x2 = wp[2], x3 = wp[3], x4 = wp[4];
-		ow[0] = __funnelshift_r(x0, x1, sh); ow[1] = __funnelshift_r(x1, x2, sh); ow[2] = __funnelshift_r(x2, x3, sh); ow[3] = __funnelshift_r(x3, x4, sh);
-	}
-	if (runRem >= FT_CH) {                          // inside one long run
-		ow[0] = ow[1] = ow[2] = ow[3] = runSym * 0x11111111u;
-		atomicAdd(&S.recCnt[sbMine][runSym], FT_CH);
-	} else if (runRem || kEnd > k0) {               // records start (or a run ends) inside these 32 symbols
-		// are all of them single symbols?  (the rule late in a batch: then no record of the tile is longer)
-		uint32_t k = kEnd; bool single = runRem == 0;
-		if (single && S.anyLong) { k = k0; while (single && k < kEnd) { single = ((uint32_t)S.sLS[k] >> 3) == 0; ++k; } }
-		if (single) {
-			for (uint32_t j = k0; j < k; ++j) {
-				const uint32_t sy = S.sLS[j] & 7u;
-				insert_symbol(ow, (uint32_t)S.sKey[j] - rel, sy);
-				atomicAdd(&S.recCnt[sbMine][sy], 1u);
-			}
-		} else {
-			typedef unsigned __int128 u128;
-			auto fill = [](uint32_t sy) -> u128 { const uint64_t f = 0x1111111111111111ull * sy; return ((u128)f << 64) | f; };
-			u128 O = ((u128)(((uint64_t)ow[3] << 32) | ow[2]) << 64) | (((uint64_t)ow[1] << 32) | ow[0]); // nibble 0 = next old symbol
-			u128 R = 0;
-			uint32_t pos = 0;
-			k = k0;
-			if (runRem) { R = fill(runSym) & ((((u128)1) << (4 * runRem)) - 1); pos = runRem; atomicAdd(&S.recCnt[sbMine][runSym], runRem); }
-			while (pos < FT_CH) {
-				uint32_t nk = k < nS ? (uint32_t)S.sKey[k] - rel : (uint32_t)FT_CH;
-				if (nk > FT_CH) nk = FT_CH;
-				const uint32_t cnt = nk - pos;            // old symbols in front of the next record (< 32 here)
-				if (cnt) { R |= (O & ((((u128)1) << (4 * cnt)) - 1)) << (4 * pos); O >>= 4 * cnt; pos = nk; }
-				if (pos >= FT_CH) break;
-				uint32_t len = run_len(k); const uint32_t sy = S.sLS[k] & 7u;
-				if (len > FT_CH - pos) len = FT_CH - pos;
-				atomicAdd(&S.recCnt[sbMine][sy], len);
-				if (len == FT_CH) { R = fill(sy); break; }
-				R |= (fill(sy) & ((((u128)1) << (4 * len)) - 1)) << (4 * pos);
-				pos += len; ++k;
-			}
-			ow[0] = (uint32_t)R; ow[1] = (uint32_t)(R >> 32); ow[2] = (uint32_t)(R >> 64); ow[3] = (uint32_t)(R >> 96);
+		const uint32_t rel = tid * FT_CH;
+		const uint32_t k0 = S.k0C[tid], kEnd = S.k0C[tid + 1]; // staged records that start in this cell
+		uint32_t runRem = 0, runSym = 0, oldIdx;
+		if (k0 > 0) { // inside the run of entry k0-1 ?
+			const uint32_t e = k0 - 1, end = (uint32_t)S.sKey[e] + ((uint32_t)S.sLS[e] >> 3) + 1;
+			if (end > rel) { runRem = end - rel; runSym = S.sLS[e] & 7u; oldIdx = (uint32_t)S.sKey[e] - S.sPre[e] + skip; }
 		}
+		if (!runRem) oldIdx = rel - (k0 < nS ? (uint32_t)S.sPre[k0] : recIn) + skip;
+		Cell x;
+		{ // 32 old symbols from oldIdx on (unaligned)
+			const uint32_t *wp = S.old + (oldIdx >> 5) * 3; const uint32_t sh = oldIdx & 31;
+			x.b0 = __funnelshift_r(wp[0], wp[3], sh); x.b1 = __funnelshift_r(wp[1], wp[4], sh); x.b2 = __funnelshift_r(wp[2], wp[5], sh);
+		}
+		if (runRem) cell_insert(x, 0, runRem < FT_CH ? runRem : FT_CH, runSym);
+		for (uint32_t k = k0; k < kEnd; ++k) {
+			const uint32_t qq = (uint32_t)S.sKey[k] - rel, len = ((uint32_t)S.sLS[k] >> 3) + 1;
+			cell_insert(x, qq, len < FT_CH - qq ? len : FT_CH - qq, S.sLS[k] & 7u);
+		}
+		// symbols behind the end of the array (last tile) are zero
+		const uint32_t nv = rel >= tileLen ? 0u : (tileLen - rel < FT_CH ? tileLen - rel : FT_CH);
+		const uint32_t vm = low_mask(nv);
+		x.b0 &= vm; x.b1 &= vm; x.b2 &= vm;
+		S.out[tid * 3] = x.b0; S.out[tid * 3 + 1] = x.b1; S.out[tid * 3 + 2] = x.b2;
+		fence_proxy_async();
+		// raw counts of the warp's 32 output cells (two warps = one FT_DIR sub-tile)
+		uint32_t pk[3];
+		raw_pack16(raw_of_cell(x, vm, nv), pk);
+#pragma unroll
+		for (int k = 0; k < 3; ++k) pk[k] = warp_redux_add(pk[k]);
+		if (lane == 0) { S.warpCnt[wid][0] = pk[0]; S.warpCnt[wid][1] = pk[1]; S.warpCnt[wid][2] = pk[2]; }
 	}
-	// symbols behind the end of the array (last tile) are zero
-	if (rel + FT_CH > tileLen) chunk_mask(ow, rel >= tileLen ? 0u : tileLen - rel);
-	reinterpret_cast<uint4*>(A.newS + (o0 >> 1))[tid] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 	__syncthreads();
-	// raw counts in front of local old index x
-	auto prefix_at = [&](uint32_t x) -> Raw6 {
-		const uint32_t c = x / FT_CH;
-		Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
-		if (x & (FT_CH - 1)) raw_addto(rr, raw_count_chunk(S.old4[c], x & (FT_CH - 1)));
-		return rr;
-	};
-	// ---- phase C: symbol counts of the four FT_DIR sub-tiles = old symbols in them + record symbols (warp 0) ----
-	if (tid < FT_SUB * 6) {
-		const uint32_t sb = (uint32_t)tid / 6u, f = (uint32_t)tid % 6u;
+	// ---- phase C: the tile leaves through one bulk store ------------------------------------------------
+	if (tid == 0) { bulk_s2g(A.newS + (uint64_t)tile * (FT_TILEW * 4), S.out, FT_TILEW * 4); bulk_commit(); }
+	// symbol counts of the four FT_DIR sub-tiles (warp 1)
+	if (tid >= 32 && tid < 32 + FT_SUB * 6) {
+		const uint32_t sb = (uint32_t)(tid - 32) / 6u, f = (uint32_t)(tid - 32) % 6u;
 		const uint64_t dt = (uint64_t)tile * FT_SUB + sb;
 		if (dt * FT_DIR < A.nNew || dt == 0) {
-			const Raw6 lo = prefix_at(S.subX[sb]), hi = prefix_at(S.subX[sb + 1]);
-			A.newTileCnt[dt * 6 + f] = raw_symbol(hi, f) - raw_symbol(lo, f) + S.recCnt[sb][f];
+			const Raw6 r = raw_unpack16(S.warpCnt[2 * sb][0] + S.warpCnt[2 * sb + 1][0], S.warpCnt[2 * sb][1] + S.warpCnt[2 * sb + 1][1],
+			                            S.warpCnt[2 * sb][2] + S.warpCnt[2 * sb + 1][2]);
+			A.newTileCnt[dt * 6 + f] = raw_symbol(r, f);
 		}
 	}
-	// ---- phase C: rank(a, P) for the records that start in this tile (taken from the last warp downwards) ----
+	// rank(a, P) for the records that start in this tile (taken from the last warp downwards)
 	{
 		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
 		for (uint32_t k = 255 - tid; k < r1 - r0; k += 256) {
 			const uint32_t r = r0 + k, dst = A.recDst[r];
 			if (dst == NONE32) continue;
-			const uint32_t a = S.sLS[nCarry + k] & 7u;
-			const Raw6 rr = prefix_at((uint32_t)((uint64_t)A.V.P[r] - a0));
-			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a);
+			const uint32_t e = nCarry + k, a = S.sLS[e] & 7u;
+			const uint32_t xo = (uint32_t)S.sKey[e] - S.sPre[e] + skip; // old symbols of the load window in front of the record
+			const uint32_t c = xo / FT_CH;
+			const Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
+			const uint32_t part = __popc(cell_match(cell_load(S.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
+			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a) + part;
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
 				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r) * 7 + a];
 			A.gLNext[dst] = g;
 		}
 	}
+	if (tid == 0) bulk_wait_read(); // the store has read S.out: the caller may reuse (or release) the shared memory
 }
 
 #ifndef FT_MINCTA
@@ -379,7 +350,9 @@ __global__ void __launch_bounds__(256, FT_MINCTA) k_flat_merge(FlatArgs A)
 		if (threadIdx.x == 0) A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = blockIdx.x;
 		return;
 	}
-	flat_merge_tile<FT_CAP_SMALL>(A, S, blockIdx.x, d0, d1);
+	if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
+	__syncthreads();
+	flat_merge_tile<FT_CAP_SMALL>(A, S, blockIdx.x, d0, d1, 0u);
 }
 
 // overflow kernel (persistent): tiles where records are dense -- small indexes, first columns of an input-order batch
@@ -388,13 +361,16 @@ __global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
 	RB2_DYN_SMEM(smraw);
 	FlatSmemT<FT_OUT> &S = *reinterpret_cast<FlatSmemT<FT_OUT>*>(smraw);
 	const uint32_t n = A.ovf[0];
+	if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
+	uint32_t parity = 0;
 	for (;;) {
 		if (threadIdx.x == 0) S.tile = atomicAdd(&A.ovf[1], 1u);
 		__syncthreads();
-		const uint32_t q = S.tile;
-		if (q >= n) break;
-		const uint32_t tile = A.ovf[2 + q];
-		flat_merge_tile<FT_OUT>(A, S, tile, A.desc[tile], A.desc[tile + 1]);
+		const uint32_t qi = S.tile;
+		if (qi >= n) break;
+		const uint32_t tile = A.ovf[2 + qi];
+		flat_merge_tile<FT_OUT>(A, S, tile, A.desc[tile], A.desc[tile + 1], parity);
+		parity ^= 1u;
 		__syncthreads();
 	}
 }
@@ -418,15 +394,17 @@ struct FlatDirScan { // K=6 (int64): per-tile symbol counts -> counts in front o
 // per-tile symbol counts of a flat array (after blocks -> flat)
 __global__ void __launch_bounds__(256) k_flat_count_tiles(const uint8_t *flat, uint64_t n, uint32_t *tileCnt)
 {
-	// one warp per FT_DIR tile: 32 lanes x 2 chunks
+	// one warp per FT_DIR tile: 32 lanes x 2 cells
 	const int lane = threadIdx.x & 31;
 	const uint64_t tile = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
 	if (tile * FT_DIR >= n && tile != 0) return;
 	const uint64_t base = tile * FT_DIR + lane * 2 * FT_CH;
 	const uint32_t rem = base >= n ? 0u : (n - base < 2 * FT_CH ? (uint32_t)(n - base) : 2u * FT_CH);
-	const uint4 *src = reinterpret_cast<const uint4*>(flat + (base >> 1));
-	Raw6 s = raw_count_chunk(src[0], rem < FT_CH ? rem : FT_CH);
-	raw_addto(s, raw_count_chunk(src[1], rem > FT_CH ? rem - FT_CH : 0));
+	const uint32_t *src = reinterpret_cast<const uint32_t*>(flat) + (base / FT_CH) * 3;
+	const uint32_t n0 = rem < FT_CH ? rem : FT_CH, n1 = rem > FT_CH ? rem - FT_CH : 0;
+	Raw6 s = { 0, 0, 0, 0, 0, 0 };
+	if (n0) s = raw_of_cell(cell_load(src), low_mask(n0), n0);
+	if (n1) raw_addto(s, raw_of_cell(cell_load(src + 3), low_mask(n1), n1));
 	s.s0 = warp_sum(s.s0); s.s1 = warp_sum(s.s1); s.s2 = warp_sum(s.s2); s.s01 = warp_sum(s.s01); s.s02 = warp_sum(s.s02); s.n = warp_sum(s.n);
 	if (lane < 6) tileCnt[tile * 6 + lane] = raw_symbol(s, (uint32_t)lane);
 }
@@ -439,9 +417,10 @@ __device__ __forceinline__ void flat_rank6(const uint8_t *flat, const int64_t *d
 	const uint32_t rem = part > (uint32_t)lane * 2 * FT_CH ? (part - lane * 2 * FT_CH < 2 * FT_CH ? part - lane * 2 * FT_CH : 2u * FT_CH) : 0u;
 	Raw6 s = { 0, 0, 0, 0, 0, 0 };
 	if (rem) {
-		const uint4 *src = reinterpret_cast<const uint4*>(flat + ((t * FT_DIR + lane * 2 * FT_CH) >> 1));
-		s = raw_count_chunk(src[0], rem < FT_CH ? rem : FT_CH);
-		raw_addto(s, raw_count_chunk(src[1], rem > FT_CH ? rem - FT_CH : 0));
+		const uint32_t *src = reinterpret_cast<const uint32_t*>(flat) + ((t * FT_DIR + lane * 2 * FT_CH) / FT_CH) * 3;
+		const uint32_t n0 = rem < FT_CH ? rem : FT_CH, n1 = rem > FT_CH ? rem - FT_CH : 0;
+		s = raw_of_cell(cell_load(src), low_mask(n0), n0);
+		if (n1) raw_addto(s, raw_of_cell(cell_load(src + 3), low_mask(n1), n1));
 	}
 	s.s0 = warp_sum(s.s0); s.s1 = warp_sum(s.s1); s.s2 = warp_sum(s.s2); s.s01 = warp_sum(s.s01); s.s02 = warp_sum(s.s02); s.n = warp_sum(s.n);
 #pragma unroll
@@ -449,7 +428,11 @@ __device__ __forceinline__ void flat_rank6(const uint8_t *flat, const int64_t *d
 }
 
 // sizes6[g][a] = #a in [gL, gL+gSize) for every group with a non-empty interval (rope_rank2a, mrope.c:202).
+// Short intervals (the rule: an interval holds the suffixes that share the string's suffix read so far,
+// at most the coverage of the data after the first columns) are counted directly by the owning thread;
+// long ones by the whole warp from the directory.
 // posOff: sharded engines pass whole-index positions; bucket b's local position = position - posOff[b*7+6].
+#define FT_SHORT_IV 128
 __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, const int64_t *dir, uint32_t G, const int64_t *gL, const int64_t *gSize,
                                                           int64_t *sizes6, const Ctl *ctl, const int64_t *posOff, int nb)
 {
@@ -459,7 +442,21 @@ __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, c
 	const uint32_t g = g0 + lane;
 	int64_t myL = g < G ? gL[g] : 0; const int64_t mySz = g < G ? gSize[g] : 0;
 	if (posOff && g < G && mySz > 0) myL -= posOff[bucket_of(ctl->gBkt, (uint32_t)nb, g) * 7 + 6];
-	uint32_t todo = __ballot_sync(FULLMASK, mySz > 0);
+	if (mySz > 0 && mySz <= FT_SHORT_IV) {
+		uint32_t c[6] = { 0, 0, 0, 0, 0, 0 };
+		uint64_t p = (uint64_t)myL; const uint64_t end = p + (uint64_t)mySz;
+		while (p < end) {
+			const uint32_t lo = (uint32_t)(p & (FT_CH - 1));
+			const uint32_t n = end - p < FT_CH - lo ? (uint32_t)(end - p) : FT_CH - lo;
+			const Raw6 r = raw_of_cell(cell_load(reinterpret_cast<const uint32_t*>(flat) + (p / FT_CH) * 3), low_mask(n) << lo, n);
+#pragma unroll
+			for (int a = 0; a < 6; ++a) c[a] += raw_symbol(r, (uint32_t)a);
+			p += n;
+		}
+#pragma unroll
+		for (int a = 0; a < 6; ++a) sizes6[(size_t)g * 6 + a] = c[a];
+	}
+	uint32_t todo = __ballot_sync(FULLMASK, mySz > FT_SHORT_IV);
 	while (todo) {
 		const int src = __ffs(todo) - 1; todo &= todo - 1;
 		const int64_t L = __shfl_sync(FULLMASK, myL, src), sz = __shfl_sync(FULLMASK, mySz, src);
@@ -475,10 +472,35 @@ __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, c
 	}
 }
 
+// per-bucket symbol totals of the array: out[k][a] = occ(a, pos[k]) for up to 64 positions (one warp each)
+__global__ void __launch_bounds__(32) k_flat_rank_at(const uint8_t *flat, const int64_t *dir, const int64_t *pos, int64_t *out)
+{
+	int64_t c[6];
+	flat_rank6(flat, dir, pos[blockIdx.x], threadIdx.x, c);
+	if (threadIdx.x < 6) {
+		int64_t v = 0;
+#pragma unroll
+		for (int a = 0; a < 6; ++a) if ((int)threadIdx.x == a) v = c[a];
+		out[blockIdx.x * 6 + threadIdx.x] = v;
+	}
+}
+
 // ---- leaf blocks -> flat --------------------------------------------------------------------------------
-// two steps: expand the runs to one byte per symbol (one warp per logical block: every lane expands the
-// runs that start in its 16 bytes), then pack two symbols per byte
+// One warp per logical block: every lane expands the runs that start in its 16 bytes straight into the
+// (zeroed) planes -- a run sets a bit range in the planes its symbol has a 1 in; the two end words of a
+// range may be shared with neighbouring runs (atomicOr), the words in between are owned by the run.
 // (sharded engines: off[b*7+6] = symbols of the whole index in front of bucket b that other ranks hold)
+__device__ __forceinline__ void plane_set_range(uint32_t *flatW, int plane, uint64_t s, uint32_t l)
+{
+	const uint64_t e = s + l; // bits [s, e)
+	uint64_t c = s / FT_CH; const uint64_t cl = (e - 1) / FT_CH;
+	const uint32_t lo = (uint32_t)(s & (FT_CH - 1));
+	if (c == cl) { atomicOr(flatW + c * 3 + plane, low_mask(l) << lo); return; }
+	atomicOr(flatW + c * 3 + plane, 0xffffffffu << lo);
+	for (++c; c < cl; ++c) flatW[c * 3 + plane] = 0xffffffffu;
+	atomicOr(flatW + cl * 3 + plane, low_mask((uint32_t)(e - cl * FT_CH)));
+}
+
 __global__ void __launch_bounds__(128) k_blocks_to_flat(const uint8_t *pool, const uint32_t *order, const int64_t *cumLen, uint32_t nlog,
                                                         const int64_t *off, const uint32_t *bkt, int nb, uint8_t *flat, Ctl *ctl)
 {
@@ -490,26 +512,21 @@ __global__ void __launch_bounds__(128) k_blocks_to_flat(const uint8_t *pool, con
 	LaneDec d; uint32_t basePos, baseCnt[6], blkLen, blkCnt[6], nbytes, err = 0; uint4 own;
 	warp_decode_block(pool + (size_t)order[i] * RB2_BLK, lane, sImg[wid], sCnt[wid], d, basePos, baseCnt, blkLen, blkCnt, nbytes, err, own);
 	const int64_t posBase = off ? off[bucket_of(bkt, (uint32_t)nb, i) * 7 + 6] : 0;
-	uint8_t *dst = flat + (cumLen[i] - posBase) + basePos;
+	uint64_t dst = (uint64_t)(cumLen[i] - posBase) + basePos;
+	uint32_t *flatW = reinterpret_cast<uint32_t*>(flat);
 	uint32_t bp = lane * 16 + d.fb;
 	for (uint32_t q = 0; q < d.nr; ++q) {
-		uint32_t l, s, nb;
-		parse_run(sImg[wid], bp, s, l, nb);
-		bp += nb;
-		for (uint32_t j = 0; j < l; ++j) dst[j] = (uint8_t)s;
+		uint32_t l, s, nbr;
+		parse_run(sImg[wid], bp, s, l, nbr);
+		bp += nbr;
+		if (l) {
+			if (s & 1u) plane_set_range(flatW, 0, dst, l);
+			if (s & 2u) plane_set_range(flatW, 1, dst, l);
+			if (s & 4u) plane_set_range(flatW, 2, dst, l);
+		}
 		dst += l;
 	}
 	if (err && lane == 0) atomicOr(&ctl->err, err);
-}
-
-__global__ void __launch_bounds__(256) k_pack_nibbles(const uint8_t *bytes, uint64_t n, uint8_t *flat)
-{
-	const uint64_t i = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 8; // 8 symbols -> one word
-	if (i >= n) return;
-	uint32_t w = 0;
-#pragma unroll
-	for (int j = 0; j < 8; ++j) if (i + j < n) w |= (uint32_t)(bytes[i + j] & 15u) << (4 * j);
-	reinterpret_cast<uint32_t*>(flat)[i >> 3] = w;
 }
 
 // ---- flat -> leaf blocks --------------------------------------------------------------------------------
@@ -525,16 +542,24 @@ __device__ __forceinline__ int enc_bucket_of_chunk(const EncTab &T, uint64_t c)
 	return b;
 }
 
-// the FE_CHUNK symbols that start at symbol s0, as eight words (low nibble first)
-__device__ __forceinline__ void load_chunk64(const uint8_t *flat, uint64_t s0, uint32_t (&w)[8])
+// the FE_CHUNK symbols that start at symbol s0, as three 64-bit planes; `starts` = the positions (< n)
+// where a run starts (position 0 and wherever a symbol differs from its predecessor)
+struct Chunk64 { uint64_t b0, b1, b2, starts; };
+__device__ __forceinline__ Chunk64 load_chunk64(const uint8_t *flat, uint64_t s0, uint32_t n)
 {
-	const uint32_t *wp = reinterpret_cast<const uint32_t*>(flat) + (s0 >> 3);
-	const uint32_t sh = (uint32_t)(s0 & 7) * 4;
-	uint32_t x[9];
+	const uint32_t *wp = reinterpret_cast<const uint32_t*>(flat) + (s0 / FT_CH) * 3;
+	const uint32_t sh = (uint32_t)(s0 & (FT_CH - 1));
+	uint64_t b[3];
 #pragma unroll
-	for (int j = 0; j < 9; ++j) x[j] = wp[j];
-#pragma unroll
-	for (int j = 0; j < 8; ++j) w[j] = __funnelshift_r(x[j], x[j + 1], sh);
+	for (int p = 0; p < 3; ++p) {
+		const uint32_t x0 = wp[p], x1 = wp[3 + p], x2 = wp[6 + p];
+		b[p] = (uint64_t)__funnelshift_r(x1, x2, sh) << 32 | __funnelshift_r(x0, x1, sh);
+	}
+	const uint64_t vm = n >= 64 ? ~0ull : (1ull << n) - 1ull;
+	Chunk64 c;
+	c.b0 = b[0] & vm; c.b1 = b[1] & vm; c.b2 = b[2] & vm;
+	c.starts = (((c.b0 ^ (c.b0 << 1)) | (c.b1 ^ (c.b1 << 1)) | (c.b2 ^ (c.b2 << 1))) | 1ull) & vm;
+	return c;
 }
 
 // bytes of the encoded chunk
@@ -545,17 +570,13 @@ __global__ void __launch_bounds__(256) k_flat_chunk_bytes(const uint8_t *flat, E
 	const int b = enc_bucket_of_chunk(T, c);
 	const uint64_t s0 = T.symStart[b] + (c - T.chunkStart[b]) * FE_CHUNK;
 	const uint32_t n = (uint32_t)(s0 + FE_CHUNK < T.symStart[b + 1] ? FE_CHUNK : T.symStart[b + 1] - s0);
-	uint32_t w[8];
-	load_chunk64(flat, s0, w);
-	uint32_t bytes = 0, prev = 8, len = 0;
+	const Chunk64 ch = load_chunk64(flat, s0, n);
+	// a run of 16 or more symbols takes two bytes: those are the starts followed by 15 non-starts
+	uint64_t ns = ~ch.starts, long15 = ns >> 1;
 #pragma unroll
-	for (int i = 0; i < FE_CHUNK; ++i) if ((uint32_t)i < n) {
-		const uint32_t sy = (w[i >> 3] >> ((i & 7) * 4)) & 15u;
-		if (sy != prev) { bytes += len == 0 ? 0 : (len < 16 ? 1 : 2); prev = sy; len = 0; }
-		++len;
-	}
-	bytes += len == 0 ? 0 : (len < 16 ? 1 : 2);
-	chunkBytes[c] = (uint8_t)bytes;
+	for (int k = 2; k <= 15; ++k) long15 &= ns >> k;   // bit i: positions i+1 .. i+15 are no starts
+	const uint64_t in15 = n >= 16 ? ((n - 15 >= 64 ? ~0ull : (1ull << (n - 15)) - 1ull)) : 0ull; // start i with i + 15 < n
+	chunkBytes[c] = (uint8_t)(__popcll(ch.starts) + __popcll(ch.starts & long15 & in15));
 }
 
 struct ChunkScan { // K=1 (uint64): exclusive prefix of the chunk sizes
@@ -588,35 +609,29 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 	uint8_t *img = sImg[wid * 4 + grp];
 	for (int j = gl; j < (RB2_BLK + 64) / 4; j += 8) reinterpret_cast<uint32_t*>(img)[j] = 0;
 	__syncwarp(gmask);
-	uint32_t acc[5] = { 0, 0, 0, 0, 0 }, nsym = 0;
+	Raw6 acc = { 0, 0, 0, 0, 0, 0 };
 	for (uint64_t c = c0 + gl; c < c1; c += 8) {
 		const uint64_t s0 = T.symStart[b] + (c - cLo) * FE_CHUNK;
 		const uint32_t n = (uint32_t)(s0 + FE_CHUNK < T.symStart[b + 1] ? FE_CHUNK : T.symStart[b + 1] - s0);
-		uint32_t w[8];
-		load_chunk64(flat, s0, w);
+		const Chunk64 ch = load_chunk64(flat, s0, n);
 		uint8_t *o = img + 2 + (uint32_t)(chunkPre[c] - b0);
-		uint32_t prev = 8, len = 0;
-#pragma unroll
-		for (int i = 0; i < FE_CHUNK; ++i) if ((uint32_t)i < n) {
-			const uint32_t sy = (w[i >> 3] >> ((i & 7) * 4)) & 15u;
-			if (sy != prev) { if (len) o += enc_run(o, prev, len); prev = sy; len = 0; }
-			++len;
+		uint64_t st = ch.starts;
+		while (st) { // run by run
+			const uint32_t i = (uint32_t)__ffsll((long long)st) - 1;
+			st &= st - 1;
+			const uint32_t nx = st ? (uint32_t)__ffsll((long long)st) - 1 : n;
+			const uint32_t sy = (uint32_t)((ch.b0 >> i) & 1ull) | (uint32_t)((ch.b1 >> i) & 1ull) << 1 | (uint32_t)((ch.b2 >> i) & 1ull) << 2;
+			o += enc_run(o, sy, nx - i);
 		}
-		if (len) o += enc_run(o, prev, len);
-		// symbol counts of the chunk (symbols behind n masked away)
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const uint32_t kv = n > (uint32_t)j * 8 ? n - j * 8 : 0;
-			raw_add_word(kv >= 8 ? w[j] : (kv ? w[j] & ((1u << (kv * 4)) - 1u) : 0u), acc);
-		}
-		nsym += n;
+		// symbol counts of the chunk
+		acc.s0 += __popcll(ch.b0); acc.s1 += __popcll(ch.b1); acc.s2 += __popcll(ch.b2);
+		acc.s01 += __popcll(ch.b0 & ch.b1); acc.s02 += __popcll(ch.b0 & ch.b2); acc.n += n;
 	}
 	// sums over the eight lanes of the group
 #pragma unroll
 	for (int o = 4; o > 0; o >>= 1) {
-#pragma unroll
-		for (int q = 0; q < 5; ++q) acc[q] += __shfl_xor_sync(gmask, acc[q], o);
-		nsym += __shfl_xor_sync(gmask, nsym, o);
+		acc.s0 += __shfl_xor_sync(gmask, acc.s0, o); acc.s1 += __shfl_xor_sync(gmask, acc.s1, o); acc.s2 += __shfl_xor_sync(gmask, acc.s2, o);
+		acc.s01 += __shfl_xor_sync(gmask, acc.s01, o); acc.s02 += __shfl_xor_sync(gmask, acc.s02, o); acc.n += __shfl_xor_sync(gmask, acc.n, o);
 	}
 	if (gl == 0) { img[0] = (uint8_t)(nbytes & 0xff); img[1] = (uint8_t)(nbytes >> 8); }
 	__syncwarp(gmask);
@@ -624,8 +639,5 @@ __global__ void __launch_bounds__(128) k_flat_encode(const uint8_t *flat, EncTab
 	const uint4 *src = reinterpret_cast<const uint4*>(img);
 #pragma unroll
 	for (int j = 0; j < 4; ++j) dst[j * 8 + gl] = src[j * 8 + gl];
-	if (gl < 6) {
-		const Raw6 r = { acc[0], acc[1], acc[2], acc[3], acc[4], nsym };
-		blkCnt[(size_t)k * 6 + gl] = raw_symbol(r, (uint32_t)gl);
-	}
+	if (gl < 6) blkCnt[(size_t)k * 6 + gl] = raw_symbol(acc, (uint32_t)gl);
 }

@@ -24,9 +24,10 @@ static uint64_t local_symbols(const rb2_engine *e)
 	return n;
 }
 
-// Dense or sparse?  One dense column streams the whole local array (~0.6 ps per symbol); one sparse
-// column costs ~0.22 ns per record (measured, profiles/README.md).  `strings` = records per column at
-// the start of the batch, `addLocal` = symbols this engine expects to receive.
+// Dense or sparse?  One dense column streams the whole local array (3 bits per symbol, read + written:
+// ~0.2 ps per symbol at the measured merge rate); one sparse column costs ~0.22 ns per record on an index that
+// sits in L2 and more on a large one (profiles/README.md).  `strings` = records per column at the start of
+// the batch, `addLocal` = symbols this engine expects to receive.  RB2_FLAT_RATIO overrides the crossover.
 static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
 {
 	const int pref = flat_pref();
@@ -34,11 +35,13 @@ static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
 	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
 	size_t freeB = 0, totB = 0;
 	RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-	const uint64_t have = e->flat.s[0].cap + e->flat.s[1].cap;
-	const uint64_t need = cap + cap / 8 + (cap * 5 / 4) + (n0 ? n0 : 0) + (64ull << 20); // two arrays (4 bits per symbol), directories, the re-encoded pool, expansion scratch
-	if (need > freeB + have + (uint64_t)e->poolCap * RB2_BLK) return false; // does not fit: block-wise updates need far less
+	const uint64_t have = e->flat.s[0].cap + e->flat.s[1].cap + (e->flat.dir[0].cap + e->flat.dir[1].cap) * 8;
+	const uint64_t need = 2 * flat_bytes(cap) + cap / 16 + (64ull << 20); // two arrays, their directories and tile tables
+	if (need > freeB + have) return false; // does not fit: block-wise updates need far less
 	if (pref == 1) return true;
-	return strings >= 65536 && (double)n0 + 0.5 * (double)addLocal < 256.0 * (double)strings;
+	static double ratio = -1;
+	if (ratio < 0) { const char *s = getenv("RB2_FLAT_RATIO"); ratio = s && *s ? atof(s) : 2048.0; }
+	return strings >= 65536 && (double)n0 + 0.5 * (double)addLocal < ratio * (double)strings;
 }
 
 static void flat_scan_dir(rb2_engine *e, int which, uint64_t n)
@@ -49,28 +52,52 @@ static void flat_scan_dir(rb2_engine *e, int which, uint64_t n)
 	run_scan<6, int64_t, FlatDirScan>(e, fs, nd, e->scanCta64, (int64_t*)0, e->midTmp64);
 }
 
-// leaf blocks -> flat array (start of a dense batch)
+// grow a buffer that holds live data (the current array / directory): allocate, copy, free
+template <typename T> static void grow_keep(rb2_engine *e, DevBuf<T> &b, size_t n, size_t live)
+{
+	if (n <= b.cap) return;
+	T *np; const size_t cap = n + n / 16 + 64;
+	RB2_CUDA(cudaMalloc(&np, cap * sizeof(T)));
+	if (b.p && live) RB2_CUDA(cudaMemcpyAsync(np, b.p, live * sizeof(T), cudaMemcpyDeviceToDevice, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	if (b.p) RB2_CUDA(cudaFree(b.p));
+	b.p = np; b.cap = cap;
+}
+
+// Start of a dense batch: the flat array either is resident from the previous dense batch (f.valid) and only
+// has to make room, or is built from the leaf blocks.
 static void flat_begin(rb2_engine *e, uint64_t addLocal)
 {
 	FlatState &f = e->flat;
 	ph_begin(e, PH_CONVERT);
 	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
-	for (int k = 0; k < 2; ++k) { f.s[k].need(flat_bytes(cap)); f.dir[k].need((cap / FT_DIR + 3) * 6); }
+	if (f.valid) {
+		if (f.n != n0) RB2_FATAL("internal: resident flat array holds %llu symbols, the index %llu", (unsigned long long)f.n, (unsigned long long)n0);
+		// the other buffer holds nothing live: release it first so that the peak is old + new current array
+		if (flat_bytes(cap) > f.s[f.cur ^ 1].cap) f.s[f.cur ^ 1].release();
+		grow_keep(e, f.s[f.cur], flat_bytes(cap), flat_bytes(n0 + FT_PAD) < f.s[f.cur].cap ? flat_bytes(n0 + FT_PAD) : f.s[f.cur].cap);
+		grow_keep(e, f.dir[f.cur], (cap / FT_DIR + 3) * 6, (n0 / FT_DIR + 2) * 6);
+	} else {
+		f.cur = 0;
+		f.s[0].need(flat_bytes(cap)); f.dir[0].need((cap / FT_DIR + 3) * 6);
+	}
+	f.s[f.cur ^ 1].need(flat_bytes(cap)); f.dir[f.cur ^ 1].need((cap / FT_DIR + 3) * 6);
 	f.tileCnt.need((cap / FT_DIR + 3) * 6);
 	f.tileR0.need(cap / FT_OUT + 4); f.desc.need(cap / FT_OUT + 4); f.ovf.need(cap / FT_OUT + 8);
-	f.cur = 0; f.n = n0;
-	if (n0 > 0) {
-		Dir &d = e->dir[e->cur];
-		f.bytes.need(n0 + 64);
-		LAUNCH(e, k_blocks_to_flat, cdiv(e->nlog, 4), 128, 0, e->pool, d.order, d.cumLen, e->nlog, e->comm ? e->dDirOff : (const int64_t*)0,
-		       e->dctl->blkBkt, e->nb, f.bytes.p, e->dctl);
-		LAUNCH(e, k_pack_nibbles, cdiv((n0 + 7) / 8, 256), 256, 0, f.bytes.p, n0, f.s[0].p);
-		LAUNCH(e, k_flat_count_tiles, cdiv((n0 + FT_DIR - 1) / FT_DIR, 8), 256, 0, f.s[0].p, n0, f.tileCnt.p);
-	} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 24, e->st));
-	flat_scan_dir(e, 0, n0);
+	if (!f.valid) {
+		f.n = n0;
+		if (n0 > 0) {
+			Dir &d = e->dir[e->cur];
+			RB2_CUDA(cudaMemsetAsync(f.s[0].p, 0, flat_bytes(n0 + FT_CH), e->st));
+			LAUNCH(e, k_blocks_to_flat, cdiv(e->nlog, 4), 128, 0, e->pool, d.order, d.cumLen, e->nlog, e->comm ? e->dDirOff : (const int64_t*)0,
+			       e->dctl->blkBkt, e->nb, f.s[0].p, e->dctl);
+			LAUNCH(e, k_flat_count_tiles, cdiv((n0 + FT_DIR - 1) / FT_DIR, 8), 256, 0, f.s[0].p, n0, f.tileCnt.p);
+		} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 24, e->st));
+		flat_scan_dir(e, 0, n0);
+	}
 	ph_end(e, PH_CONVERT);
 	f.pending |= 1u << PH_CONVERT;
-	f.on = true;
+	f.on = true; f.valid = true; f.blocksStale = true;
 }
 
 // one column: merge nrec records (inserting `inserted` symbols) into the flat array
@@ -97,14 +124,14 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	ph_end(e, PH_DIR);
 	++e->stats.n_merge_launches;
 	e->stats.merge_blocks += nTiles;
-	e->stats.merge_bytes_rw += (int64_t)(f.n + nNew) / 2 + (int64_t)nrec * (leanP ? 21 : 28); // old array read, new written (4 bits per symbol), records (20 B) read, ranks (8 B) written
+	e->stats.merge_bytes_rw += (int64_t)(flat_bytes(f.n) + flat_bytes(nNew)) + (int64_t)nrec * (leanP ? 21 : 28); // old array read, new written (3 bits per symbol), records (13 / 20 B) read, ranks (8 B) written
 	f.cur ^= 1; f.n = nNew;
 	f.pending |= (1u << PH_MERGE) | (1u << PH_DIR);
 	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096 && !leanP) { // developer aid: dump tiny arrays column by column
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		std::vector<uint8_t> hs(nNew); std::vector<int64_t> hp(nrec), hd(12); std::vector<uint32_t> hpre(nrec + 1), hsc(nrec), hdst(nrec);
 		{ std::vector<uint8_t> pk(flat_bytes(nNew)); RB2_CUDA(cudaMemcpy(pk.data(), f.s[f.cur].p, pk.size(), cudaMemcpyDeviceToHost));
-		  for (uint64_t i = 0; i < nNew; ++i) hs[i] = (pk[i >> 1] >> ((i & 1) * 4)) & 15; }
+		  for (uint64_t i = 0; i < nNew; ++i) hs[i] = (uint8_t)flat_get(pk.data(), i); }
 		RB2_CUDA(cudaMemcpy(hp.data(), e->recP.p, nrec * 8, cudaMemcpyDeviceToHost));
 		RB2_CUDA(cudaMemcpy(hpre.data(), e->recPre.p, (nrec + 1) * 4, cudaMemcpyDeviceToHost));
 		RB2_CUDA(cudaMemcpy(hsc.data(), e->recSC.p, nrec * 4, cudaMemcpyDeviceToHost));
@@ -124,8 +151,39 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	}
 }
 
-// flat array -> leaf blocks (end of a dense batch): buckets are encoded independently
-static void flat_end(rb2_engine *e)
+// End of a dense batch: the array stays resident (the leaf blocks are now stale); refresh the host
+// mirrors of the per-bucket symbol totals from the array's directory.
+static void flat_finish(rb2_engine *e)
+{
+	FlatState &f = e->flat;
+	if (f.pending) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, f.pending); f.pending = 0; }
+	f.on = false;
+	if (e->comm) return; // sharded engines keep their totals in gtot
+	int64_t hpos[8], hout[8 * 6];
+	int64_t acc = 0;
+	for (int b = 0; b <= 6; ++b) { hpos[b] = acc; if (b < 6) acc += e->bktLen[b]; }
+	if ((uint64_t)acc != f.n) RB2_FATAL("internal: flat array holds %llu symbols, the buckets %lld", (unsigned long long)f.n, (long long)acc);
+	e->stageCnt.need(8 + 8 * 6);
+	RB2_CUDA(cudaMemcpyAsync(e->stageCnt.p, hpos, 7 * 8, cudaMemcpyHostToDevice, e->st));
+	LAUNCH(e, k_flat_rank_at, 7, 32, 0, f.s[f.cur].p, f.dir[f.cur].p, e->stageCnt.p, e->stageCnt.p + 8);
+	RB2_CUDA(cudaMemcpyAsync(hout, e->stageCnt.p + 8, 7 * 6 * 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	for (int b = 0; b < 6; ++b) for (int a = 0; a < 6; ++a) e->tot[b][a] = hout[(b + 1) * 6 + a] - hout[b * 6 + a];
+}
+
+// batch scratch that can be rebuilt at any time (released when the conversion below is short of memory)
+static void release_batch_scratch(rb2_engine *e)
+{
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	e->sbuf.release(); e->T.release(); e->asym.release(); e->sizes6.release(); e->recP.release(); e->recSC.release(); e->recDst.release(); e->recPre.release();
+	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
+	e->strEnd.release(); e->tileA.release(); e->tileB.release(); e->grpCta.release();
+	FlatState &f = e->flat;
+	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.tileR0.release(); f.desc.release(); f.ovf.release();
+}
+
+// flat array -> leaf blocks: buckets are encoded independently
+static void flat_to_blocks(rb2_engine *e)
 {
 	FlatState &f = e->flat;
 	if (f.pending) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, f.pending); f.pending = 0; }
@@ -140,6 +198,11 @@ static void flat_end(rb2_engine *e)
 	T.symStart[e->nb] = sym; T.chunkStart[e->nb] = ch;
 	if (sym != f.n) RB2_FATAL("internal: flat array holds %llu symbols, the buckets %llu", (unsigned long long)f.n, (unsigned long long)sym);
 	const uint64_t nChunk = ch;
+	{ // the conversion needs ~9 bytes per chunk plus the pool: make room if the batch scratch is in the way
+		size_t freeB = 0, totB = 0;
+		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+		if ((nChunk + 2) * 9 + f.n + (1ull << 30) > freeB) release_batch_scratch(e);
+	}
 	f.chunkBytes.need(nChunk + 1); f.chunkPre.need(nChunk + 2);
 	std::vector<uint64_t> edge(2 * (size_t)e->nb, 0);
 	if (nChunk) {
@@ -152,6 +215,7 @@ static void flat_end(rb2_engine *e)
 		}
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 	}
+	f.chunkBytes.release();
 	uint32_t nBlocks = 0;
 	for (int b = 0; b < e->nb; ++b) {
 		T.blkStart[b] = nBlocks; T.byteStart[b] = edge[2 * b];
@@ -173,5 +237,17 @@ static void flat_end(rb2_engine *e)
 	ph_end(e, PH_CONVERT);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	ph_collect(e, 1u << PH_CONVERT);
-	f.on = false;
+	f.chunkPre.release();
+	f.blocksStale = false;
+	e->stats.pool_blocks = e->hctl->poolUsed;
+	e->stats.pool_capacity = e->poolCap;
 }
+
+// Everything that reads or edits leaf blocks (iterator, dump, rank queries, rope_insert_run, a sparse
+// batch, loading blocks) calls this first: after dense batches the blocks are rebuilt from the array.
+static void ensure_blocks(rb2_engine *e)
+{
+	if (e->flat.valid && e->flat.blocksStale) flat_to_blocks(e);
+}
+// ... and whatever edits the blocks invalidates the resident array
+static void blocks_edited(rb2_engine *e) { e->flat.valid = false; e->flat.blocksStale = false; }

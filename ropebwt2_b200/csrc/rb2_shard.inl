@@ -463,7 +463,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (flat) {
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		ph_collect(e, e->flat.pending); e->flat.pending = 0;
-		flat_end(e);
+		flat_finish(e); flat_to_blocks(e); // sharded engines re-encode at the end of every batch
+		e->flat.valid = false; e->flat.blocksStale = false;
 		++e->stats.flat_batches;
 	}
 	shard_publish_totals(e);
