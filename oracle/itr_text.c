@@ -111,3 +111,45 @@ int64_t blocks_text(const uint8_t *blocks, int64_t n_blocks, uint8_t *out, int64
 	}
 	return n <= cap? n : -n;
 }
+
+/*
+ * Streaming decode for indexes too large to hold as text (bench.py's md5 check of a 10 - 120 G-symbol
+ * index against the reference's md5): open, then read the text chunk by chunk.
+ */
+#include <stdlib.h>
+typedef struct { uint64_t itr_space[512]; itr_next_fn next; const uint8_t *q, *end; int c; int64_t rem; int done; } itr_stream_t;
+
+void *itr_stream_open(void *mr, itr_first_fn first, itr_next_fn next, int to_free)
+{
+	itr_stream_t *s = (itr_stream_t*)calloc(1, sizeof(itr_stream_t));
+	s->next = next;
+	first(mr, s->itr_space, to_free);
+	return s;
+}
+
+/* up to `cap` symbols into out (nt6 codes, or "$ACGTN" characters when ascii != 0); 0 at the end */
+int64_t itr_stream_read(void *s_, uint8_t *out, int64_t cap, int ascii)
+{
+	itr_stream_t *s = (itr_stream_t*)s_;
+	int64_t n = 0;
+	while (n < cap && !s->done) {
+		if (s->rem == 0) {
+			if (s->q == s->end) {
+				const uint8_t *blk = s->next(s->itr_space);
+				if (blk == 0) { s->done = 1; break; }
+				s->q = blk + 2; s->end = blk + 2 + *(const uint16_t*)blk;
+				continue;
+			}
+			s->q = dec_run(s->q, &s->c, &s->rem);
+			continue;
+		}
+		{
+			int64_t l = s->rem < cap - n? s->rem : cap - n;
+			memset(out + n, ascii? "$ACGTN"[s->c] : s->c, (size_t)l);
+			n += l; s->rem -= l;
+		}
+	}
+	return n;
+}
+
+void itr_stream_close(void *s) { free(s); }

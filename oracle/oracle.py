@@ -157,6 +157,31 @@ def decode_index(lib: C.CDLL, mr, total: int, to_free: int = 0, ascii: bool = Fa
     return out[:total], nb.value, nr.value
 
 
+def index_md5(lib: C.CDLL, mr, to_free: int = 0, chunk: int = 1 << 26):
+    """md5 of the text `ropebwt2 -LR...` would print for the index behind ``mr`` (main.c:308-323:
+    the BWT as "$ACGTN" characters + newline), streamed block by block through ``lib``'s own
+    iterator.  Returns (hex digest, number of symbols)."""
+    import hashlib
+    il = _itrlib()
+    il.itr_stream_open.restype = C.c_void_p
+    il.itr_stream_open.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    il.itr_stream_read.restype = C.c_int64
+    il.itr_stream_read.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+    il.itr_stream_close.argtypes = [C.c_void_p]
+    st = il.itr_stream_open(mr, C.cast(lib.mr_itr_first, C.c_void_p), C.cast(lib.mr_itr_next_block, C.c_void_p), to_free)
+    buf = np.empty(chunk, dtype=np.uint8)
+    h, total = hashlib.md5(), 0
+    while True:
+        n = il.itr_stream_read(st, buf.ctypes.data, chunk, 1)
+        if n <= 0:
+            break
+        h.update(memoryview(buf[:n]))
+        total += n
+    il.itr_stream_close(st)
+    h.update(b"\n")
+    return h.hexdigest(), total
+
+
 class RefLib:
     """The unmodified reference ``mrope.h`` API (``oracle/_ref/libref.so``)."""
 
