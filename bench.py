@@ -1,32 +1,40 @@
 #!/usr/bin/env python
 """bench.py -- Gbp/s inserted by the batched multi-string insertion path (mr_insert_multi).
 
-Workload (BASELINE.json configs[1]): 100 M x 101 bp synthetic uniform reads, forward strand,
-RLO (`ropebwt2 -LRs`), one batch into an empty index, on one B200.  A "step" is one
-mr_insert_multi call over that batch.  With N > 1 GPUs the ranks build ONE index of N x 100 M reads
-together (sharded build: 36 sub-buckets spread over the ranks, one count all-gather and one
-string-state exchange per column over NCCL): per-GPU work is fixed, so the
-scaling is "weak".  `--layout replicas` runs N independent indexes instead (no exchange).
+Workloads (BASELINE.json configs; seeded counter-based generators, ropebwt2_b200/synth.py):
 
-  value   device-resident input (rb2_insert_multi_dev), timed with CUDA events on the engine's
-          stream around the whole call, max over ranks
-  e2e     the reference-facing call (mr_insert_multi through the C-ABI) on a pinned HOST buffer:
-          H2D copy of the batch and D2H of the symbol counts inside the timed region
-  roofline  the dominant kernel (k_flat_merge in the dense regime this workload runs in): algorithmic
-          bytes per launch / its CUDA-event time, against the measured HBM copy bandwidth
-  cpu_baseline  the unmodified reference binary (oracle/_ref/ropebwt2 -LRs) on a bounded sample
+  --config cfg2 (default)  100 M x 101 bp uniform reads, forward strand, RLO (`ropebwt2 -LRs`), ONE batch
+                           into an empty index, one B200.  A "step" = one mr_insert_multi call over that
+                           batch.  With N > 1 GPUs the ranks build ONE index of N x 100 M reads together
+                           (sharded build): per-GPU work is fixed -> "weak" scaling.
+  --config cfg3            the north-star job: 1.2 B x 101 bp reads of a 30x genome, RLO, inserted the way
+                           the reference driver does it: 12 successive mr_insert_multi calls of
+                           102,110,743 reads (main.c:94,238-251) into ONE growing index.  A "step" = one of
+                           those calls; the line reports the whole job and every batch.
+  --config cfg4            1 M x 10 kbp uniform reads, input order (`-LR`), one batch (the long-read path).
 
-`--impl reference` times the reference's own CPU implementation (all the threads it can use:
-4 workers + master) on a bounded sample of the same workload.
+  value   device time of the hot path with the batch already resident in HBM (CUDA events on the engine's
+          stream around every call, max over ranks)
+  e2e     the reference-facing call (mr_insert_multi through the C-ABI) on a pinned HOST buffer: H2D copy
+          of the batch and D2H of the symbol counts inside the timed region
+  parity  after the timed region the index is decoded block by block through mr_itr_next_block and its
+          md5 compared with the md5 of the UNMODIFIED reference's output on the same reads
+          (tests/golden/ref_full_runs.json, recorded by tools/ref_full_run.py); a mismatch is fatal
+  roofline  the dominant kernel (k_flat_merge in the dense regime): algorithmic bytes per launch / its
+          CUDA-event time, against the measured HBM copy bandwidth
+  cpu_baseline  the unmodified reference binary (oracle/_ref/ropebwt2) on a bounded sample
+
+`--impl reference` times the reference's own CPU implementation (all the threads it can use: 4 workers +
+master) on the SAME workload, in full (cfg2: one run of ~6-13 minutes whatever --steps says).
 """
 import argparse
 import ctypes as C
 import json
 import os
+import socket
 import statistics
 import subprocess
 import sys
-import tempfile
 import threading
 import time
 
@@ -37,6 +45,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gbp/s inserted (101bp reads), bit-exact BWT"
 UNIT = "Gbp/s"
+REF_BATCH_BYTES = 10415295693  # the reference driver's default -m (main.c:94)
+FLAGS = {"cfg2": "-LRs", "cfg3": "-LRs", "cfg3u": "-LRs", "cfg4": "-LR"}
 
 
 def parse():
@@ -45,25 +55,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (BASELINE config 2: 100M)")
-    ap.add_argument("--length", type=int, default=101)
-    ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-reference sample (about 15 s of reference time)")
+    ap.add_argument("--config", default="cfg2", choices=sorted(FLAGS))
+    ap.add_argument("--reads", type=int, default=0, help="override the number of reads (per GPU for cfg2); default: the config's own")
+    ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="reads in the bounded CPU-reference sample of the b200 arm (about 15 s of reference time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the md5 check of the final index")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference: run a sample of this many reads instead of the full workload")
     ap.add_argument("--layout", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1: one index sharded over all GPUs (default) or one independent index per GPU")
     return ap.parse_args()
-
-
-def fill_batch(dst: np.ndarray, n: int, length: int, seed: int, chunk: int = 4_000_000) -> None:
-    """Write the mr_insert_multi buffer (reversed read + NUL per read, main.c:200-225) for `n`
-    seeded uniform reads into dst (n*(length+1) bytes), chunk by chunk to bound host memory."""
-    view = dst.reshape(n, length + 1)
-    for k, a in enumerate(range(0, n, chunk)):
-        b = min(n, a + chunk)
-        rng = np.random.default_rng([seed, k])
-        view[a:b, :length] = rng.integers(1, 5, size=(b - a, length), dtype=np.uint8)[:, ::-1]
-        view[a:b, length] = 0
 
 
 class ClockSampler(threading.Thread):
@@ -105,34 +105,31 @@ def ref_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference_sample(n: int, length: int, seed: int, path: str = None):
-    """One timed run of the unmodified reference binary on n seeded reads; returns (Gbp/s over the
-    reference's own hot-path timer (main.c:241,249), hot-path seconds, wall seconds)."""
-    from oracle import oracle as orc  # the checker; allowed only in this baseline leg
-    from ropebwt2_b200.synth import NT6
-    own = path is None
-    if own:
-        buf = np.empty(n * (length + 1), dtype=np.uint8)
-        fill_batch(buf, n, length, seed)
-        lines = buf.reshape(n, length + 1)[:, :length][:, ::-1]  # forward reads
-        txt = np.empty((n, length + 1), dtype=np.uint8)
-        txt[:, :length] = NT6[lines]
-        txt[:, length] = 10
-        f = tempfile.NamedTemporaryFile(suffix=".txt", delete=False)
-        f.write(txt.tobytes())
-        f.close()
-        path = f.name
-    t = time.time()
-    r = subprocess.run([ref_binary(), "-LRs", "-o", "/dev/null", path], capture_output=True, timeout=7200)
-    wall = time.time() - t
-    if r.returncode != 0:
-        raise RuntimeError(r.stderr.decode()[-300:])
-    hot = orc.ref_hot_path_seconds(r.stderr.decode())
-    if own:
-        os.unlink(path)
-    return n * length / hot / 1e9, hot, wall, path
+def workload_of(args, world: int = 1):
+    """(the workload all ranks build together, reads per rank, flags)."""
+    from ropebwt2_b200 import synth
+    w = synth.workload(args.config, 0)
+    per_rank = args.reads or w["n"]
+    if args.config == "cfg2":
+        w = synth.workload(args.config, per_rank * world)  # rank r inserts reads [r*per_rank, (r+1)*per_rank)
+    else:
+        w = synth.workload(args.config, per_rank)
+    return w, per_rank, FLAGS[args.config]
 
 
+def mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference binary on the box's host cores
+# ------------------------------------------------------------------------------------------------------
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -140,35 +137,142 @@ def reference_arm(args):
     if ref_binary() is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ropebwt2 was not prebuilt (needs /root/reference once)"}))
         return
-    n, L = args.cpu_reads, args.length
-    # write the sample once, time K runs after W warm-ups
-    buf = np.empty(n * (L + 1), dtype=np.uint8)
-    fill_batch(buf, n, L, args.seed)
-    from ropebwt2_b200.synth import NT6
-    txt = np.empty((n, L + 1), dtype=np.uint8)
-    txt[:, :L] = NT6[buf.reshape(n, L + 1)[:, :L][:, ::-1]]
-    txt[:, L] = 10
-    f = tempfile.NamedTemporaryFile(suffix=".txt", delete=False)
-    f.write(txt.tobytes())
-    f.close()
-    hots = []
-    for it in range(args.warmup + args.steps):
-        g, hot, wall, _ = run_reference_sample(n, L, args.seed, f.name)
-        if it >= args.warmup:
-            hots.append(hot)
-    os.unlink(f.name)
-    mean = sum(hots) / len(hots)
-    val = n * L / mean / 1e9
-    sample = f"{n} x {L} bp uniform reads (seed {args.seed}), ropebwt2 -LRs, hot-path timer main.c:241,249"
+    from oracle import oracle as orc  # the checker; allowed only in this baseline leg
+    from ropebwt2_b200 import synth
+    world = args.gpus
+    w, per_rank, flags = workload_of(args, 1)   # the reference runs the one-GPU workload whatever N is (it does not scale with N)
+    full_n = w["n"]
+    # memory: ~25 GB RSS for cfg2 (10.2 GB buffer + 4.8 GB string state + the B+-trees)
+    need_gb = 2.8e-7 * full_n if args.config != "cfg4" else 30.0
+    sample = args.ref_sample
+    note = ""
+    if not sample and (args.config in ("cfg3", "cfg3u") or mem_available_gb() < need_gb):
+        # cfg3 takes ~3-5 h on CPU: never inside a bench run.  Its recorded full run stands in (measured in the build container).
+        rec = orc.ref_recorded(w, flags)
+        if args.config in ("cfg3", "cfg3u") and rec:
+            val = rec["gbp_per_s_hot_path"]
+            print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": len(rec["hot_path_s_per_batch"]), "warmup": 0,
+                              "ms_per_step": rec["hot_path_s"] * 1e3 / len(rec["hot_path_s_per_batch"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "u8", "data": "synthetic", "recorded": True,
+                              "config": {"workload": "RECORDED full run (tools/ref_full_run.py, %s, %d host cores): %s %s" % (rec["when"], rec["host_cores"], synth.workload_key(w, flags), rec["batch"]),
+                                         "md5_text": rec["md5_text"]},
+                              "cpu_baseline": {"value": val, "unit": UNIT, "cores": 5, "kind": "reference", "sample": "full workload, recorded"},
+                              "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
+        sample = 4_000_000
+        note = "host has %.0f GB available: a bounded sample instead of the full workload; " % mem_available_gb()
+    if sample:
+        w = synth.workload(args.config, sample)
+    key = synth.workload_key(w, flags)
+    cache = "/tmp/rb2_reference_arm_%s.json" % (socket.gethostname())
+    rec = None
+    if os.path.exists(cache):
+        try:
+            c = json.load(open(cache))
+            if c.get("key") == key and time.time() - c.get("t", 0) < 6 * 3600:
+                rec, note = c["rec"], note + "measured earlier in this session on this box (N does not change the CPU reference); "
+        except Exception:
+            rec = None
+    if rec is None:
+        rec = orc.ref_stream_run(w, flags, want_md5=True, gen_threads=max(2, (os.cpu_count() or 8) // 4))
+        try:
+            json.dump({"key": key, "t": time.time(), "rec": rec}, open(cache, "w"))
+        except Exception:
+            pass
+    nb = max(1, len(rec["hot_path_s_per_batch"]))
+    val = rec["gbp_per_s_hot_path"]
+    recorded = orc.ref_recorded(w, flags)
+    same = recorded["md5_text"] == rec["md5_text"] if recorded else None
+    if same is False:
+        raise SystemExit("the reference's md5 on this box differs from the recorded one: the generators disagree")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": nb, "warmup": 0,
+        "ms_per_step": rec["hot_path_s"] * 1e3 / nb, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"bounded sample of BASELINE configs[1]: {sample}", "threads": "4 workers + master (reference maximum, mrope.h:53)",
-                   "host_cores": os.cpu_count()},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 5, "kind": "reference", "sample": sample},
+        "config": {"workload": note + "%s: %s, oracle/_ref/ropebwt2 %s (unmodified reference), ONE full run (%d mr_insert_multi call%s), hot-path timer main.c:241,249 = %.1f s, wall %.1f s"
+                               % ("FULL workload of " + args.config if not sample else "sample of " + args.config, key, flags, nb, "" if nb == 1 else "s", rec["hot_path_s"], rec["wall_s"]),
+                   "threads": "4 workers + master (reference maximum, mrope.h:53)", "host_cores": os.cpu_count(),
+                   "steps_requested": args.steps, "md5_text": rec["md5_text"], "md5_equals_recorded_run": same},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 5, "kind": "reference", "sample": "the full workload" if not sample else "%d reads" % sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------------------
+# b200 arm
+# ------------------------------------------------------------------------------------------------------
+def fill_host_batch(host: np.ndarray, w: dict, a: int, b: int, device, slice_reads: int = 4_000_000):
+    """mr_insert_multi buffer (reversed read + NUL per read) of reads a..b-1 into the pinned host array,
+    generated on the GPU slice by slice (bit-identical to the numpy / C generators, tests/test_synth.py)."""
+    import torch
+    from ropebwt2_b200 import synth
+    L1 = w["L"] + 1
+    ht = torch.from_numpy(host[:(b - a) * L1])
+    for x in range(a, b, slice_reads):
+        y = min(b, x + slice_reads)
+        t = torch.empty((y - x) * L1, dtype=torch.uint8, device=device)
+        synth.fill_batch_torch(t, w, x, y, chunk=slice_reads)
+        ht[(x - a) * L1:(y - a) * L1].copy_(t)
+        del t
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_of(st, steps):
+    peak, peak_src = peaks()
+    dense = st.get("flat_batches", 0) > 0
+    if dense:
+        kernel, items, nbytes = "k_flat_merge", st["merge_blocks"], st["merge_bytes_rw"]
+    else:
+        kernel = "k_merge_half"
+        items = st["merge_blocks"] - st["general_items"]
+        nbytes = items * 2 * 512
+    gbs = nbytes / (st["ms_merge"] * 1e-3) / 1e9 if st["ms_merge"] > 0 else 0.0
+    traffic = info = None
+    pj = os.path.join(ROOT, "profiles", "flat_merge_traffic.json" if dense else "merge_traffic.json")
+    if os.path.exists(pj):
+        j = json.load(open(pj))
+        info = {k: v for k, v in j.items() if k in ("capture", "items_in_launch", "algorithmic_bytes_same_launch", "note")}
+        traffic = j.get("dram_bytes_per_launch")
+    return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
+            "traffic_capture": info, "peak_source": peak_src, "launches": int(st["n_merge_launches"]), "ms_in_kernel": st["ms_merge"],
+            "algorithmic_bytes": int(nbytes), "items": int(items),
+            "regime": "dense (flat 3-bit plane array, TMA-staged)" if dense else "sparse (leaf blocks)",
+            "items_left_to_k_merge_fast_and_general": int(st["general_items"]), "ms_in_k_merge_fast_and_general": st["ms_merge_general"],
+            "share_of_step": st["ms_merge"] / st["ms_total"] if st["ms_total"] else None}
+
+
+def cpu_sample(args, flags):
+    from oracle import oracle as orc
+    from ropebwt2_b200 import synth
+    w = synth.workload(args.config, args.cpu_reads if args.config != "cfg4" else max(1, args.cpu_reads // 400))
+    rec = orc.ref_stream_run(w, flags, want_md5=False)
+    return {"value": rec["gbp_per_s_hot_path"], "unit": UNIT, "cores": 5, "kind": "reference",
+            "sample": "%s, oracle/_ref/ropebwt2 %s (4 workers + master), hot-path timer %.2f s, wall %.2f s, host has %d cores"
+                      % (synth.workload_key(w, flags), flags, rec["hot_path_s"], rec["wall_s"], os.cpu_count())}
+
+
+def verify_md5(L, mr_handle, w, flags):
+    """md5 of the index behind an mrope_t (decoded through mr_itr_next_block) vs the recorded reference run."""
+    from oracle import oracle as orc  # the checker
+    rec = orc.ref_recorded(w, flags)
+    t = time.time()
+    md5, total = orc.index_md5(L, mr_handle)
+    out = {"md5": md5, "symbols": total, "seconds": round(time.time() - t, 1)}
+    if rec is None:
+        out["result"] = "unpinned: no recorded reference run for this workload"
+        return out
+    if md5 != rec["md5_text"] or total + 1 != rec["text_bytes"]:
+        raise SystemExit("PARITY FAILURE: md5 of the GPU index %s (%d symbols) != reference %s (%d bytes)" % (md5, total, rec["md5_text"], rec["text_bytes"]))
+    out["result"] = "md5 == reference (oracle/_ref/ropebwt2 %s, recorded %s)" % (flags, rec["when"])
+    return out
 
 
 def main():
@@ -185,7 +289,7 @@ def main():
     os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     import torch
     import torch.distributed as dist
-    from ropebwt2_b200.dist import Reducer, rank_info, shard_seed
+    from ropebwt2_b200.dist import Reducer, rank_info
     rank, world, local = rank_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
@@ -193,36 +297,48 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     red = Reducer(world, torch.device("cuda", local))
+    os.environ["RB2_DEVICE"] = str(local)
+    if args.config in ("cfg3", "cfg3u"):
+        out = run_multibatch(args, torch, red, rank, world, local)
+    else:
+        out = run_single_batch(args, torch, red, rank, world, local)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
 
+
+def run_single_batch(args, torch, red, rank, world, local):
+    """cfg2 / cfg4: one batch into an empty index per step."""
     from ropebwt2_b200 import Engine, MRope, load
     L = load()
-    n, ln = args.reads, args.length
+    w, n, flags = workload_of(args, world)
+    ln = w["L"]
+    so = 1 if "s" in flags else 0
     nbytes = n * (ln + 1)
     bp = n * ln
+    dev = torch.device("cuda", local)
 
     # ---- inputs: pinned host batch (e2e leg) and a device-resident copy (value leg) ----------
     L.rb2_host_alloc.restype = C.c_void_p
     hptr = L.rb2_host_alloc(nbytes)
     host = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(hptr))
-    fill_batch(host, n, ln, shard_seed(args.seed, rank))
+    fill_host_batch(host, w, rank * n, (rank + 1) * n, dev)
     sharded = world > 1 and args.layout == "sharded"
     if sharded:
         # one index over all ranks: the library's own NCCL communicator, unique id handed out through torch.distributed
         from ropebwt2_b200.binding import ShardedEngine, nccl_unique_id
         from ropebwt2_b200.dist import broadcast_bytes
-        eng = ShardedEngine(local, 1, rank, world, nccl_uid=broadcast_bytes(nccl_unique_id() if rank == 0 else None))
+        eng = ShardedEngine(local, so, rank, world, nccl_uid=broadcast_bytes(nccl_unique_id() if rank == 0 else None))
     else:
-        eng = Engine(local, 1)
+        eng = Engine(local, so)
     dptr = eng.dev_alloc(nbytes)
     eng.dev_upload(dptr, host)
-    os.environ["RB2_DEVICE"] = str(local)
 
     def barrier():
         torch.cuda.synchronize()
         red.barrier()
         torch.cuda.synchronize()
-
-    max_over_ranks = red.max
 
     # ---- value leg: device-resident input ------------------------------------------------
     for _ in range(args.warmup):
@@ -239,11 +355,10 @@ def main():
     barrier()
     wall_value = time.time() - t0
     st = eng.stats()
-    ms_value = max_over_ranks(st["ms_total"])
+    ms_value = red.max(st["ms_total"])
     counts = eng.counts()
     n_idx = world if sharded else 1  # strings in the index this rank sees
-    ok = int(counts.sum()) == nbytes * n_idx and int(counts[:, 0].sum()) == n * n_idx
-    if not ok:
+    if not (int(counts.sum()) == nbytes * n_idx and int(counts[:, 0].sum()) == n * n_idx):
         raise SystemExit("symbol conservation violated: the index does not hold the batch")
     eng.dev_free(dptr)
 
@@ -255,9 +370,10 @@ def main():
             return int(eng.counts().sum())
         e2e_stats, e2e_reset_stats = eng.stats, eng.reset_stats
         e2e_api = "rb2_insert_multi_sharded (include/ropebwt2_b200.h) on a pinned host buffer per rank + rb2_counts"
+        mr = None
     else:
         eng.close()
-        mr = MRope(1)
+        mr = MRope(so)
 
         def e2e_step():
             L.rb2_reset(mr.engine_handle)
@@ -276,86 +392,133 @@ def main():
     barrier()
     wall_e2e = time.time() - t0
     st2 = e2e_stats()
-    ms_e2e = max_over_ranks(st2["ms_total"])
+    ms_e2e = red.max(st2["ms_total"])
     clocks = sampler.summary()
     assert tot == nbytes * n_idx
-    ms_exch = max_over_ranks(st.get("ms_exchange", 0.0))
+    ms_exch = red.max(st.get("ms_exchange", 0.0))
+
+    # ---- parity: md5 of the index the last e2e step built vs the unmodified reference (outside the timed region) ----
+    parity = {"result": "symbol conservation only (--no-verify)"}
+    if not args.no_verify:
+        if mr is not None:
+            parity = verify_md5(L, mr.h, w, flags)
+        else:
+            parity = {"result": "symbol conservation checked in-run at this N; bit-exactness of the sharded build: tests/test_sharded_gpu.py, tests/test_sharded_nccl.py and "
+                                "the --config cfg2 md5 check at N=1 (the sharded path runs the same kernels)"}
     if sharded:
         eng.close()
     else:
         mr.close()
     L.rb2_host_free(C.c_void_p(hptr))
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # dominant kernel.  Dense regime (the headline workload): k_flat_merge, one streaming pass per column
-    # over the flat symbol array -- algorithmic bytes = old array read + new array written + records
-    # (20 B read, 8 B rank written each).  Sparse regime: k_merge_half (two leaf blocks per warp) --
-    # every item it finishes reads one 512-byte leaf block and writes it back.
-    dense = st.get("flat_batches", 0) > 0
-    if dense:
-        kernel = "k_flat_merge"
-        fast_items = st["merge_blocks"]
-        fast_bytes = st["merge_bytes_rw"]
-    else:
-        kernel = "k_merge_half"
-        fast_items = st["merge_blocks"] - st["general_items"]
-        fast_bytes = fast_items * 2 * 512
-    merge_gbs = fast_bytes / (st["ms_merge"] * 1e-3) / 1e9 if st["ms_merge"] > 0 else 0.0
-    traffic = None
-    traffic_info = None
-    ncu_json = os.path.join(ROOT, "profiles", "flat_merge_traffic.json" if dense else "merge_traffic.json")
-    if os.path.exists(ncu_json):
-        traffic_info = {k: v for k, v in json.load(open(ncu_json)).items() if k in ("capture", "items_in_launch", "algorithmic_bytes_same_launch", "note")}
-        traffic = json.load(open(ncu_json)).get("dram_bytes_per_launch")  # one late launch (column 90) at this workload size
     value = world * bp * args.steps / (ms_value * 1e-3) / 1e9
     e2e_val = world * bp * args.steps / (ms_e2e * 1e-3) / 1e9
+    from ropebwt2_b200 import synth
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if ln == 101 else "Gbp/s inserted (%d bp reads), bit-exact BWT" % ln, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: {n} x {ln} bp uniform reads per GPU, forward strand, RLO (-LRs), one batch into an empty index",
-                   "reads_per_gpu": n, "read_length": ln, "sorting_order": "RLO",
+        "config": {"workload": "BASELINE %s: %s (%d reads per GPU), forward strand, %s, one batch into an empty index" % (args.config, synth.workload_key(w, flags), n, "RLO" if so else "input order"),
+                   "reads_per_gpu": n, "read_length": ln, "sorting_order": "RLO" if so else "IO",
                    "parallelism": (f"sharded x{world}: ONE index of {world * n} reads, 36 sub-buckets over {world} GPUs, "
                                    "per column one count all-gather + one string-state exchange (NCCL send/recv)") if sharded
                    else (f"replicas x{world}" if world > 1 else "one GPU"),
-                   "l2": "inputs (%.1f GB batch, multi-GB leaf-block pool) far exceed the 126 MB L2" % (nbytes / 1e9),
+                   "l2": "inputs (%.1f GB batch, multi-GB symbol array) far exceed the 126 MB L2" % (nbytes / 1e9),
                    "timing": "CUDA events on the engine stream around each call; wall-clock cross-check %.3f s/step" % (wall_value / args.steps),
-                   "parity": "symbol conservation checked in-run; bit-exactness vs the reference is tests/test_parity_gpu.py"},
+                   "parity": parity["result"]},
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 7 * 48,
-                "ms_per_step": ms_e2e / args.steps, "wall_s_per_step": wall_e2e / args.steps,
-                "api": e2e_api},
+                "ms_per_step": ms_e2e / args.steps, "wall_s_per_step": wall_e2e / args.steps, "api": e2e_api,
+                "phases_ms_per_step": {k: st2[k] / args.steps for k in ("ms_h2d", "ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_directory", "ms_convert")}},
         "gpu_launches": int(st["n_launches"]),
-        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": merge_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": merge_gbs / peak, "traffic": traffic, "traffic_capture": traffic_info, "peak_source": peak_src,
-                     "launches": int(st["n_merge_launches"]), "ms_in_kernel": st["ms_merge"],
-                     "algorithmic_bytes": int(fast_bytes), "items": int(fast_items), "regime": "dense (flat symbol array)" if dense else "sparse (leaf blocks)",
-                     "items_left_to_k_merge_fast_and_general": int(st["general_items"]), "ms_in_k_merge_fast_and_general": st["ms_merge_general"],
-                     "share_of_step": st["ms_merge"] / st["ms_total"] if st["ms_total"] else None},
+        "roofline": roofline_of(st, args.steps),
         "phases_ms_per_step": {k: st[k] / args.steps for k in ("ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_merge_general", "ms_directory", "ms_exchange", "ms_convert")},
     }
     if sharded:
         out["exchange"] = {"ms_per_step_max_over_ranks": ms_exch / args.steps, "bytes_received_per_step_rank0": int(st["exch_bytes"] / args.steps),
                            "collectives_per_column": "1 all-gather (1.8 KB/rank) + 1 grouped send/recv of the string state"}
-    if not args.no_cpu_baseline and ref_binary() is not None:
-        g, hot, wall, _ = run_reference_sample(args.cpu_reads, ln, args.seed)
-        out["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": 5, "kind": "reference",
-                               "sample": f"{args.cpu_reads} x {ln} bp uniform reads, oracle/_ref/ropebwt2 -LRs (4 workers + master), "
-                                         f"hot-path timer {hot:.2f} s, wall {wall:.2f} s, host has {os.cpu_count()} cores"}
+    if not args.no_cpu_baseline and ref_binary() is not None and world == 1:
+        out["cpu_baseline"] = cpu_sample(args, flags)
     else:
-        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/ropebwt2 not available"}
-    print(json.dumps(out))
+        out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "N > 1 or oracle/_ref/ropebwt2 not available"}
+    return out
+
+
+def run_multibatch(args, torch, red, rank, world, local):
+    """cfg3: the reference driver's own batching -- successive mr_insert_multi calls into one growing index."""
+    from ropebwt2_b200 import MRope, load, synth
     if world > 1:
-        dist.destroy_process_group()
+        raise SystemExit("--config cfg3 runs on one GPU here (N > 1: --config cfg2, the sharded build)")
+    L = load()
+    w, n, flags = workload_of(args, 1)
+    ln = w["L"]
+    so = 1 if "s" in flags else 0
+    per = (REF_BATCH_BYTES + ln) // (ln + 1)  # main.c:238: flush once the buffer holds >= m bytes
+    if args.reads and args.reads < 2 * per:
+        per = max(1, args.reads // 12)          # scaled-down runs keep the 12-batch shape
+    cuts = list(range(0, n, per)) + [n]
+    dev = torch.device("cuda", local)
+    L.rb2_host_alloc.restype = C.c_void_p
+    cap = per * (ln + 1)
+    hptr = L.rb2_host_alloc(cap)
+    host = np.ctypeslib.as_array((C.c_uint8 * cap).from_address(hptr))
+    mr = MRope(so)
+    sampler = ClockSampler(local)
+    sampler.start()
+    batches = []
+    t_job = 0.0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        nbytes = (b - a) * (ln + 1)
+        fill_host_batch(host, w, a, b, dev)
+        mr.reset_stats()
+        t0 = time.time()
+        mr.L.mr_insert_multi(mr.h, nbytes, C.cast(hptr, C.POINTER(C.c_uint8)), 1)
+        tot = int(mr.counts().sum())
+        wall = time.time() - t0
+        st = mr.stats()
+        t_job += st["ms_total"]
+        free, total_mem = torch.cuda.mem_get_info()
+        batches.append({"reads": b - a, "ms": st["ms_total"], "ms_h2d": st["ms_h2d"], "wall_s": wall, "Gbp/s": (b - a) * ln / (st["ms_total"] * 1e-3) / 1e9,
+                        "regime": "dense" if st["flat_batches"] else "sparse", "ms_merge": st["ms_merge"], "ms_groups": st["ms_groups"], "ms_members": st["ms_members"],
+                        "ms_convert": st["ms_convert"], "merge_GB/s": st["merge_bytes_rw"] / max(st["ms_merge"], 1e-9) / 1e6,
+                        "hbm_used_GB": (total_mem - free) / 1e9, "launches": int(st["n_launches"]), "index_symbols": tot})
+        print("[bench] batch %d/%d: %s" % (len(batches), len(cuts) - 1, json.dumps(batches[-1])), file=sys.stderr, flush=True)
+    clocks = sampler.summary()
+    L.rb2_host_free(C.c_void_p(hptr))
+    if tot != n * (ln + 1):
+        raise SystemExit("symbol conservation violated")
+    parity = {"result": "symbol conservation only (--no-verify)"}
+    if not args.no_verify:
+        parity = verify_md5(L, mr.h, w, flags)
+    mr.close()
+    bp = n * ln
+    ms_h2d = sum(x["ms_h2d"] for x in batches)
+    e2e_val = bp / (t_job * 1e-3) / 1e9
+    value = bp / ((t_job - ms_h2d) * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    mbytes = sum(x["merge_GB/s"] * x["ms_merge"] * 1e6 for x in batches)
+    mms = sum(x["ms_merge"] for x in batches)
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": len(batches), "warmup": 0, "ms_per_step": (t_job - ms_h2d) / len(batches),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE %s (north star): %s, forward strand, RLO, %d successive mr_insert_multi calls of %d reads (the reference driver's default -m, main.c:94) into ONE growing index"
+                               % (args.config, synth.workload_key(w, flags), len(batches), per),
+                   "l2": "every column streams the whole symbol array (GBs) : far beyond the 126 MB L2", "parity": parity["result"],
+                   "timing": "CUDA events on the engine stream around every call, summed over the job; value excludes the H2D copy of each batch, e2e includes it"},
+        "parity": parity, "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": cap, "d2h_bytes_per_step": 7 * 48, "ms_per_step": t_job / len(batches),
+                "api": "mr_insert_multi (include/mrope.h) on a pinned host buffer + mr_get_c counts, once per batch"},
+        "gpu_launches": sum(x["launches"] for x in batches),
+        "roofline": {"bound": "hbm", "kernel": "k_flat_merge", "achieved": mbytes / max(mms, 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": mbytes / max(mms, 1e-9) / 1e6 / peak, "traffic": None, "peak_source": peak_src, "ms_in_kernel": mms, "algorithmic_bytes": int(mbytes),
+                     "share_of_step": mms / t_job},
+        "batches": batches,
+        "hbm_high_water_GB": max(x["hbm_used_GB"] for x in batches),
+        "cpu_baseline": cpu_sample(args, flags) if (not args.no_cpu_baseline and ref_binary() is not None) else {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "not run"},
+    }
 
 
 if __name__ == "__main__":

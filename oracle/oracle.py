@@ -182,6 +182,69 @@ def index_md5(lib: C.CDLL, mr, to_free: int = 0, chunk: int = 1 << 26):
     return h.hexdigest(), total
 
 
+def ref_stream_run(w: dict, flags: str = "-LRs", batch: str = "", want_md5: bool = True, gen_threads: int = 2) -> dict:
+    """Run the UNMODIFIED reference binary on workload ``w`` (ropebwt2_b200.synth.workload): the reads
+    are streamed into its stdin (``ropebwt2 <flags> -``, main.c:173) from the seeded C generator, its
+    text output goes through a streaming md5 (or to /dev/null).  Returns md5, the reference's own
+    hot-path timer (sum of the ``inserted ... in X sec`` lines, main.c:241,249) and wall seconds."""
+    import hashlib
+    import threading
+    import time
+    from ropebwt2_b200 import synth
+    cmd = [_need(os.path.join(REF, "ropebwt2")), flags]
+    if batch:
+        cmd += ["-m", batch]
+    if not want_md5:
+        cmd += ["-o", "/dev/null"]
+    cmd += ["-"]
+    t0 = time.time()
+    p = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, bufsize=0)
+    md5, nout, err = hashlib.md5(), [0], []
+
+    def pump_out():
+        while True:
+            b = p.stdout.read(1 << 24)
+            if not b:
+                break
+            md5.update(b)
+            nout[0] += len(b)
+
+    def pump_err():
+        err.append(p.stderr.read())
+
+    to, te = threading.Thread(target=pump_out), threading.Thread(target=pump_err)
+    to.start(), te.start()
+    try:
+        for lines in synth.stream_lines(w, threads=gen_threads):
+            p.stdin.write(lines)
+        p.stdin.close()
+    except BrokenPipeError:
+        pass
+    to.join(), te.join()
+    rc = p.wait()
+    wall = time.time() - t0
+    stderr = err[0].decode()
+    if rc != 0:
+        raise RuntimeError("reference failed: " + stderr[-500:])
+    hot = [float(ln.split(" symbols in ")[1].split(" sec")[0]) for ln in stderr.splitlines() if "] inserted " in ln]
+    return {"workload": w, "flags": flags, "batch": batch or "default (-m 10415295693 bytes, main.c:94)",
+            "md5_text": md5.hexdigest() if want_md5 else None, "text_bytes": nout[0], "hot_path_s": sum(hot), "hot_path_s_per_batch": hot,
+            "wall_s": wall, "host_cores": os.cpu_count(), "threads": "4 workers + master",
+            "gbp_per_s_hot_path": w["n"] * w["L"] / sum(hot) / 1e9, "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}
+
+
+GOLDEN_RUNS = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref_full_runs.json")
+
+
+def ref_recorded(w: dict, flags: str):
+    """The recorded full run of the reference for this workload (tools/ref_full_run.py), or None."""
+    import json
+    from ropebwt2_b200 import synth
+    if not os.path.exists(GOLDEN_RUNS):
+        return None
+    return json.load(open(GOLDEN_RUNS)).get(synth.workload_key(w, flags))
+
+
 class RefLib:
     """The unmodified reference ``mrope.h`` API (``oracle/_ref/libref.so``)."""
 

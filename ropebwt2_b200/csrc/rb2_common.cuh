@@ -30,11 +30,23 @@
 // One elected thread arms the mbarrier with the byte count and issues the copy; whoever needs the
 // data waits on the barrier's phase parity.  Addresses and sizes are multiples of 16 bytes.
 #ifdef RB2_EMU
+// emulated mbarrier: count:8 | pending arrivals:8 | phase:16 | pending transaction bytes:32 (signed)
 static inline void rb2_emu_check16(const void *a, const void *b, uint32_t n) { if ((((uintptr_t)a | (uintptr_t)b | n) & 15) != 0) { fprintf(stderr, "[cuda_emu] bulk copy not 16-byte aligned\n"); abort(); } }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t) { *bar = 0; }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *, uint32_t) {}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { rb2_emu_check16(dst, src, bytes); memcpy(dst, src, bytes); *bar += 1; }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { while (((uint32_t)*bar & 1u) == parity) rb2emu::yield(); }
+static inline void rb2_emu_mbar_update(uint64_t *bar, int arrive, int64_t tx)
+{
+	uint64_t v = *bar;
+	uint32_t count = (uint32_t)(v & 0xff), pend = (uint32_t)((v >> 8) & 0xff), phase = (uint32_t)((v >> 16) & 0xffff);
+	int64_t t = (int32_t)(uint32_t)(v >> 32);
+	if (arrive) { if (pend == 0) { fprintf(stderr, "[cuda_emu] mbarrier: more arrivals than its count\n"); abort(); } --pend; }
+	t += tx;
+	if (pend == 0 && t == 0) { ++phase; pend = count; }
+	*bar = (uint64_t)count | (uint64_t)pend << 8 | (uint64_t)(phase & 0xffff) << 16 | (uint64_t)(uint32_t)(int32_t)t << 32;
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { *bar = (uint64_t)count | (uint64_t)count << 8; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { rb2_emu_mbar_update(bar, 1, bytes); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) { rb2_emu_mbar_update(bar, 1, 0); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) { rb2_emu_check16(dst, src, bytes); memcpy(dst, src, bytes); rb2_emu_mbar_update(bar, 0, -(int64_t)bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { while ((((uint32_t)(*bar >> 16)) & 1u) == parity) rb2emu::yield(); }
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) { rb2_emu_check16(dst, src, bytes); memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulk_commit() {}
 __device__ __forceinline__ void bulk_wait_read() {}
@@ -50,6 +62,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 // global -> shared; completes `bytes` transaction bytes on the mbarrier when the data has landed
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)

@@ -1817,9 +1817,9 @@ enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, P
 struct FlatState {
 	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
 	bool valid = false, blocksStale = false; // the array holds the current index (resident between dense batches) / the leaf blocks do not
-	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, tileR0, ovf; DevBuf<TileDesc> desc;
+	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, ovf; DevBuf<TileDesc> desc;
 	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
-	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); tileR0.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
 };
 
 struct rb2_engine {
@@ -2038,7 +2038,8 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatSmemT<FT_OUT>)));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatDSmemT<FT_OUT>)));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatPSmem)));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);
@@ -2231,8 +2232,8 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	ph_end(e, PH_TRANSPOSE);
 
 	// ---- state for column 0 (mrope.c:279-285) -------------------------------------------
-	for (int k = 0; k < 2; ++k) { e->gL[k].need(m); e->gSize[k].need(m); e->gOff[k].need((size_t)m + 1); e->sid[k].need((size_t)m + 4); }
-	e->asym.need((size_t)m + 8);
+	for (int k = 0; k < 2; ++k) { e->gL[k].need((size_t)m + 64); e->gSize[k].need((size_t)m + 64); e->gOff[k].need((size_t)m + 64); e->sid[k].need((size_t)m + 64); } // (+64: the merge kernel's TMA slices are widened to 16-byte boundaries)
+	e->asym.need((size_t)m + 64);
 	const size_t recCap = (size_t)m + m / RB2_MAXRUN + 64;
 	e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
 	// dense regime: the whole batch runs on a flat symbol array (rb2_flat.cuh), re-encoded at the end

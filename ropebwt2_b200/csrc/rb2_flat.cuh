@@ -104,29 +104,22 @@ struct RecView {
 	__device__ __forceinline__ uint64_t Key(uint32_t r) const { return (uint64_t)P[r] + Pre(r); }
 };
 
-// ---- tile -> record ranges ---------------------------------------------------------------------------
-// tileR0[t] = first record whose output run starts at or behind t*FT_OUT (key_r = P_r + pre_r); one
-// thread per record (plus a virtual one behind the last) fills the tiles between its predecessor and itself.
-__global__ void __launch_bounds__(256) k_flat_splits(const RecView V, uint32_t R, uint64_t nTiles, uint32_t *tileR0)
-{
-	const uint64_t r = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-	if (r > R) return;
-	const int64_t tPrev = r == 0 ? -1 : (int64_t)(V.Key((uint32_t)r - 1) / FT_OUT);
-	const int64_t t = r == R ? (int64_t)nTiles : (int64_t)(V.Key((uint32_t)r) / FT_OUT);
-	for (int64_t tt = tPrev + 1; tt <= t; ++tt) tileR0[tt] = (uint32_t)r;
-}
-
-// Per-tile geometry, one thread per tile boundary t (output position min(t*FT_OUT, nNew)): the first old
-// symbol that lands at or behind it, the first record that starts there, and the record run that reaches
-// across it from the left.  Computed ahead of k_flat_merge so that its CTAs start with two independent loads.
+// ---- tile geometry ---------------------------------------------------------------------------------------
+// One thread per tile boundary t (output position min(t*FT_OUT, nNew)): the first record whose output run
+// starts at or behind it (bisection over the strictly increasing keys key_r = P_r + pre_r), the first old
+// symbol that lands at or behind it, and the record run that reaches across it from the left.  Computed
+// ahead of k_flat_merge so that its CTAs start with two independent loads.
 struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FT_OUT) << 3 | symbol
 
-__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, const uint32_t *tileR0, uint64_t nTiles, uint64_t nNew, TileDesc *desc)
+__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nTiles, uint64_t nNew, TileDesc *desc)
 {
 	const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (t > nTiles) return;
 	const uint64_t o0 = t * FT_OUT < nNew ? t * FT_OUT : nNew;
-	const uint32_t r0 = tileR0[t];
+	uint32_t lo = 0, hi = R; // first r with Key(r) >= t*FT_OUT (R if none)
+	if (t == nTiles) lo = R;
+	while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (V.Key(mid) >= t * FT_OUT) hi = mid; else lo = mid + 1; }
+	const uint32_t r0 = lo;
 	uint64_t before = 0; uint32_t carry = 0;
 	if (r0 > 0) {
 		const uint64_t pre = V.Pre(r0 - 1), key = (uint64_t)V.P[r0 - 1] + pre; const uint32_t sc = V.SC(r0 - 1);
@@ -152,14 +145,16 @@ struct FlatArgs {
 
 #define FT_NCH (FT_OLDMAX / FT_CH + 2)   // cells of old symbols one tile can hold (one more than it counts: funnel-shift partner)
 #define FT_OLDW ((FT_NCH * 3 + 3) & ~3)  // ... as words, a multiple of 16 bytes (TMA destination)
-#define FT_NOC (FT_OUT / FT_CH)          // output cells per tile = threads per CTA
+#define FT_NOC (FT_OUT / FT_CH)          // output cells per tile = worker threads per CTA
 #define FT_TILEW (FT_NOC * 3)            // words of one output tile
-#define FT_CAP_SMALL 2047                // records per tile the main kernel stages (more: overflow kernel, same code)
-template <int CAP> struct FlatSmemT {
-	alignas(16) uint32_t old[FT_OLDW];   // the old symbols this tile needs, from a directory tile boundary (TMA bulk load)
+#define FP_CAP   1023                    // records per tile the main (persistent) kernel stages; more: overflow kernel, same tile code
+#define FP_STAGES 2                      // tiles in flight per CTA of the main kernel: one being merged, one being fetched
+#define FT_BAR_WORK 2                    // named barrier of the 256 worker threads of a CTA
+
+// working set of one tile in shared memory
+template <int CAP> struct FlatWorkT {
 	alignas(16) uint32_t out[FT_TILEW];  // the finished tile (TMA bulk store)
-	alignas(8) uint64_t mbar;            // completion of the bulk load
-	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every cell of old (16-bit fields)
+	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every cell of the old symbols (16-bit fields)
 	uint16_t sKey[CAP + 1];              // staged records: run start inside the tile
 	uint16_t sLS[CAP + 1];               // (run length inside the tile - 1) << 3 | symbol
 	uint16_t sPre[CAP + 1];              // record symbols of this tile in front of the record
@@ -167,7 +162,15 @@ template <int CAP> struct FlatSmemT {
 	uint16_t k0C[FT_NOC + 2];            // ... and their exclusive prefix = the first record at or behind each cell
 	uint32_t warpTot[8][3];
 	uint32_t warpCnt[8][3];              // raw counts of the 32 output cells of each warp
-	uint32_t tile;                       // overflow kernel: the tile this CTA works on
+};
+
+// where the inputs of one tile are: the old symbols from the directory tile boundary a0 on (shared memory),
+// and the tile's records, indexed from 0 (shared memory in the main kernel, global memory in the overflow kernel)
+struct TileIn {
+	const uint32_t *old; const int64_t *P; const uint32_t *pre, *sc, *dst; const uint8_t *asym;
+	uint32_t r0;
+	__device__ __forceinline__ uint32_t Pre(uint32_t k) const { return pre ? pre[k] : r0 + k; }
+	__device__ __forceinline__ uint32_t SC(uint32_t k) const { return sc ? sc[k] : (8u | asym[k]); }
 };
 
 // insert c copies (1 <= c, q + c <= 32) of symbol sy at bit position q of a cell; what is pushed past bit 31 falls out
@@ -182,11 +185,12 @@ __device__ __forceinline__ void cell_insert(Cell &x, uint32_t q, uint32_t c, uin
 	x.b2 = (x.b2 & low) | (((x.b2 & ~low) << sh) & keepHi) | ((sy & 4u) ? fill : 0u);
 }
 
-// One output tile.  (A) TMA bulk load of the old symbols, their counts per cell | records -> shared memory,
-// (B) every thread assembles one output cell, (C) TMA bulk store | ranks of the tile's records | symbol
-// counts of its sub-tiles.  `parity`: phase of S.mbar this call waits for (S.mbar is initialised by the caller).
+// One output tile, executed by the 256 worker threads of a CTA (tid = 0..255) once its inputs are in place.
+// (A) raw counts per cell of the old symbols | records -> keys, indexed by output cell, (B) every thread
+// assembles one output cell, (C) TMA bulk store | ranks of the tile's records | symbol counts of its
+// sub-tiles.  Three barriers, all FT_BAR_WORK.
 template <int CAP>
-__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP> &S, const uint32_t tile, const TileDesc d0, const TileDesc d1, const uint32_t parity)
+__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatWorkT<CAP> &S, const TileIn &in, const uint32_t tile, const TileDesc d0, const TileDesc d1)
 {
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const uint64_t o0 = (uint64_t)tile * FT_OUT;
@@ -198,23 +202,17 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	const uint32_t loadLen = (uint32_t)(d1.i0 - a0), skip = (uint32_t)(i0 - a0);
 	const uint32_t recIn = tileLen - (loadLen - skip); // record symbols inside the tile
 	const uint64_t before = o0 - i0;               // record symbols in front of the tile
-	const uint32_t nLoad = loadLen / FT_CH + 2;    // cells that are read (<= FT_NCH); the last one only as a funnel-shift partner
+	const uint32_t nLoad = loadLen / FT_CH + 2;    // cells that were fetched (<= FT_NCH); the last one only as a funnel-shift partner
 	const uint32_t nCarry = carryLen ? 1u : 0u, nS = nCarry + (r1 - r0);
 	constexpr int NCNT = 160;                      // threads (5 warps) that count; the other 3 warps stage records
 
-	// ---- phase A: old symbols -> shared memory (TMA) + raw counts per cell pair | records -> shared memory -----
-	if (tid == 0) {
-		const uint32_t bytes = (nLoad * 12u + 15u) & ~15u;
-		mbar_expect_tx(&S.mbar, bytes);
-		bulk_g2s(S.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.mbar);
-	}
+	// ---- phase A: raw counts per cell pair | records -> keys ------------------------------------------------
 	uint32_t p[3] = { 0, 0, 0 }, q[3] = { 0, 0, 0 }, inc[3] = { 0, 0, 0 };
 	if (tid < NCNT) {
 		// thread j owns cells 2j, 2j+1 (symbols behind loadLen are whatever follows in the array: the
 		// prefixes that include them are never used)
-		mbar_wait(&S.mbar, parity);
 		if ((uint32_t)tid * 2 < nLoad) {
-			const Cell x = cell_load(S.old + tid * 6), y = cell_load(S.old + tid * 6 + 3);
+			const Cell x = cell_load(in.old + tid * 6), y = cell_load(in.old + tid * 6 + 3);
 			Raw6 r = raw_of_cell(x, 0xffffffffu, FT_CH);
 			raw_pack16(r, q);
 			raw_addto(r, raw_of_cell(y, 0xffffffffu, FT_CH));
@@ -239,9 +237,8 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			atomicAdd(&S.cntC[0], 1u);
 		}
 		for (uint32_t k = st; k < r1 - r0; k += 256 - NCNT) {
-			const uint32_t r = r0 + k;
-			const uint32_t pre = A.V.Pre(r), sc = A.V.SC(r);
-			const uint32_t key = (uint32_t)((uint64_t)A.V.P[r] + pre - o0);
+			const uint32_t pre = in.Pre(k), sc = in.SC(k);
+			const uint32_t key = (uint32_t)((uint64_t)in.P[k] + pre - o0);
 			uint32_t len = sc >> 3;
 			if (len > FT_OUT - key) len = FT_OUT - key;
 			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
@@ -259,8 +256,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 			if (lane == 31) S.k0C[FT_NOC] = (uint16_t)ex;
 		}
 	}
-	__syncthreads();
-	if (tid >= NCNT) mbar_wait(&S.mbar, parity); // (complete by now: every thread that reads S.old has observed the phase itself)
+	RB2_NAMED_BAR(FT_BAR_WORK, 256);
 	// prefix in front of every cell (needed behind the next barrier)
 	if (tid < NCNT && (uint32_t)tid * 2 < nLoad) {
 		uint32_t base[3] = { 0, 0, 0 };
@@ -283,7 +279,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		if (!runRem) oldIdx = rel - (k0 < nS ? (uint32_t)S.sPre[k0] : recIn) + skip;
 		Cell x;
 		{ // 32 old symbols from oldIdx on (unaligned)
-			const uint32_t *wp = S.old + (oldIdx >> 5) * 3; const uint32_t sh = oldIdx & 31;
+			const uint32_t *wp = in.old + (oldIdx >> 5) * 3; const uint32_t sh = oldIdx & 31;
 			x.b0 = __funnelshift_r(wp[0], wp[3], sh); x.b1 = __funnelshift_r(wp[1], wp[4], sh); x.b2 = __funnelshift_r(wp[2], wp[5], sh);
 		}
 		if (runRem) cell_insert(x, 0, runRem < FT_CH ? runRem : FT_CH, runSym);
@@ -304,7 +300,7 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 		for (int k = 0; k < 3; ++k) pk[k] = warp_redux_add(pk[k]);
 		if (lane == 0) { S.warpCnt[wid][0] = pk[0]; S.warpCnt[wid][1] = pk[1]; S.warpCnt[wid][2] = pk[2]; }
 	}
-	__syncthreads();
+	RB2_NAMED_BAR(FT_BAR_WORK, 256);
 	// ---- phase C: the tile leaves through one bulk store ------------------------------------------------
 	if (tid == 0) { bulk_s2g(A.newS + (uint64_t)tile * (FT_TILEW * 4), S.out, FT_TILEW * 4); bulk_commit(); }
 	// symbol counts of the four FT_DIR sub-tiles (warp 1)
@@ -321,45 +317,108 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatSmemT<CAP
 	{
 		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
 		for (uint32_t k = 255 - tid; k < r1 - r0; k += 256) {
-			const uint32_t r = r0 + k, dst = A.recDst[r];
+			const uint32_t dst = in.dst[k];
 			if (dst == NONE32) continue;
 			const uint32_t e = nCarry + k, a = S.sLS[e] & 7u;
 			const uint32_t xo = (uint32_t)S.sKey[e] - S.sPre[e] + skip; // old symbols of the load window in front of the record
 			const uint32_t c = xo / FT_CH;
 			const Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
-			const uint32_t part = __popc(cell_match(cell_load(S.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
+			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
 			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a) + part;
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
-				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r) * 7 + a];
+				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k) * 7 + a];
 			A.gLNext[dst] = g;
 		}
 	}
-	if (tid == 0) bulk_wait_read(); // the store has read S.out: the caller may reuse (or release) the shared memory
+	if (tid == 0) bulk_wait_read(); // the store has read S.out
+	RB2_NAMED_BAR(FT_BAR_WORK, 256); // the working set and the inputs may be reused
 }
 
-#ifndef FT_MINCTA
-#define FT_MINCTA 8
-#endif
-// main kernel: one CTA per tile; tiles with more records than it stages go to the overflow list
-__global__ void __launch_bounds__(256, FT_MINCTA) k_flat_merge(FlatArgs A)
+// ---- main kernel: persistent CTAs, warp-specialised -----------------------------------------------------------
+// 8 worker warps + 1 producer warp.  The producer (one thread) walks the CTA's tiles ahead of the workers: it
+// reads the tile's geometry and fetches everything the tile needs -- the old symbols and the tile's slice of
+// every record array -- into one of FP_STAGES shared-memory stages with TMA bulk copies that complete on the
+// stage's `full` mbarrier; the workers merge the tile of one stage while the next one is in flight and hand
+// the stage back through its `empty` mbarrier.  Tiles with more records than a stage holds go to the overflow list.
+struct alignas(16) FlatStage {
+	alignas(16) uint32_t old[FT_OLDW];
+	alignas(16) int64_t P[FP_CAP + 3];       // slices start at a 16-byte boundary of the source array: up to 1 / 3 / 15 elements of slack in front
+	alignas(16) uint32_t pre[FP_CAP + 9], sc[FP_CAP + 9], dst[FP_CAP + 9];
+	alignas(16) uint8_t asym[FP_CAP + 33];
+	TileDesc d0, d1; uint32_t tile, offP, off4, off1;
+};
+struct FlatPSmem {
+	FlatStage st[FP_STAGES];
+	FlatWorkT<FP_CAP> W;
+	alignas(8) uint64_t full[FP_STAGES], empty[FP_STAGES];
+};
+
+__global__ void __launch_bounds__(288, 3) k_flat_merge(FlatArgs A, uint32_t nTiles)
 {
 	RB2_DYN_SMEM(smraw);
-	FlatSmemT<FT_CAP_SMALL> &S = *reinterpret_cast<FlatSmemT<FT_CAP_SMALL>*>(smraw);
-	const TileDesc d0 = A.desc[blockIdx.x], d1 = A.desc[blockIdx.x + 1];
-	if (d1.r0 - d0.r0 + 1 > FT_CAP_SMALL) { // (+1: a run carried in from the left)
-		if (threadIdx.x == 0) A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = blockIdx.x;
+	FlatPSmem &S = *reinterpret_cast<FlatPSmem*>(smraw);
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < FP_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+	}
+	__syncthreads();
+	if (threadIdx.x >= 256) {
+		// ---- producer ----
+		if (threadIdx.x != 256) return;
+		uint32_t n = 0;
+		for (uint32_t tile = blockIdx.x; ; tile += gridDim.x) {
+			const bool last = tile >= nTiles;
+			TileDesc d0, d1;
+			if (!last) {
+				d0 = A.desc[tile]; d1 = A.desc[tile + 1];
+				if (d1.r0 - d0.r0 + 1 > FP_CAP) { A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = tile; continue; } // (+1: a run carried in from the left)
+			}
+			const uint32_t s = n % FP_STAGES, ph = (n / FP_STAGES) & 1u;
+			mbar_wait(&S.empty[s], ph ^ 1u);
+			FlatStage &st = S.st[s];
+			if (last) { st.tile = NONE32; mbar_arrive(&S.full[s]); break; }
+			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
+			const uint32_t nLoad = (uint32_t)(d1.i0 - a0) / FT_CH + 2;
+			const uint32_t bOld = (nLoad * 12u + 15u) & ~15u;
+			const uint32_t r0 = d0.r0, nr = d1.r0 - d0.r0;
+			// slices of the record arrays, widened to 16-byte boundaries of the source
+			const uint32_t rP = r0 & ~1u, r4 = r0 & ~3u, r1b = r0 & ~15u;
+			const uint32_t bP = nr ? (((r0 + nr - rP) * 8u + 15u) & ~15u) : 0u;
+			const uint32_t b4 = nr ? (((r0 + nr - r4) * 4u + 15u) & ~15u) : 0u;
+			const uint32_t b1 = nr ? ((r0 + nr - r1b + 15u) & ~15u) : 0u;
+			st.d0 = d0; st.d1 = d1; st.tile = tile; st.offP = r0 - rP; st.off4 = r0 - r4; st.off1 = r0 - r1b;
+			mbar_expect_tx(&S.full[s], bOld + bP + b4 + (A.V.pre ? b4 : 0u) + (A.V.sc ? b4 : b1));
+			bulk_g2s(st.old, A.oldS + (a0 / FT_CH) * 12, bOld, &S.full[s]);
+			if (nr) {
+				bulk_g2s(st.P, A.V.P + rP, bP, &S.full[s]);
+				bulk_g2s(st.dst, A.recDst + r4, b4, &S.full[s]);
+				if (A.V.pre) bulk_g2s(st.pre, A.V.pre + r4, b4, &S.full[s]);
+				if (A.V.sc) bulk_g2s(st.sc, A.V.sc + r4, b4, &S.full[s]);
+				else bulk_g2s(st.asym, A.V.asym + r1b, b1, &S.full[s]);
+			}
+			++n;
+		}
 		return;
 	}
-	if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
-	__syncthreads();
-	flat_merge_tile<FT_CAP_SMALL>(A, S, blockIdx.x, d0, d1, 0u);
+	// ---- workers ----
+	for (uint32_t n = 0; ; ++n) {
+		const uint32_t s = n % FP_STAGES, ph = (n / FP_STAGES) & 1u;
+		mbar_wait(&S.full[s], ph);
+		const FlatStage &st = S.st[s];
+		const uint32_t tile = st.tile;
+		if (tile == NONE32) break;
+		TileIn in = { st.old, st.P + st.offP, A.V.pre ? st.pre + st.off4 : (const uint32_t*)0, A.V.sc ? st.sc + st.off4 : (const uint32_t*)0,
+		              st.dst + st.off4, st.asym + st.off1, st.d0.r0 };
+		flat_merge_tile<FP_CAP>(A, S.W, in, tile, st.d0, st.d1);
+		if (threadIdx.x == 0) mbar_arrive(&S.empty[s]); // (behind the tile's closing barrier: every worker is done with the stage)
+	}
 }
 
-// overflow kernel (persistent): tiles where records are dense -- small indexes, first columns of an input-order batch
+// overflow kernel (persistent, no prefetch): tiles where records are dense -- small indexes, first columns of a batch
+template <int CAP> struct FlatDSmemT { alignas(16) uint32_t old[FT_OLDW]; FlatWorkT<CAP> W; alignas(8) uint64_t mbar; uint32_t tile; };
 __global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
-	FlatSmemT<FT_OUT> &S = *reinterpret_cast<FlatSmemT<FT_OUT>*>(smraw);
+	FlatDSmemT<FT_OUT> &S = *reinterpret_cast<FlatDSmemT<FT_OUT>*>(smraw);
 	const uint32_t n = A.ovf[0];
 	if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
 	uint32_t parity = 0;
@@ -369,9 +428,19 @@ __global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
 		const uint32_t qi = S.tile;
 		if (qi >= n) break;
 		const uint32_t tile = A.ovf[2 + qi];
-		flat_merge_tile<FT_OUT>(A, S, tile, A.desc[tile], A.desc[tile + 1], parity);
+		const TileDesc d0 = A.desc[tile], d1 = A.desc[tile + 1];
+		if (threadIdx.x == 0) {
+			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
+			const uint32_t bytes = (((uint32_t)(d1.i0 - a0) / FT_CH + 2) * 12u + 15u) & ~15u;
+			mbar_expect_tx(&S.mbar, bytes);
+			bulk_g2s(S.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.mbar);
+		}
+		mbar_wait(&S.mbar, parity);
 		parity ^= 1u;
-		__syncthreads();
+		const uint32_t r0 = d0.r0;
+		TileIn in = { S.old, A.V.P + r0, A.V.pre ? A.V.pre + r0 : (const uint32_t*)0, A.V.sc ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
+		              A.V.asym ? A.V.asym + r0 : (const uint8_t*)0, r0 };
+		flat_merge_tile<FT_OUT>(A, S.W, in, tile, d0, d1);
 	}
 }
 

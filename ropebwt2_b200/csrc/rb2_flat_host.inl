@@ -83,7 +83,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 	}
 	f.s[f.cur ^ 1].need(flat_bytes(cap)); f.dir[f.cur ^ 1].need((cap / FT_DIR + 3) * 6);
 	f.tileCnt.need((cap / FT_DIR + 3) * 6);
-	f.tileR0.need(cap / FT_OUT + 4); f.desc.need(cap / FT_OUT + 4); f.ovf.need(cap / FT_OUT + 8);
+	f.desc.need(cap / FT_OUT + 4); f.ovf.need(cap / FT_OUT + 8);
 	if (!f.valid) {
 		f.n = n0;
 		if (n0 > 0) {
@@ -107,17 +107,16 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
 	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
-	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.tileR0.need(nNew / FT_OUT + 4); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
 	ph_begin(e, PH_MERGE);
 	// leanP: all-singleton column without interval sizes -- the records are the state arrays themselves
 	const RecView V = leanP ? RecView{ leanP, 0, 0, e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
-	LAUNCH(e, k_flat_splits, cdiv((uint64_t)nrec + 1, 256), 256, 0, V, nrec, nTiles, f.tileR0.p);
-	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, f.tileR0.p, nTiles, nNew, f.desc.p);
+	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, f.desc.p);
 	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
 	                f.desc.p, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	LAUNCH(e, k_flat_merge, (uint32_t)nTiles, 256, sizeof(FlatSmemT<FT_CAP_SMALL>), fa);
-	LAUNCH(e, k_flat_merge_dense, e->nSM * 3, 256, sizeof(FlatSmemT<FT_OUT>), fa);
+	LAUNCH(e, k_flat_merge, (uint32_t)std::min<uint64_t>(nTiles, (uint64_t)e->nSM * 3), 288, sizeof(FlatPSmem), fa, (uint32_t)nTiles);
+	LAUNCH(e, k_flat_merge_dense, e->nSM * 3, 256, sizeof(FlatDSmemT<FT_OUT>), fa);
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);
@@ -179,7 +178,7 @@ static void release_batch_scratch(rb2_engine *e)
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->strEnd.release(); e->tileA.release(); e->tileB.release(); e->grpCta.release();
 	FlatState &f = e->flat;
-	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.tileR0.release(); f.desc.release(); f.ovf.release();
+	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.desc.release(); f.ovf.release();
 }
 
 // flat array -> leaf blocks: buckets are encoded independently

@@ -237,7 +237,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	uint64_t Gglob = sorted ? 1 : mAll, Mglob = mAll;
 	const int cs = 0; // current state lives in buffer 0; buffer 1 receives a column's output in source order
 	if (e->owner[0] == me) {
-		e->gL[0].need(Gglob); e->gSize[0].need(Gglob); e->gOff[0].need(Gglob + 1); e->sid[0].need(mAll + 4);
+		e->gL[0].need(Gglob + 64); e->gSize[0].need(Gglob + 64); e->gOff[0].need(Gglob + 64); e->sid[0].need(mAll + 64);
 		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
 		G = (uint32_t)Gglob; M = (uint32_t)mAll;
 	}
@@ -254,8 +254,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		// ---- per-column capacity (contents of these buffers are dead here) ---------------------
 		// (a group yields at most one next group and one record per symbol, plus records for counts above the run limit)
 		const size_t gnMax = std::min<uint64_t>(M, 6ull * G);
-		e->gL[1].need(gnMax); e->gSize[1].need(useSizes ? gnMax : 0); e->gOff[1].need(gnMax + 1); e->sid[1].need((size_t)M + 4);
-		e->asym.need((size_t)M + 8);
+		e->gL[1].need(gnMax + 64); e->gSize[1].need(useSizes ? gnMax + 64 : 0); e->gOff[1].need(gnMax + 64); e->sid[1].need((size_t)M + 64);
+		e->asym.need((size_t)M + 64);
 		const size_t recCap = gnMax + M / RB2_MAXRUN + 64;
 		e->recP.need(recCap); e->recSC.need(recCap); e->recDst.need(recCap);
 		if (flat) { e->recPre.need(recCap + 1); shard_dir_offsets(e, e->gtot, true); }
@@ -407,7 +407,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const uint32_t Gn = (uint32_t)curG[me], Mn = (uint32_t)curM[me];
 		const bool singles = GglobN == MglobN;
 		auto exchange_early = [&]() {
-			e->gSize[cs].need(useSizes ? Gn : 0); e->gOff[cs].need((size_t)Gn + 1); e->sid[cs].need((size_t)Mn + 4);
+			e->gSize[cs].need(useSizes ? (size_t)Gn + 64 : 0); e->gOff[cs].need((size_t)Gn + 64); e->sid[cs].need((size_t)Mn + 64);
 			cm->group_begin();
 			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), e->st2);
 			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), e->st2);
@@ -431,7 +431,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			// interval starts: behind the merge, on the second stream -- the next column only needs them when its
 			// records are merged (all-singleton columns) or its groups are scanned
 			RB2_CUDA(cudaEventRecord(e->evMerge, e->st));
-			e->gL[cs].need(Gn);
+			e->gL[cs].need((size_t)Gn + 64);
 			RB2_CUDA(cudaStreamWaitEvent(e->st2, e->evMerge, 0));
 			RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][0], e->st2));
 			cm->group_begin();

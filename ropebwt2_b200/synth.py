@@ -240,13 +240,13 @@ def hash_reads(w: dict, a: int, b: int, device=None):
     return torch.where(sub, (base - 1 + shift) % 4 + 1, base).to(torch.uint8)
 
 
-def stream_lines(w: dict, chunk: int = 2_000_000):
+def stream_lines(w: dict, chunk: int = 2_000_000, threads: int = 2):
     """The workload as `-L` text (one read per line, main.c:180-186), chunk by chunk (bytes)."""
     lib = c_generator()
     for a in range(0, w["n"], chunk):
         b = min(w["n"], a + chunk)
         if lib is not None:
-            yield c_reads(lib, w, a, b, True).tobytes()
+            yield c_reads(lib, w, a, b, True, threads).tobytes()
             continue
         r = hash_reads(w, a, b)
         buf = np.empty((b - a, w["L"] + 1), dtype=np.uint8)

@@ -5,6 +5,7 @@ the oracle's bit for bit, and batches of the two regimes must chain (blocks -> f
 import numpy as np
 import pytest
 
+from conftest import not_on_emu, sz
 from oracle import oracle as orc
 from ropebwt2_b200 import MRope, load
 from ropebwt2_b200.synth import encode_batch, genome_reads, uniform_reads, varlen_reads
@@ -19,9 +20,10 @@ def text(m):
 @pytest.mark.parametrize("so", [0, 1, 2])
 def test_forced_dense_multi_batch(monkeypatch, so):
     monkeypatch.setenv("RB2_FLAT", "1")
-    rd = genome_reads(9000, 60, 13 + so, coverage=40.0)
+    n = sz(9000, 1800)
+    rd = genome_reads(n, sz(60, 40), 13 + so, coverage=40.0)
     o, m = orc.Oracle(so), MRope(so)
-    for part in (rd[:4000], rd[4000:6000], rd[6000:]):
+    for part in (rd[:n * 4 // 9], rd[n * 4 // 9:n * 2 // 3], rd[n * 2 // 3:]):
         buf = encode_batch(part, True, so == 2)
         o.insert_multi(buf)
         m.insert_multi(buf)
@@ -37,7 +39,7 @@ def test_regimes_alternate(monkeypatch, so):
     o, m = orc.Oracle(so), MRope(so)
     for i, seed in enumerate((1, 2, 3, 4)):
         monkeypatch.setenv("RB2_FLAT", "1" if i % 2 == 0 else "0")
-        buf = encode_batch(varlen_reads(1500, 70, seed), True, True)
+        buf = encode_batch(varlen_reads(sz(1500, 300), sz(70, 40), seed), True, True)
         o.insert_multi(buf)
         m.insert_multi(buf)
         assert np.array_equal(text(m), o.text()), (so, i)
@@ -52,6 +54,7 @@ def test_regimes_alternate(monkeypatch, so):
     m.close()
 
 
+@not_on_emu
 def test_auto_choice_and_big_counts(monkeypatch):
     """without RB2_FLAT the engine picks dense for a short-read batch of this size; 300k copies of one
     read give per-symbol counts above the 4-byte run limit (records split, runs longer than a tile)"""
@@ -74,10 +77,10 @@ def test_batched_rank_queries(monkeypatch):
         monkeypatch.setenv("RB2_FLAT", regime)
         o, m = orc.Oracle(1), MRope(1)
         for seed in (3, 4):
-            buf = encode_batch(genome_reads(3000, 70, seed, coverage=30.0))
+            buf = encode_batch(genome_reads(sz(3000, 600), sz(70, 40), seed, coverage=30.0))
             o.insert_multi(buf)
             m.insert_multi(buf)
-        xs = np.concatenate([[0, 1, o.total() - 1, o.total()], rng.integers(0, o.total() + 1, size=3000)])
+        xs = np.concatenate([[0, 1, o.total() - 1, o.total()], rng.integers(0, o.total() + 1, size=sz(3000, 400))])
         got = m.rank_batch(xs)
         for x, g in zip(xs[:300], got[:300]):
             assert np.array_equal(g, o.rank1a(int(x))), (regime, int(x))
@@ -86,3 +89,29 @@ def test_batched_rank_queries(monkeypatch):
         assert (np.diff(got[order], axis=0) >= 0).all()
         assert np.array_equal(got[3], o.counts().sum(0))
         m.close()
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_resident_array_across_batches(monkeypatch, so):
+    """Successive dense batches (the north-star shape: 12 mr_insert_multi calls into one growing index):
+    the flat array stays resident, nothing is decoded in between, non-empty intervals from batch 2 on;
+    leaf blocks are rebuilt only when the iterator asks for them at the end."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    n = sz(24000, 2400)
+    rd = genome_reads(n, sz(60, 40), 23 + so, coverage=40.0)
+    o, m = orc.Oracle(so), MRope(so)
+    for k in range(6):
+        buf = encode_batch(rd[k * n // 6:(k + 1) * n // 6], True, so == 2)
+        o.insert_multi(buf)
+        m.insert_multi(buf)
+        assert np.array_equal(m.counts(), o.counts()), k   # mr_get_c is current after every call
+    assert m.stats()["flat_batches"] == 6
+    assert np.array_equal(text(m), o.text())
+    for x in (0, 1, o.total() // 3, o.total()):
+        assert np.array_equal(m.rank2a(x)[0], o.rank1a(x))
+    # and the array is still usable afterwards
+    buf = encode_batch(uniform_reads(sz(3000, 300), sz(60, 40), 5))
+    o.insert_multi(buf)
+    m.insert_multi(buf)
+    assert np.array_equal(text(m), o.text())
+    m.close()
