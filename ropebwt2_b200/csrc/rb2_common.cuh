@@ -19,7 +19,7 @@
 #ifdef RB2_EMU
 #define RB2_DYN_SMEM(name) uint8_t *name = RB2_EMU_DYN_SMEM
 #define RB2_NAMED_BAR(id, nthreads) rb2emu::named_barrier((id), (nthreads))
-#define RB2_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) rb2emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define RB2_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) rb2emu::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); }, #kernel)
 #else
 #define RB2_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #define RB2_NAMED_BAR(id, nthreads) asm volatile("bar.sync %0, %1;" :: "n"(id), "n"(nthreads) : "memory")

@@ -69,6 +69,7 @@ struct Ctl { // device control block (one per engine), mirrored through pinned h
 	// sharded engines: per-symbol exclusive prefix of next groups / members at the first group of
 	// every bucket (row nb = totals); the differences of two rows are what a bucket sends on
 	uint32_t grpPre[(NBMAX + 1) * 6], memPre[(NBMAX + 1) * 6];
+	uint32_t memTotAB[2][8]; // k_column_fused: members per symbol of this column / of the next one (ping-pong)
 };
 
 struct Dir {
@@ -1845,7 +1846,7 @@ struct rb2_engine {
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
 	int64_t *dRankOut, *hRankOut;
 	// batch scratch
-	DevBuf<uint8_t> sbuf, T, asym, stage;
+	DevBuf<uint8_t> sbuf, T, asym, asym2, stage; DevBuf<uint64_t> look;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
 	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemPieces, itemFirst, itemRest, todo, todoA, scanCta;
 	DevBuf<ItemMeta> itemMeta;
@@ -2093,7 +2094,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
 	dir_free(e->dir[0]); dir_free(e->dir[1]);
-	e->sbuf.release(); e->T.release(); e->asym.release(); e->stage.release();
+	e->sbuf.release(); e->T.release(); e->asym.release(); e->asym2.release(); e->look.release(); e->stage.release();
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recSC.release(); e->recDst.release(); e->recHi.release();
@@ -2250,6 +2251,11 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	const bool useSizes = sorted && n0 > 0;
 	if (useSizes) e->sizes6.need((size_t)m * 6);
 	int cs = 0; // current state buffer
+	// all-singleton columns of a dense batch run as one kernel (k_column_fused): the next symbols travel with the strings
+	static int fusedPref = -1;
+	if (fusedPref < 0) { const char *fp = getenv("RB2_FUSED"); fusedPref = !(fp && *fp == '0'); }
+	bool asymReady = false; int tp = 0; // asym / memTotAB[tp] already hold this column's symbols and their totals
+	uint8_t *asymCur = 0, *asymNxt = 0;
 	LAUNCH(e, k_init_state, cdiv(m, 256), 256, 0, sorted, m, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
 	uint32_t G = sorted ? 1 : m, M = m;
 	uint32_t gBkt[8], mBkt[8];
@@ -2274,26 +2280,43 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		// ---- members: next symbol + tile histograms ---------------------------------
 		ph_begin(e, PH_MEMBERS);
 		const uint32_t nTile = cdiv(M, MEM_TILE);
-		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
-		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
-		TView tv; memset(&tv, 0, sizeof(tv));
-		tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * t_stride(m);
-		LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, e->asym.p, e->tileB.p);
-		run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
+		const bool fused = fusedPref && flat && G == M && m > 1;
+		if (!asymCur) { e->asym2.need((size_t)m + 64); asymCur = e->asym.p; asymNxt = e->asym2.p; }
+		if (!asymReady) {
+			e->tileB.need(((size_t)nTile + 1) * 6 + 8);
+			RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
+			TView tv; memset(&tv, 0, sizeof(tv));
+			tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * t_stride(m);
+			LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, asymCur, e->tileB.p);
+			run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
+			if (fused) RB2_CUDA(cudaMemcpyAsync(e->dctl->memTotAB[tp], e->dctl->memTot, 8 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->st));
+		}
 		ph_end(e, PH_MEMBERS);
 
 		// ---- groups: interval sizes, histograms, records ------------------------------
 		ph_begin(e, PH_GROUPS);
-		if (useSizes) {
+		if (useSizes && !fused) {
 			if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, e->gL[cs].p, e->gSize[cs].p,
 			                 e->sizes6.p, e->dctl, (const int64_t*)0, e->nb);
 			else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
 		}
 		const bool lean = flat && !useSizes && G == M && m > 1;
-		if (G == M) {
+		if (fused) {
+			// every group is a singleton, dense regime: partition + insertion points + next-symbol fetch in one kernel
+			e->look.need((size_t)nTile * CF_NC + 2);
+			RB2_CUDA(cudaMemsetAsync(e->look.p, 0, ((size_t)nTile * CF_NC + 1) * 8, e->st));
+			FusedArgs fa = { e->sid[cs].p, asymCur, M, nTile, col + 1 < ncol ? e->T.p + (size_t)(col + 1) * t_stride(m) : (const uint8_t*)0,
+			                 e->gL[cs].p, e->gSize[cs].p, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, e->dctl, tp,
+			                 e->sid[cs ^ 1].p, asymNxt, e->recDst.p, e->recP.p, e->gSize[cs ^ 1].p,
+			                 e->look.p, reinterpret_cast<uint32_t*>(e->look.p + (size_t)nTile * CF_NC) };
+			if (useSizes) { if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_fused<true, true>), nTile, 256, 0, fa); else LAUNCH(e, (k_column_fused<true, false>), nTile, 256, 0, fa); }
+			else LAUNCH(e, (k_column_fused<false, false>), nTile, 256, 0, fa);
+			ph_end(e, PH_GROUPS);
+			ph_begin(e, PH_MEMBERS2); ph_end(e, PH_MEMBERS2);
+		} else if (G == M) {
 			// every group is a singleton: records, next groups and the partition in one kernel
 			LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[cs ^ 1].p, M, flat ? e->recPre.p : (uint32_t*)0);
-			SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
+			SingleArgs sa = { e->sid[cs].p, asymCur, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
 			                  e->sid[cs ^ 1].p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 			else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
@@ -2302,7 +2325,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		} else {
 			const uint32_t nGC = cdiv(G, 256);
 			e->grpCta.need((size_t)nGC * NGC + NGC);
-			GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
+			GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, asymCur, e->tileB.p, G,
 			                 e->grpCta.p, e->gSize[cs ^ 1].p, e->gOff[cs ^ 1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl, flat ? e->recPre.p : (uint32_t*)0 };
 			if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 			else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
@@ -2313,12 +2336,19 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			ph_end(e, PH_GROUPS);
 
 			ph_begin(e, PH_MEMBERS2);
-			LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[cs ^ 1].p);
+			LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, asymCur, M, e->tileB.p, e->dctl, e->sid[cs ^ 1].p);
 			ph_end(e, PH_MEMBERS2);
 		}
 		ctl_pull(e);
 		ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2) | e->flat.pending);
 		e->flat.pending = 0;
+		if (fused) { // the next column's ranges follow from this column's symbol totals (k_col_bases_single on the host)
+			uint32_t ms = 0;
+			h->gSymBase[0] = h->mSymBase[0] = 0;
+			for (int a = 1; a <= 6; ++a) { h->gSymBase[a] = h->mSymBase[a] = ms; if (a < 6) ms += h->memTotAB[tp][a]; }
+			h->gSymBase[7] = h->mSymBase[7] = ms;
+			h->Gnext = h->Mnext = ms; h->nrec = M;
+		}
 		const uint32_t nrec = h->nrec;
 
 		if (m == 1) { // remember where the string's sentinel goes (mr_insert1's return value)
@@ -2329,7 +2359,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		}
 		const rb2_stats_t before = e->stats;
 		if (flat) {
-			flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p, lean ? e->gL[cs].p : (const int64_t*)0);
+			flat_apply_records(e, nrec, M, e->gL[cs ^ 1].p, fused ? (useSizes ? e->recP.p : e->gL[cs].p) : (lean ? e->gL[cs].p : (const int64_t*)0), asymCur);
 			if (column_log()) { RB2_CUDA(cudaStreamSynchronize(e->st)); ph_collect(e, e->flat.pending); e->flat.pending = 0; } // per-column times
 		} else apply_records(e, nrec, e->gL[cs ^ 1].p);
 		e->stats.n_records += nrec;
@@ -2344,6 +2374,8 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int b = 0; b < 8; ++b) { gBkt[b] = h->gSymBase[b]; mBkt[b] = h->mSymBase[b]; }
 		G = h->Gnext; M = h->Mnext;
 		cs ^= 1;
+		asymReady = fused;
+		if (fused) { std::swap(asymCur, asymNxt); tp ^= 1; }
 	}
 	if (flat) { // the array stays resident; leaf blocks are rebuilt when something asks for them (ensure_blocks)
 		flat_finish(e);

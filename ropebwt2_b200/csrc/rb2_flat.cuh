@@ -541,6 +541,161 @@ __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, c
 	}
 }
 
+// ---- one kernel per all-singleton column -------------------------------------------------------------------
+// Once every group is a single string (always in input order; in the sorted modes as soon as all suffixes read
+// so far are distinct) a column is: partition the strings by their next symbol (mrope.c:303-310), and -- with
+// non-empty intervals, i.e. a sorted mode on a non-empty index -- find each string's insertion point inside
+// its interval (rope_rank2a, mrope.c:199-218).  k_column_fused does all of it in ONE pass over the strings:
+//   * the symbol a string inserts in this column was fetched by the PREVIOUS column's kernel while it moved
+//     the string (asym is stored in string order, so it is read sequentially here), together with the grand
+//     totals per symbol, so every destination index is known from a prefix over the tiles in front;
+//   * that prefix comes from a decoupled look-back over per-tile aggregates (one 64-bit word per counter:
+//     state in the top two bits), tiles taken in ticket order so that the tiles in front are always running;
+//   * the string's NEXT symbol is gathered from the column-major symbol matrix and travels with it.
+// SIZED: the interval [gL, gL+gSize) of the flat array is counted by the string's thread (short intervals) or
+// by its warp from the directory (long ones); the record position goes to recP, the next interval size along.
+#define LB_AGG (1ull << 62)
+#define LB_INC (2ull << 62)
+#define LB_VAL ((1ull << 62) - 1)
+#define CF_NC 12       // counters: [0,6) strings per symbol of this column, [6,12) strings per symbol of the next one
+#define CF_TILE 1024   // strings per CTA (256 threads x 4)
+
+struct FusedArgs {
+	const uint32_t *sid; const uint8_t *asym; uint32_t M, nTile;
+	const uint8_t *Tnext;         // the next column of the symbol matrix (4 bits per symbol), null behind the last column
+	const int64_t *gL, *gSize; const uint8_t *flat; const int64_t *dir; // SIZED
+	Ctl *ctl; int parity;         // ctl->memTotAB[parity] = this column's totals, [parity ^ 1] receives the next column's
+	uint32_t *sidNext; uint8_t *asymNext; uint32_t *recDst; int64_t *recP, *gSizeNext;
+	uint64_t *look; uint32_t *ticket; // [nTile][CF_NC] look-back words and the tile counter, zeroed
+};
+
+template <bool SIZED, bool COMP>
+__global__ void __launch_bounds__(256) k_column_fused(FusedArgs A)
+{
+	__shared__ uint64_t sm[3 * 8];
+	__shared__ uint32_t sTile;
+	__shared__ uint64_t sEx[CF_NC];
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) sTile = atomicAdd(A.ticket, 1u);
+	__syncthreads();
+	const uint32_t t = sTile;
+	const uint32_t k = t * CF_TILE + tid * 4;
+	uint32_t a4 = 0, n4 = 0, id[4] = { 0, 0, 0, 0 };
+	uint32_t c[CF_NC];
+#pragma unroll
+	for (int x = 0; x < CF_NC; ++x) c[x] = 0;
+	if (k < A.M) {
+		a4 = *reinterpret_cast<const uint32_t*>(A.asym + k); // asym is padded to a multiple of 4
+		if (k + 4 <= A.M) { const uint4 v = *reinterpret_cast<const uint4*>(A.sid + k); id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w; }
+		else for (int i = 0; i < 4; ++i) id[i] = k + i < A.M ? A.sid[k + i] : 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) if (k + i < A.M) {
+			const uint32_t a = (a4 >> (8 * i)) & 0xff;
+			uint32_t an = 0;
+			if (a && A.Tnext) an = (A.Tnext[id[i] >> 1] >> ((id[i] & 1) * 4)) & 15u;
+			n4 |= an << (8 * i);
+#pragma unroll
+			for (int x = 0; x < 6; ++x) { c[x] += a == (uint32_t)x; c[6 + x] += (a != 0) && an == (uint32_t)x; }
+		}
+	}
+	// exclusive prefix inside the CTA; a CTA holds 1024 strings, so four counters share one 64-bit word (16 bits each)
+	uint64_t pk[3], pt[3];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) pk[j] = (uint64_t)c[4 * j] | (uint64_t)c[4 * j + 1] << 16 | (uint64_t)c[4 * j + 2] << 32 | (uint64_t)c[4 * j + 3] << 48;
+	cta_excl_scan<3, 256, uint64_t>(pk, pt, sm);
+	uint32_t ex[CF_NC], tot[CF_NC];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+#pragma unroll
+		for (int q = 0; q < 4; ++q) { ex[4 * j + q] = (uint32_t)(pk[j] >> (16 * q)) & 0xffffu; tot[4 * j + q] = (uint32_t)(pt[j] >> (16 * q)) & 0xffffu; }
+	}
+	// publish the tile's aggregate, look back for the prefix over the tiles in front (lane x of warp 0 = counter x)
+	if (wid == 0 && lane < CF_NC) {
+		uint32_t mine = 0;
+#pragma unroll
+		for (int x = 0; x < CF_NC; ++x) if (lane == x) mine = tot[x];
+		volatile uint64_t *lk = A.look;
+		uint64_t acc = 0;
+		if (t == 0) lk[lane] = LB_INC | mine;
+		else {
+			lk[(size_t)t * CF_NC + lane] = LB_AGG | mine;
+			for (uint32_t p = t - 1;; --p) {
+				uint64_t w;
+				do { w = lk[(size_t)p * CF_NC + lane]; } while ((w >> 62) == 0);
+				acc += w & LB_VAL;
+				if ((w >> 62) == 2) break;
+			}
+			lk[(size_t)t * CF_NC + lane] = LB_INC | (acc + mine);
+		}
+		sEx[lane] = acc;
+		if (t == A.nTile - 1 && lane >= 6) A.ctl->memTotAB[A.parity ^ 1][lane - 6] = (uint32_t)(acc + mine); // grand totals of the next column
+	}
+	__syncthreads();
+	if (k >= A.M) return;
+	uint32_t base[6];
+	{
+		uint32_t m = 0;
+		base[0] = 0;
+#pragma unroll
+		for (int x = 1; x < 6; ++x) { base[x] = m + (uint32_t)sEx[x] + ex[x]; m += A.ctl->memTotAB[A.parity][x]; }
+	}
+	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const bool valid = k + i < A.M;
+		const uint32_t g = k + i, a = (a4 >> (8 * i)) & 0xff;
+		uint32_t d = NONE32;
+		if (valid) {
+#pragma unroll
+			for (int x = 1; x < 6; ++x) if (a == (uint32_t)x) d = base[x]++;
+		}
+		if (SIZED) {
+			int64_t P = valid ? A.gL[g] : 0, sza = 0;
+			const int64_t sz = valid ? A.gSize[g] : 0;
+			if (sz > 0 && sz <= FT_SHORT_IV) {
+				Raw6 acc = { 0, 0, 0, 0, 0, 0 };
+				uint64_t p = (uint64_t)P; const uint64_t end = p + (uint64_t)sz;
+				while (p < end) {
+					const uint32_t lo = (uint32_t)(p & (FT_CH - 1));
+					const uint32_t n = end - p < FT_CH - lo ? (uint32_t)(end - p) : FT_CH - lo;
+					raw_addto(acc, raw_of_cell(cell_load(reinterpret_cast<const uint32_t*>(A.flat) + (p / FT_CH) * 3), low_mask(n) << lo, n));
+					p += n;
+				}
+#pragma unroll
+				for (int slot = 0; slot < 6; ++slot) { // insertion point: behind the old symbols of the earlier slots
+					const uint32_t z = raw_symbol(acc, (uint32_t)ord[slot]);
+					if ((uint32_t)ord[slot] == a) { sza = z; break; }
+					P += z;
+				}
+			}
+			uint32_t todo = __ballot_sync(FULLMASK, sz > FT_SHORT_IV);
+			while (todo) { // long intervals: the whole warp, from the directory
+				const int src = __ffs(todo) - 1; todo &= todo - 1;
+				const int64_t L = __shfl_sync(FULLMASK, P, src), szv = __shfl_sync(FULLMASK, sz, src);
+				int64_t cl[6], cu[6];
+				flat_rank6(A.flat, A.dir, L, lane, cl);
+				flat_rank6(A.flat, A.dir, L + szv, lane, cu);
+				if (lane == src) {
+#pragma unroll
+					for (int slot = 0; slot < 6; ++slot) {
+						const int64_t z = cu[ord[slot]] - cl[ord[slot]];
+						if ((uint32_t)ord[slot] == a) { sza = z; break; }
+						P += z;
+					}
+				}
+			}
+			if (valid) {
+				A.recP[g] = P;
+				if (a) A.gSizeNext[d] = sza;
+			}
+		}
+		if (valid) {
+			if (a) { A.sidNext[d] = id[i]; A.asymNext[d] = (uint8_t)((n4 >> (8 * i)) & 0xff); }
+			A.recDst[g] = d;
+		}
+	}
+}
+
 // per-bucket symbol totals of the array: out[k][a] = occ(a, pos[k]) for up to 64 positions (one warp each)
 __global__ void __launch_bounds__(32) k_flat_rank_at(const uint8_t *flat, const int64_t *dir, const int64_t *pos, int64_t *out)
 {

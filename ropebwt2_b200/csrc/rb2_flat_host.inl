@@ -101,7 +101,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 }
 
 // one column: merge nrec records (inserting `inserted` symbols) into the flat array
-static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0)
+static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0, const uint8_t *asym = 0)
 {
 	FlatState &f = e->flat;
 	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
@@ -109,8 +109,8 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
 	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
 	ph_begin(e, PH_MERGE);
-	// leanP: all-singleton column without interval sizes -- the records are the state arrays themselves
-	const RecView V = leanP ? RecView{ leanP, 0, 0, e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
+	// leanP: all-singleton column -- the records are the state arrays themselves (position = leanP[r], symbol = asym[r], count 1, r symbols in front)
+	const RecView V = leanP ? RecView{ leanP, 0, 0, asym ? asym : e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
 	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, f.desc.p);
 	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,

@@ -5,6 +5,9 @@
 #undef gridDim
 #undef threadIdx
 #include <sys/mman.h>
+#include <signal.h>
+#include <execinfo.h>
+#include <unistd.h>
 
 namespace rb2emu {
 
@@ -95,8 +98,36 @@ struct StackPool {
 static thread_local StackPool pool;
 static thread_local std::vector<unsigned char> dynbuf;
 
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body)
+static thread_local const char *cur_kernel = 0;
+static void on_segv(int sig)
 {
+	char msg[512];
+	Cta *c = cta;
+	int n = snprintf(msg, sizeof(msg), "[cuda_emu] signal %d in kernel %s, block (%u,%u,%u), thread %u\n", sig, cur_kernel ? cur_kernel : "(host code)",
+	                 c ? c->bidx.x : 0, c ? c->bidx.y : 0, c ? c->bidx.z : 0, cur_threadIdx.x);
+	if (write(2, msg, n) < 0) {}
+	void *bt[32];
+	int k = backtrace(bt, 32);
+	backtrace_symbols_fd(bt, k, 2);
+	_exit(139);
+}
+static void install_handler()
+{
+	static bool done = false;
+	if (done) return;
+	done = true;
+	static char altstack[1 << 16];
+	stack_t ss; ss.ss_sp = altstack; ss.ss_size = sizeof(altstack); ss.ss_flags = 0;
+	sigaltstack(&ss, 0);
+	struct sigaction sa; memset(&sa, 0, sizeof(sa));
+	sa.sa_handler = on_segv; sa.sa_flags = SA_ONSTACK;
+	sigaction(SIGSEGV, &sa, 0); sigaction(SIGBUS, &sa, 0);
+}
+
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body, const char *name)
+{
+	install_handler();
+	cur_kernel = name;
 	if (cta) { fprintf(stderr, "[cuda_emu] nested launch\n"); abort(); }
 	const unsigned nt = block.x * block.y * block.z;
 	if (nt == 0 || nt > 1024) { fprintf(stderr, "[cuda_emu] bad block size %u\n", nt); abort(); }
@@ -133,6 +164,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &bod
 		}
 	}
 	cta = 0;
+	cur_kernel = 0;
 }
 
 } // namespace rb2emu

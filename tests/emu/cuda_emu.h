@@ -79,7 +79,7 @@ extern thread_local Cta *cta;            // the CTA running on this host thread
 extern thread_local dim3 cur_threadIdx;
 
 void yield();                             // fibre -> scheduler
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body);
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body, const char *name = "?");
 unsigned live_in_mask(unsigned warp, unsigned mask);
 
 inline void bar_wait(Bar &b, unsigned expected_fn(void*), void *arg)
