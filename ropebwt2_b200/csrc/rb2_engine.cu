@@ -69,7 +69,6 @@ struct Ctl { // device control block (one per engine), mirrored through pinned h
 	// sharded engines: per-symbol exclusive prefix of next groups / members at the first group of
 	// every bucket (row nb = totals); the differences of two rows are what a bucket sends on
 	uint32_t grpPre[(NBMAX + 1) * 6], memPre[(NBMAX + 1) * 6];
-	uint32_t memTotAB[2][8]; // k_column_fused: members per symbol of this column / of the next one (ping-pong)
 };
 
 struct Dir {
@@ -119,11 +118,12 @@ __global__ void __launch_bounds__(256) k_string_ends(const uint8_t *s, int64_t l
 	for (int i = 0; i < 16; ++i) if (b[i] == 0) strEnd[k++] = off + i;
 }
 
-__global__ void k_maxlen(const int64_t *strEnd, uint32_t m, unsigned long long *maxlen)
+// (strings kBase .. kBase+m-1 of the batch: a batch whose symbol matrix would not fit is processed in ranges)
+__global__ void k_maxlen(const int64_t *strEnd, uint32_t kBase, uint32_t m, unsigned long long *maxlen)
 {
 	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned long long l = 0;
-	if (k < m) l = (unsigned long long)(strEnd[k] - (k ? strEnd[k-1] + 1 : 0));
+	if (k < m) { k += kBase; l = (unsigned long long)(strEnd[k] - (k ? strEnd[k-1] + 1 : 0)); }
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(FULLMASK, l, o); l = y > l ? y : l; }
 	if ((threadIdx.x & 31) == 0 && l) atomicMax(maxlen, l);
@@ -136,7 +136,7 @@ __global__ void k_maxlen(const int64_t *strEnd, uint32_t m, unsigned long long *
 // [4 symbols][string] words, and half a warp stores the same symbol of 128 consecutive strings (64 bytes).
 #define TR_S 128
 __host__ __device__ __forceinline__ uint64_t t_stride(uint64_t m) { return (((m + 1) >> 1) + 15) & ~(uint64_t)15; }
-__global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64_t *strEnd, uint32_t m, int64_t ncol, uint8_t *T)
+__global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64_t *strEnd, uint32_t kBase, uint32_t m, int64_t ncol, uint8_t *T)
 {
 	__shared__ __align__(16) uint32_t tile[8][TR_S + 4];
 	__shared__ int64_t sStart[TR_S];
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) k_transpose(const uint8_t *s, const int64
 	if (tid < TR_S) {
 		const uint32_t k = k0 + tid;
 		int64_t st = 0; int32_t ln = -1;
-		if (k < m) { st = k ? strEnd[k-1] + 1 : 0; ln = (int32_t)(strEnd[k] - st); }
+		if (k < m) { const uint32_t kk = kBase + k; st = kk ? strEnd[kk-1] + 1 : 0; ln = (int32_t)(strEnd[kk] - st); }
 		sStart[tid] = st; sLen[tid] = ln;
 		atomicMax(&sMax, ln);
 	}
@@ -1846,7 +1846,7 @@ struct rb2_engine {
 	Ctl *dctl, *hctl;   // device control block and its pinned host mirror
 	int64_t *dRankOut, *hRankOut;
 	// batch scratch
-	DevBuf<uint8_t> sbuf, T, asym, asym2, stage; DevBuf<uint64_t> look;
+	DevBuf<uint8_t> sbuf, T, asym, asym2, stage;
 	DevBuf<int64_t> strEnd, gL[2], gSize[2], sizes6, recP, stageCnt;
 	DevBuf<uint32_t> gOff[2], sid[2], tileA, tileB, grpCta, recSC, recDst, recHi, itemOff, itemPieces, itemFirst, itemRest, todo, todoA, scanCta;
 	DevBuf<ItemMeta> itemMeta;
@@ -2094,7 +2094,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
 	dir_free(e->dir[0]); dir_free(e->dir[1]);
-	e->sbuf.release(); e->T.release(); e->asym.release(); e->asym2.release(); e->look.release(); e->stage.release();
+	e->sbuf.release(); e->T.release(); e->asym.release(); e->asym2.release(); e->stage.release();
 	e->strEnd.release(); e->sizes6.release(); e->recP.release(); e->stageCnt.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->tileA.release(); e->tileB.release(); e->grpCta.release(); e->recSC.release(); e->recDst.release(); e->recHi.release();
@@ -2199,10 +2199,11 @@ static FILE *column_log(void)
 	return f;
 }
 
+static void insert_string_range(rb2_engine *e, const uint8_t *s, uint32_t kBase, uint32_t m);
+
 // One sub-batch whose strings already sit in device memory at `s` (len bytes, ends with NUL).
 static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 {
-	const int sorted = e->so != RB2_SO_IO;
 	// ---- split into strings, transpose -------------------------------------------------
 	ph_begin(e, PH_TRANSPOSE);
 	const uint32_t nT = cdiv(len, 4096);
@@ -2216,20 +2217,47 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (m == 0) RB2_FATAL("batch holds no terminated string");
 	e->strEnd.need(m);
 	LAUNCH(e, k_string_ends, nT, 256, 0, s, len, e->tileA.p, e->strEnd.p);
-	RB2_CUDA(cudaMemsetAsync(e->dMaxLen, 0, 8, e->st));
-	LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, m, e->dMaxLen);
-	unsigned long long maxlen = 0;
-	RB2_CUDA(cudaMemcpyAsync(&maxlen, e->dMaxLen, 8, cudaMemcpyDeviceToHost, e->st));
+	ph_end(e, PH_TRANSPOSE);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
-	const int64_t ncol = (int64_t)maxlen + 1;
+	ph_collect(e, 1u << PH_TRANSPOSE);
+	insert_string_range(e, s, 0, m);
+	e->stats.n_symbols += len;
+}
+
+// Strings kBase .. kBase+m-1 of the batch at `s` (string ends in e->strEnd).  The per-batch state is a dense
+// rectangle of (longest string + 1) columns x m strings: when one long string among many short ones (or a
+// long-read batch) would make it far larger than the strings themselves, or larger than the free memory, the
+// range is cut in two and the halves are inserted one after the other -- the BWT does not depend on how a
+// batch is cut, and the reference accepts any mix of lengths.
+static void insert_string_range(rb2_engine *e, const uint8_t *s, uint32_t kBase, uint32_t m)
+{
+	const int sorted = e->so != RB2_SO_IO;
+	ph_begin(e, PH_TRANSPOSE);
+	RB2_CUDA(cudaMemsetAsync(e->dMaxLen, 0, 8, e->st));
+	LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, kBase, m, e->dMaxLen);
+	unsigned long long maxlen = 0;
+	int64_t ends[2] = { -1, 0 };
+	RB2_CUDA(cudaMemcpyAsync(&maxlen, e->dMaxLen, 8, cudaMemcpyDeviceToHost, e->st));
+	if (kBase) RB2_CUDA(cudaMemcpyAsync(&ends[0], e->strEnd.p + kBase - 1, 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaMemcpyAsync(&ends[1], e->strEnd.p + kBase + m - 1, 8, cudaMemcpyDeviceToHost, e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	const int64_t ncol = (int64_t)maxlen + 1, len = ends[1] - ends[0];
 	{
 		size_t freeB = 0, totB = 0;
 		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-		if ((size_t)ncol * t_stride(m) > e->T.cap && (size_t)ncol * t_stride(m) > freeB + e->T.cap)
-			RB2_FATAL("column-major symbol matrix (%lld columns x %u strings) does not fit in HBM", (long long)ncol, m);
+		const size_t need = (size_t)ncol * t_stride(m);
+		const bool tooBig = need > e->T.cap && need > (freeB + e->T.cap) / 2;
+		const bool wasteful = need > (size_t)8 * (size_t)len + ((size_t)64 << 20); // the matrix holds 4 bits per symbol: > 16x padding
+		if ((tooBig || wasteful) && m > 1) {
+			ph_end(e, PH_TRANSPOSE);
+			insert_string_range(e, s, kBase, m / 2);
+			insert_string_range(e, s, kBase + m / 2, m - m / 2);
+			return;
+		}
+		if (tooBig) RB2_FATAL("one string of %lld symbols does not fit in HBM as a column-major symbol matrix", (long long)maxlen);
 	}
 	e->T.need((size_t)ncol * t_stride(m) + 16);
-	LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, m, ncol, e->T.p);
+	LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, kBase, m, ncol, e->T.p);
 	ph_end(e, PH_TRANSPOSE);
 
 	// ---- state for column 0 (mrope.c:279-285) -------------------------------------------
@@ -2254,7 +2282,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	// all-singleton columns of a dense batch run as one kernel (k_column_fused): the next symbols travel with the strings
 	static int fusedPref = -1;
 	if (fusedPref < 0) { const char *fp = getenv("RB2_FUSED"); fusedPref = !(fp && *fp == '0'); }
-	bool asymReady = false; int tp = 0; // asym / memTotAB[tp] already hold this column's symbols and their totals
+	bool asymReady = false; // asymCur already holds this column's symbols (fetched by the previous column's kernel)
 	uint8_t *asymCur = 0, *asymNxt = 0;
 	LAUNCH(e, k_init_state, cdiv(m, 256), 256, 0, sorted, m, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
 	uint32_t G = sorted ? 1 : m, M = m;
@@ -2282,15 +2310,14 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const uint32_t nTile = cdiv(M, MEM_TILE);
 		const bool fused = fusedPref && flat && G == M && m > 1;
 		if (!asymCur) { e->asym2.need((size_t)m + 64); asymCur = e->asym.p; asymNxt = e->asym2.p; }
+		e->tileB.need(((size_t)nTile + 1) * 6 + 8);
+		RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
 		if (!asymReady) {
-			e->tileB.need(((size_t)nTile + 1) * 6 + 8);
-			RB2_CUDA(cudaMemsetAsync(e->tileB.p + (size_t)nTile * 6, 0, 24, e->st)); // terminal entry -> totals
 			TView tv; memset(&tv, 0, sizeof(tv));
 			tv.n = 1; tv.off[1] = m; tv.col[0] = e->T.p + (size_t)col * t_stride(m);
 			LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, asymCur, e->tileB.p);
-			run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
-			if (fused) RB2_CUDA(cudaMemcpyAsync(e->dctl->memTotAB[tp], e->dctl->memTot, 8 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->st));
-		}
+		} else LAUNCH(e, k_tile_hist, nTile, 256, 0, asymCur, M, e->tileB.p); // the symbols came with the strings
+		run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 		ph_end(e, PH_MEMBERS);
 
 		// ---- groups: interval sizes, histograms, records ------------------------------
@@ -2303,12 +2330,9 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const bool lean = flat && !useSizes && G == M && m > 1;
 		if (fused) {
 			// every group is a singleton, dense regime: partition + insertion points + next-symbol fetch in one kernel
-			e->look.need((size_t)nTile * CF_NC + 2);
-			RB2_CUDA(cudaMemsetAsync(e->look.p, 0, ((size_t)nTile * CF_NC + 1) * 8, e->st));
-			FusedArgs fa = { e->sid[cs].p, asymCur, M, nTile, col + 1 < ncol ? e->T.p + (size_t)(col + 1) * t_stride(m) : (const uint8_t*)0,
-			                 e->gL[cs].p, e->gSize[cs].p, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, e->dctl, tp,
-			                 e->sid[cs ^ 1].p, asymNxt, e->recDst.p, e->recP.p, e->gSize[cs ^ 1].p,
-			                 e->look.p, reinterpret_cast<uint32_t*>(e->look.p + (size_t)nTile * CF_NC) };
+			FusedArgs fa = { e->sid[cs].p, asymCur, M, e->tileB.p, col + 1 < ncol ? e->T.p + (size_t)(col + 1) * t_stride(m) : (const uint8_t*)0,
+			                 e->gL[cs].p, e->gSize[cs].p, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, e->dctl,
+			                 e->sid[cs ^ 1].p, asymNxt, e->recDst.p, e->recP.p, e->gSize[cs ^ 1].p };
 			if (useSizes) { if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_fused<true, true>), nTile, 256, 0, fa); else LAUNCH(e, (k_column_fused<true, false>), nTile, 256, 0, fa); }
 			else LAUNCH(e, (k_column_fused<false, false>), nTile, 256, 0, fa);
 			ph_end(e, PH_GROUPS);
@@ -2345,7 +2369,7 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		if (fused) { // the next column's ranges follow from this column's symbol totals (k_col_bases_single on the host)
 			uint32_t ms = 0;
 			h->gSymBase[0] = h->mSymBase[0] = 0;
-			for (int a = 1; a <= 6; ++a) { h->gSymBase[a] = h->mSymBase[a] = ms; if (a < 6) ms += h->memTotAB[tp][a]; }
+			for (int a = 1; a <= 6; ++a) { h->gSymBase[a] = h->mSymBase[a] = ms; if (a < 6) ms += h->memTot[a]; }
 			h->gSymBase[7] = h->mSymBase[7] = ms;
 			h->Gnext = h->Mnext = ms; h->nrec = M;
 		}
@@ -2375,14 +2399,13 @@ static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		G = h->Gnext; M = h->Mnext;
 		cs ^= 1;
 		asymReady = fused;
-		if (fused) { std::swap(asymCur, asymNxt); tp ^= 1; }
+		if (fused) std::swap(asymCur, asymNxt);
 	}
 	if (flat) { // the array stays resident; leaf blocks are rebuilt when something asks for them (ensure_blocks)
 		flat_finish(e);
 		++e->stats.flat_batches;
 	} else pull_totals(e);
 	e->stats.n_strings += m;
-	e->stats.n_symbols += len;
 	e->stats.pool_blocks = e->hctl->poolUsed;
 	e->stats.pool_capacity = e->poolCap;
 }

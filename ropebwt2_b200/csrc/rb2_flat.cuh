@@ -547,43 +547,58 @@ __global__ void __launch_bounds__(128) k_flat_rank_groups(const uint8_t *flat, c
 // non-empty intervals, i.e. a sorted mode on a non-empty index -- find each string's insertion point inside
 // its interval (rope_rank2a, mrope.c:199-218).  k_column_fused does all of it in ONE pass over the strings:
 //   * the symbol a string inserts in this column was fetched by the PREVIOUS column's kernel while it moved
-//     the string (asym is stored in string order, so it is read sequentially here), together with the grand
-//     totals per symbol, so every destination index is known from a prefix over the tiles in front;
-//   * that prefix comes from a decoupled look-back over per-tile aggregates (one 64-bit word per counter:
-//     state in the top two bits), tiles taken in ticket order so that the tiles in front are always running;
+//     the string (asym is stored in string order, so it is read sequentially here); k_tile_hist + one small scan
+//     give the per-tile prefixes and the grand totals per symbol, from which every destination index follows;
 //   * the string's NEXT symbol is gathered from the column-major symbol matrix and travels with it.
 // SIZED: the interval [gL, gL+gSize) of the flat array is counted by the string's thread (short intervals) or
 // by its warp from the directory (long ones); the record position goes to recP, the next interval size along.
-#define LB_AGG (1ull << 62)
-#define LB_INC (2ull << 62)
-#define LB_VAL ((1ull << 62) - 1)
-#define CF_NC 12       // counters: [0,6) strings per symbol of this column, [6,12) strings per symbol of the next one
-#define CF_TILE 1024   // strings per CTA (256 threads x 4)
+#define CF_TILE 1024   // strings per CTA (256 threads x 4) = MEM_TILE
+
+// per-tile histogram of the symbols of this column: tileTot[tile][6]
+__global__ void __launch_bounds__(256) k_tile_hist(const uint8_t *asym, uint32_t M, uint32_t *tileTot)
+{
+	__shared__ uint32_t sm[6 * 8];
+	const uint32_t k = blockIdx.x * CF_TILE + threadIdx.x * 4;
+	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 };
+	if (k < M) {
+		const uint32_t a4 = *reinterpret_cast<const uint32_t*>(asym + k); // asym is padded to a multiple of 4
+#pragma unroll
+		for (int i = 0; i < 4; ++i) if (k + i < M) {
+			const uint32_t a = (a4 >> (8 * i)) & 0xff;
+#pragma unroll
+			for (int x = 0; x < 6; ++x) c[x] += a == (uint32_t)x;
+		}
+	}
+#pragma unroll
+	for (int x = 0; x < 6; ++x) {
+		const uint32_t t = warp_redux_add(c[x]);
+		if ((threadIdx.x & 31) == 0) sm[x * 8 + (threadIdx.x >> 5)] = t;
+	}
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		uint32_t t = 0;
+		for (int w = 0; w < 8; ++w) t += sm[threadIdx.x * 8 + w];
+		tileTot[(size_t)blockIdx.x * 6 + threadIdx.x] = t;
+	}
+}
 
 struct FusedArgs {
-	const uint32_t *sid; const uint8_t *asym; uint32_t M, nTile;
+	const uint32_t *sid; const uint8_t *asym; uint32_t M;
+	const uint32_t *tilePre;      // exclusive prefix of k_tile_hist's rows; ctl->memTot = the grand totals
 	const uint8_t *Tnext;         // the next column of the symbol matrix (4 bits per symbol), null behind the last column
 	const int64_t *gL, *gSize; const uint8_t *flat; const int64_t *dir; // SIZED
-	Ctl *ctl; int parity;         // ctl->memTotAB[parity] = this column's totals, [parity ^ 1] receives the next column's
+	const Ctl *ctl;
 	uint32_t *sidNext; uint8_t *asymNext; uint32_t *recDst; int64_t *recP, *gSizeNext;
-	uint64_t *look; uint32_t *ticket; // [nTile][CF_NC] look-back words and the tile counter, zeroed
 };
 
 template <bool SIZED, bool COMP>
 __global__ void __launch_bounds__(256) k_column_fused(FusedArgs A)
 {
-	__shared__ uint64_t sm[3 * 8];
-	__shared__ uint32_t sTile;
-	__shared__ uint64_t sEx[CF_NC];
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) sTile = atomicAdd(A.ticket, 1u);
-	__syncthreads();
-	const uint32_t t = sTile;
-	const uint32_t k = t * CF_TILE + tid * 4;
+	__shared__ uint64_t sm[2 * 8];
+	const int lane = threadIdx.x & 31;
+	const uint32_t k = blockIdx.x * CF_TILE + threadIdx.x * 4;
 	uint32_t a4 = 0, n4 = 0, id[4] = { 0, 0, 0, 0 };
-	uint32_t c[CF_NC];
-#pragma unroll
-	for (int x = 0; x < CF_NC; ++x) c[x] = 0;
+	uint32_t c[6] = { 0, 0, 0, 0, 0, 0 };
 	if (k < A.M) {
 		a4 = *reinterpret_cast<const uint32_t*>(A.asym + k); // asym is padded to a multiple of 4
 		if (k + 4 <= A.M) { const uint4 v = *reinterpret_cast<const uint4*>(A.sid + k); id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w; }
@@ -591,53 +606,25 @@ __global__ void __launch_bounds__(256) k_column_fused(FusedArgs A)
 #pragma unroll
 		for (int i = 0; i < 4; ++i) if (k + i < A.M) {
 			const uint32_t a = (a4 >> (8 * i)) & 0xff;
-			uint32_t an = 0;
-			if (a && A.Tnext) an = (A.Tnext[id[i] >> 1] >> ((id[i] & 1) * 4)) & 15u;
-			n4 |= an << (8 * i);
+			if (a && A.Tnext) n4 |= ((A.Tnext[id[i] >> 1] >> ((id[i] & 1) * 4)) & 15u) << (8 * i);
 #pragma unroll
-			for (int x = 0; x < 6; ++x) { c[x] += a == (uint32_t)x; c[6 + x] += (a != 0) && an == (uint32_t)x; }
+			for (int x = 0; x < 6; ++x) c[x] += a == (uint32_t)x;
 		}
 	}
-	// exclusive prefix inside the CTA; a CTA holds 1024 strings, so four counters share one 64-bit word (16 bits each)
-	uint64_t pk[3], pt[3];
-#pragma unroll
-	for (int j = 0; j < 3; ++j) pk[j] = (uint64_t)c[4 * j] | (uint64_t)c[4 * j + 1] << 16 | (uint64_t)c[4 * j + 2] << 32 | (uint64_t)c[4 * j + 3] << 48;
-	cta_excl_scan<3, 256, uint64_t>(pk, pt, sm);
-	uint32_t ex[CF_NC], tot[CF_NC];
-#pragma unroll
-	for (int j = 0; j < 3; ++j) {
-#pragma unroll
-		for (int q = 0; q < 4; ++q) { ex[4 * j + q] = (uint32_t)(pk[j] >> (16 * q)) & 0xffffu; tot[4 * j + q] = (uint32_t)(pt[j] >> (16 * q)) & 0xffffu; }
-	}
-	// publish the tile's aggregate, look back for the prefix over the tiles in front (lane x of warp 0 = counter x)
-	if (wid == 0 && lane < CF_NC) {
-		uint32_t mine = 0;
-#pragma unroll
-		for (int x = 0; x < CF_NC; ++x) if (lane == x) mine = tot[x];
-		volatile uint64_t *lk = A.look;
-		uint64_t acc = 0;
-		if (t == 0) lk[lane] = LB_INC | mine;
-		else {
-			lk[(size_t)t * CF_NC + lane] = LB_AGG | mine;
-			for (uint32_t p = t - 1;; --p) {
-				uint64_t w;
-				do { w = lk[(size_t)p * CF_NC + lane]; } while ((w >> 62) == 0);
-				acc += w & LB_VAL;
-				if ((w >> 62) == 2) break;
-			}
-			lk[(size_t)t * CF_NC + lane] = LB_INC | (acc + mine);
-		}
-		sEx[lane] = acc;
-		if (t == A.nTile - 1 && lane >= 6) A.ctl->memTotAB[A.parity ^ 1][lane - 6] = (uint32_t)(acc + mine); // grand totals of the next column
-	}
-	__syncthreads();
+	// exclusive prefix inside the CTA; a CTA holds 1024 strings, so counters share 64-bit words (16 bits each)
+	uint64_t pk[2] = { (uint64_t)c[1] | (uint64_t)c[2] << 16 | (uint64_t)c[3] << 32 | (uint64_t)c[4] << 48, (uint64_t)c[5] }, pt[2];
+	cta_excl_scan<2, 256, uint64_t>(pk, pt, sm);
 	if (k >= A.M) return;
 	uint32_t base[6];
 	{
 		uint32_t m = 0;
 		base[0] = 0;
 #pragma unroll
-		for (int x = 1; x < 6; ++x) { base[x] = m + (uint32_t)sEx[x] + ex[x]; m += A.ctl->memTotAB[A.parity][x]; }
+		for (int x = 1; x < 6; ++x) {
+			const uint32_t ex = x < 5 ? (uint32_t)(pk[0] >> (16 * (x - 1))) & 0xffffu : (uint32_t)pk[1];
+			base[x] = m + A.tilePre[(size_t)blockIdx.x * 6 + x] + ex;
+			m += A.ctl->memTot[x];
+		}
 	}
 	constexpr int ord[6] = { 0, COMP ? 4 : 1, COMP ? 3 : 2, COMP ? 2 : 3, COMP ? 1 : 4, 5 }; // mrope.c:209-210
 #pragma unroll

@@ -186,7 +186,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		e->strEnd.need(m);
 		LAUNCH(e, k_string_ends, nT, 256, 0, s, len, e->tileA.p, e->strEnd.p);
 		RB2_CUDA(cudaMemsetAsync(e->dMaxLen, 0, 8, e->st));
-		LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, m, e->dMaxLen);
+		LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, 0u, m, e->dMaxLen);
 		RB2_CUDA(cudaMemcpyAsync(&maxlen, e->dMaxLen, 8, cudaMemcpyDeviceToHost, e->st));
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 	}
@@ -211,7 +211,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			RB2_FATAL("replicated symbol matrices (%.1f GB) do not fit in HBM", tBytes * 1e-9);
 	}
 	e->T.need(tBytes + 16);
-	if (m) LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
+	if (m) LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, 0u, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
 	{
 		uint8_t *dst[RB2_MAX_RANKS]; size_t bytes[RB2_MAX_RANKS];
 		for (int r = 0; r < P; ++r) { dst[r] = e->T.p + tOff[r]; bytes[r] = t_stride(all[r].m) * all[r].ncol; }

@@ -310,3 +310,17 @@ def test_reference_driver_on_our_library(tmp_path):
     out, _ = orc.ref_cli(["-i", fmr, "/dev/null"])
     want, _ = orc.ref_cli(["-LRs", "-"], lines)
     assert out == want
+
+
+@pytest.mark.parametrize("so", [0, 1])
+def test_one_long_string_among_short_ones(so):
+    """A length outlier must not blow up the per-batch state: the engine cuts such a batch into
+    string ranges; the reference accepts any mix of lengths, and the BWT does not depend on the cut."""
+    rng = np.random.default_rng(77)
+    short = [rng.integers(1, 5, size=int(rng.integers(5, 40))).astype(np.uint8) for _ in range(sz(3000, 400))]
+    contig = rng.integers(1, 5, size=sz(3_000_000, 2_500)).astype(np.uint8)
+    strs = short[:len(short) // 3] + [contig] + short[len(short) // 3:]
+    o, m = build_both(so, [encode_batch(strs)])
+    assert np.array_equal(m.counts(), o.counts())
+    assert np.array_equal(gpu_text(m), o.text())
+    m.close()
