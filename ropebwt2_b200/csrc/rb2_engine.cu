@@ -2039,8 +2039,9 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatDSmemT<FT_OUT>)));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FlatPSmem)));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceDenseSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem<true>))));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem<false>))));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);

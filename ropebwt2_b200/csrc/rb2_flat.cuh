@@ -104,27 +104,28 @@ struct RecView {
 	__device__ __forceinline__ uint64_t Key(uint32_t r) const { return (uint64_t)P[r] + Pre(r); }
 };
 
-// ---- tile geometry ---------------------------------------------------------------------------------------
-// One thread per tile boundary t (output position min(t*FT_OUT, nNew)): the first record whose output run
+// ---- slice geometry ----------------------------------------------------------------------------------------
+// The unit of work of the merge is a SLICE: FS_SLICE = FT_DIR output symbols, produced by one warp.  One
+// thread per slice boundary t (output position min(t*FS_SLICE, nNew)): the first record whose output run
 // starts at or behind it (bisection over the strictly increasing keys key_r = P_r + pre_r), the first old
-// symbol that lands at or behind it, and the record run that reaches across it from the left.  Computed
-// ahead of k_flat_merge so that its CTAs start with two independent loads.
-struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FT_OUT) << 3 | symbol
+// symbol that lands at or behind it, and the record run that reaches across it from the left.
+#define FS_SLICE FT_DIR
+struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FS_SLICE) << 3 | symbol
 
-__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nTiles, uint64_t nNew, TileDesc *desc)
+__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, TileDesc *desc)
 {
 	const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-	if (t > nTiles) return;
-	const uint64_t o0 = t * FT_OUT < nNew ? t * FT_OUT : nNew;
-	uint32_t lo = 0, hi = R; // first r with Key(r) >= t*FT_OUT (R if none)
-	if (t == nTiles) lo = R;
-	while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (V.Key(mid) >= t * FT_OUT) hi = mid; else lo = mid + 1; }
+	if (t > nSlices) return;
+	const uint64_t o0 = t * FS_SLICE < nNew ? t * FS_SLICE : nNew;
+	uint32_t lo = 0, hi = R; // first r with Key(r) >= t*FS_SLICE (R if none)
+	if (t == nSlices) lo = R;
+	while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (V.Key(mid) >= t * FS_SLICE) hi = mid; else lo = mid + 1; }
 	const uint32_t r0 = lo;
 	uint64_t before = 0; uint32_t carry = 0;
 	if (r0 > 0) {
 		const uint64_t pre = V.Pre(r0 - 1), key = (uint64_t)V.P[r0 - 1] + pre; const uint32_t sc = V.SC(r0 - 1);
 		const uint64_t end = key + (sc >> 3);
-		if (end > o0) { before = pre + (o0 - key); const uint64_t rem = end - o0; carry = (uint32_t)(rem < FT_OUT ? rem : FT_OUT) << 3 | (sc & 7u); }
+		if (end > o0) { before = pre + (o0 - key); const uint64_t rem = end - o0; carry = (uint32_t)(rem < FS_SLICE ? rem : FS_SLICE) << 3 | (sc & 7u); }
 		else before = pre + (sc >> 3);
 	}
 	TileDesc d; d.i0 = o0 - before; d.r0 = r0; d.carry = carry;
@@ -135,194 +136,179 @@ struct FlatArgs {
 	const uint8_t *oldS; const int64_t *oldDir;   // old array, counts in front of every FT_DIR-th old symbol
 	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its per-FT_DIR-tile symbol counts
 	RecView V; const uint32_t *recDst; uint32_t R;
-	const TileDesc *desc;
-	uint32_t *ovf;           // [0] tiles left to k_flat_merge_dense, [1] its work counter, [2..] the tiles
+	const TileDesc *desc; uint32_t nSlices;
+	uint32_t *ovf;           // [0] slices left to k_flat_merge_dense, [1] its work counter, [2..] the slices
 	int64_t *gLNext; const Ctl *ctl;
 	// sharded engines: records carry whole-index positions; bucket b of this rank sits recOff[b*7+6]
 	// symbols (recOff[b*7+a] symbols a) further right in the whole index than in the local array
 	const int64_t *recOff; int nb;
 };
 
-#define FT_NCH (FT_OLDMAX / FT_CH + 2)   // cells of old symbols one tile can hold (one more than it counts: funnel-shift partner)
-#define FT_OLDW ((FT_NCH * 3 + 3) & ~3)  // ... as words, a multiple of 16 bytes (TMA destination)
-#define FT_NOC (FT_OUT / FT_CH)          // output cells per tile = worker threads per CTA
-#define FT_TILEW (FT_NOC * 3)            // words of one output tile
-#define FP_CAP   1023                    // records per tile the main (persistent) kernel stages; more: overflow kernel, same tile code
-#define FP_STAGES 2                      // tiles in flight per CTA of the main kernel: one being merged, one being fetched
-#define FT_BAR_WORK 2                    // named barrier of the 256 worker threads of a CTA
+// ---- the merge: one warp per slice, no block-wide synchronisation ---------------------------------------------
+// A slice needs: the old symbols that land in it, from the directory boundary a0 in front of its first one
+// (<= FT_DIR + FS_SLICE symbols = 128 cells, one TMA bulk copy), and its records (the slice of every record
+// array, TMA bulk copies widened to 16-byte boundaries).  The warp
+//   (1) counts the old symbols cell by cell (raw prefix counts from a0: what rank() needs),
+//   (2) scatters its records into per-output-cell bit masks (which output positions are new, and their planes),
+//   (3) assembles its 64 output cells, two per lane: 32 old symbols from the right offset (funnel shift), one
+//       zero bit pushed in per new position, the new symbols' planes OR-ed on top,
+//   (4) sends the slice off with one TMA bulk store, writes the slice's symbol counts (= one directory tile),
+//   (5) returns rank(a, P) = directory row + prefix count + partial cell count for each of its records.
+// The main kernel is persistent: every warp owns two shared-memory stages and fetches slice i+2 while it merges
+// slice i (its lane 0 is the producer); slices with more records than a stage holds go to the overflow list,
+// which k_flat_merge_dense works off with the same code reading the records from global memory.
+#define FS_CELLS (FS_SLICE / FT_CH)                 // 64 output cells, two per lane
+#define FS_OLDC  (FS_SLICE / FT_CH + FT_DIR / FT_CH + 2) // cells of old symbols a slice can need (+ funnel-shift partner)
+#define FS_OLDW  ((FS_OLDC * 3 + 3) & ~3)           // ... as words, a multiple of 16 bytes
+#define FS_OUTW  (FS_CELLS * 3)                     // words of one output slice
+#define FS_CAP   255                                // records per slice the main kernel stages
+#define FS_STAGES 2
+#define FS_WARPS 4                                  // warps per CTA of the main kernel
 
-// working set of one tile in shared memory
-template <int CAP> struct FlatWorkT {
-	alignas(16) uint32_t out[FT_TILEW];  // the finished tile (TMA bulk store)
-	uint32_t chunkPre[FT_NCH][3];        // raw counts in front of every cell of the old symbols (16-bit fields)
-	uint16_t sKey[CAP + 1];              // staged records: run start inside the tile
-	uint16_t sLS[CAP + 1];               // (run length inside the tile - 1) << 3 | symbol
-	uint16_t sPre[CAP + 1];              // record symbols of this tile in front of the record
-	uint32_t cntC[FT_NOC + 1];           // staged records that start in each output cell
-	uint16_t k0C[FT_NOC + 2];            // ... and their exclusive prefix = the first record at or behind each cell
-	uint32_t warpTot[8][3];
-	uint32_t warpCnt[8][3];              // raw counts of the 32 output cells of each warp
+template <bool GENERAL> struct SliceStage {
+	alignas(16) uint32_t old[FS_OLDW];
+	alignas(16) int64_t P[FS_CAP + 3];              // slices start at a 16-byte boundary of the source array: up to 1 / 3 / 15 elements of slack in front
+	alignas(16) uint32_t dst[FS_CAP + 9];
+	alignas(16) uint32_t sc[GENERAL ? FS_CAP + 9 : (FS_CAP + 33 + 3) / 4]; // GENERAL: count << 3 | symbol; otherwise the asym bytes
+	alignas(16) uint32_t pre[GENERAL ? FS_CAP + 9 : 4];
+	TileDesc d0, d1; uint32_t slice, offP, off4, off1;
 };
+struct SliceWork {
+	alignas(16) uint32_t out[FS_OUTW];              // the finished slice (TMA bulk store)
+	alignas(16) uint32_t mask[FS_CELLS][4];         // per output cell: new positions, and planes 0..2 of the new symbols
+	uint32_t pre[FS_OLDC][3];                       // raw counts in front of every old cell, from a0 (16-bit fields)
+};
+template <bool GENERAL> struct SliceWarpSmem { SliceStage<GENERAL> st[FS_STAGES]; SliceWork W; alignas(8) uint64_t full[FS_STAGES]; };
 
-// where the inputs of one tile are: the old symbols from the directory tile boundary a0 on (shared memory),
-// and the tile's records, indexed from 0 (shared memory in the main kernel, global memory in the overflow kernel)
-struct TileIn {
-	const uint32_t *old; const int64_t *P; const uint32_t *pre, *sc, *dst; const uint8_t *asym;
-	uint32_t r0;
+// where the records of one slice are, indexed from 0 (shared memory or global memory)
+struct SliceIn {
+	const uint32_t *old; const int64_t *P; const uint32_t *pre, *sc, *dst; const uint8_t *asym; uint32_t r0;
 	__device__ __forceinline__ uint32_t Pre(uint32_t k) const { return pre ? pre[k] : r0 + k; }
 	__device__ __forceinline__ uint32_t SC(uint32_t k) const { return sc ? sc[k] : (8u | asym[k]); }
 };
 
-// insert c copies (1 <= c, q + c <= 32) of symbol sy at bit position q of a cell; what is pushed past bit 31 falls out
-__device__ __forceinline__ void cell_insert(Cell &x, uint32_t q, uint32_t c, uint32_t sy)
+// set the new-symbol masks of output positions [key, key+len) of the slice
+__device__ __forceinline__ void slice_mark(SliceWork &W, uint32_t key, uint32_t len, uint32_t sy)
 {
-	const uint32_t low = (1u << q) - 1u;                 // q <= 31
-	const uint32_t fill = low_mask(c) << q;
-	const uint32_t sh = c & 31u;                          // c == 32 only with q == 0: everything is replaced
-	const uint32_t keepHi = c >= 32 ? 0u : 0xffffffffu;
-	x.b0 = (x.b0 & low) | (((x.b0 & ~low) << sh) & keepHi) | ((sy & 1u) ? fill : 0u);
-	x.b1 = (x.b1 & low) | (((x.b1 & ~low) << sh) & keepHi) | ((sy & 2u) ? fill : 0u);
-	x.b2 = (x.b2 & low) | (((x.b2 & ~low) << sh) & keepHi) | ((sy & 4u) ? fill : 0u);
+	while (len) {
+		const uint32_t c = key / FT_CH, q = key & (FT_CH - 1), n = len < FT_CH - q ? len : FT_CH - q;
+		const uint32_t bits = low_mask(n) << q;
+		atomicOr(&W.mask[c][0], bits);
+		if (sy & 1u) atomicOr(&W.mask[c][1], bits);
+		if (sy & 2u) atomicOr(&W.mask[c][2], bits);
+		if (sy & 4u) atomicOr(&W.mask[c][3], bits);
+		key += n; len -= n;
+	}
 }
 
-// One output tile, executed by the 256 worker threads of a CTA (tid = 0..255) once its inputs are in place.
-// (A) raw counts per cell of the old symbols | records -> keys, indexed by output cell, (B) every thread
-// assembles one output cell, (C) TMA bulk store | ranks of the tile's records | symbol counts of its
-// sub-tiles.  Three barriers, all FT_BAR_WORK.
-template <int CAP>
-__device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatWorkT<CAP> &S, const TileIn &in, const uint32_t tile, const TileDesc d0, const TileDesc d1)
+// one output cell: 32 old symbols from local index oldIdx on, a gap pushed in at every bit of m, the new planes on top
+__device__ __forceinline__ Cell slice_cell(const uint32_t *old, uint32_t oldIdx, const uint32_t (&mk)[4])
 {
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	const uint64_t o0 = (uint64_t)tile * FT_OUT;
-	const uint32_t tileLen = A.nNew - o0 < FT_OUT ? (uint32_t)(A.nNew - o0) : FT_OUT;
-	const uint32_t r0 = d0.r0, r1 = d1.r0;
-	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < tileLen ? (d0.carry >> 3) : tileLen;
-	const uint64_t i0 = d0.i0;                     // old symbols [i0, i1) land in this tile
-	const uint64_t a0 = i0 & ~(uint64_t)(FT_DIR - 1);
-	const uint32_t loadLen = (uint32_t)(d1.i0 - a0), skip = (uint32_t)(i0 - a0);
-	const uint32_t recIn = tileLen - (loadLen - skip); // record symbols inside the tile
-	const uint64_t before = o0 - i0;               // record symbols in front of the tile
-	const uint32_t nLoad = loadLen / FT_CH + 2;    // cells that were fetched (<= FT_NCH); the last one only as a funnel-shift partner
-	const uint32_t nCarry = carryLen ? 1u : 0u, nS = nCarry + (r1 - r0);
-	constexpr int NCNT = 160;                      // threads (5 warps) that count; the other 3 warps stage records
+	Cell x;
+	const uint32_t *wp = old + (oldIdx >> 5) * 3; const uint32_t sh = oldIdx & 31;
+	x.b0 = __funnelshift_r(wp[0], wp[3], sh); x.b1 = __funnelshift_r(wp[1], wp[4], sh); x.b2 = __funnelshift_r(wp[2], wp[5], sh);
+	uint32_t m = mk[0];
+	if (m == 0xffffffffu) { x.b0 = 0; x.b1 = 0; x.b2 = 0; }
+	else while (m) { // increasing positions: each gap shifts what is behind it by one
+		const uint32_t low = (m & (0u - m)) - 1u; // the bits below the lowest set bit of m
+		x.b0 = (x.b0 & low) | ((x.b0 & ~low) << 1); x.b1 = (x.b1 & low) | ((x.b1 & ~low) << 1); x.b2 = (x.b2 & low) | ((x.b2 & ~low) << 1);
+		m &= m - 1;
+	}
+	x.b0 = (x.b0 & ~mk[0]) | mk[1]; x.b1 = (x.b1 & ~mk[0]) | mk[2]; x.b2 = (x.b2 & ~mk[0]) | mk[3];
+	return x;
+}
 
-	// ---- phase A: raw counts per cell pair | records -> keys ------------------------------------------------
-	uint32_t p[3] = { 0, 0, 0 }, q[3] = { 0, 0, 0 }, inc[3] = { 0, 0, 0 };
-	if (tid < NCNT) {
-		// thread j owns cells 2j, 2j+1 (symbols behind loadLen are whatever follows in the array: the
-		// prefixes that include them are never used)
-		if ((uint32_t)tid * 2 < nLoad) {
-			const Cell x = cell_load(in.old + tid * 6), y = cell_load(in.old + tid * 6 + 3);
-			Raw6 r = raw_of_cell(x, 0xffffffffu, FT_CH);
-			raw_pack16(r, q);
-			raw_addto(r, raw_of_cell(y, 0xffffffffu, FT_CH));
-			raw_pack16(r, p);
-		}
+template <bool GENERAL>
+__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane)
+{
+	const uint64_t o0 = (uint64_t)slice * FS_SLICE;
+	const uint32_t sliceLen = A.nNew - o0 < FS_SLICE ? (uint32_t)(A.nNew - o0) : FS_SLICE;
+	const uint32_t r0 = d0.r0, nr = d1.r0 - d0.r0;
+	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < sliceLen ? (d0.carry >> 3) : sliceLen;
+	const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
+	const uint32_t skip = (uint32_t)(d0.i0 - a0);      // old symbols of the window in front of the slice's first one
+	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells 4l .. 4l+3) ---------------------
+	reinterpret_cast<uint4*>(&W.mask[0][0])[lane] = make_uint4(0, 0, 0, 0);
+	reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32] = make_uint4(0, 0, 0, 0);
+	{
+		uint32_t pk[4][3], inc[3];
+		Raw6 r = { 0, 0, 0, 0, 0, 0 };
 #pragma unroll
-		for (int k = 0; k < 3; ++k) inc[k] = p[k];
+		for (int j = 0; j < 4; ++j) {
+			raw_pack16(r, pk[j]); // exclusive inside the lane
+			raw_addto(r, raw_of_cell(cell_load(in.old + (lane * 4 + j) * 3), 0xffffffffu, FT_CH));
+		}
+		raw_pack16(r, inc);
+		const uint32_t own[3] = { inc[0], inc[1], inc[2] };
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
 			for (int k = 0; k < 3; ++k) { const uint32_t y = __shfl_up_sync(FULLMASK, inc[k], o); if (lane >= o) inc[k] += y; }
 		}
-		if (lane == 31) { S.warpTot[wid][0] = inc[0]; S.warpTot[wid][1] = inc[1]; S.warpTot[wid][2] = inc[2]; }
-	} else {
-		// the three staging warps also index the records by output cell: histogram of cell ids, then one
-		// warp scans it.  Barrier 1 is private to them.
-		const int st = tid - NCNT;
-		for (int c = st; c <= FT_NOC; c += 256 - NCNT) S.cntC[c] = 0;
-		RB2_NAMED_BAR(1, 96);
-		if (st == 0 && nCarry) {
-			S.sKey[0] = 0; S.sLS[0] = (uint16_t)(((carryLen - 1) << 3) | carrySym); S.sPre[0] = 0;
-			atomicAdd(&S.cntC[0], 1u);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+#pragma unroll
+			for (int k = 0; k < 3; ++k) W.pre[lane * 4 + j][k] = inc[k] - own[k] + pk[j][k];
 		}
-		for (uint32_t k = st; k < r1 - r0; k += 256 - NCNT) {
-			const uint32_t pre = in.Pre(k), sc = in.SC(k);
-			const uint32_t key = (uint32_t)((uint64_t)in.P[k] + pre - o0);
+	}
+	__syncwarp();
+	// ---- (2) records -> masks ----------------------------------------------------------------------------
+	if (lane == 0 && carryLen) slice_mark(W, 0, carryLen, carrySym);
+	for (uint32_t k = lane; k < nr; k += 32) {
+		const uint32_t key = (uint32_t)((uint64_t)in.P[k] + in.Pre(k) - o0);
+		if (GENERAL) {
+			const uint32_t sc = in.SC(k);
 			uint32_t len = sc >> 3;
-			if (len > FT_OUT - key) len = FT_OUT - key;
-			S.sKey[nCarry + k] = (uint16_t)key; S.sLS[nCarry + k] = (uint16_t)(((len - 1) << 3) | (sc & 7u));
-			S.sPre[nCarry + k] = (uint16_t)(pre - (uint32_t)before);
-			atomicAdd(&S.cntC[key / FT_CH], 1u);
-		}
-		RB2_NAMED_BAR(1, 96);
-		if (wid == NCNT / 32) { // eight cells per lane
-			uint32_t v[8], sum = 0;
-#pragma unroll
-			for (int i = 0; i < 8; ++i) { v[i] = S.cntC[lane * 8 + i]; sum += v[i]; }
-			uint32_t ex = warp_incl_scan(sum, lane) - sum;
-#pragma unroll
-			for (int i = 0; i < 8; ++i) { S.k0C[lane * 8 + i] = (uint16_t)ex; ex += v[i]; }
-			if (lane == 31) S.k0C[FT_NOC] = (uint16_t)ex;
+			if (len > FS_SLICE - key) len = FS_SLICE - key;
+			slice_mark(W, key, len, sc & 7u);
+		} else {
+			const uint32_t sy = in.asym[k], c = key / FT_CH, bit = 1u << (key & (FT_CH - 1));
+			atomicOr(&W.mask[c][0], bit);
+			if (sy & 1u) atomicOr(&W.mask[c][1], bit);
+			if (sy & 2u) atomicOr(&W.mask[c][2], bit);
+			if (sy & 4u) atomicOr(&W.mask[c][3], bit);
 		}
 	}
-	RB2_NAMED_BAR(FT_BAR_WORK, 256);
-	// prefix in front of every cell (needed behind the next barrier)
-	if (tid < NCNT && (uint32_t)tid * 2 < nLoad) {
-		uint32_t base[3] = { 0, 0, 0 };
-		for (int w = 0; w < wid; ++w) { base[0] += S.warpTot[w][0]; base[1] += S.warpTot[w][1]; base[2] += S.warpTot[w][2]; }
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const uint32_t ex = base[k] + inc[k] - p[k];
-			S.chunkPre[tid * 2][k] = ex; S.chunkPre[tid * 2 + 1][k] = ex + q[k];
-		}
-	}
-	// ---- phase B: one output cell per thread ------------------------------------------------------------
+	if (lane == 0) bulk_wait_read(); // the previous slice's store has read W.out
+	__syncwarp();
+	// ---- (3) assemble: lane l makes output cells 2l, 2l+1 ---------------------------------------------------
 	{
-		const uint32_t rel = tid * FT_CH;
-		const uint32_t k0 = S.k0C[tid], kEnd = S.k0C[tid + 1]; // staged records that start in this cell
-		uint32_t runRem = 0, runSym = 0, oldIdx;
-		if (k0 > 0) { // inside the run of entry k0-1 ?
-			const uint32_t e = k0 - 1, end = (uint32_t)S.sKey[e] + ((uint32_t)S.sLS[e] >> 3) + 1;
-			if (end > rel) { runRem = end - rel; runSym = S.sLS[e] & 7u; oldIdx = (uint32_t)S.sKey[e] - S.sPre[e] + skip; }
-		}
-		if (!runRem) oldIdx = rel - (k0 < nS ? (uint32_t)S.sPre[k0] : recIn) + skip;
-		Cell x;
-		{ // 32 old symbols from oldIdx on (unaligned)
-			const uint32_t *wp = in.old + (oldIdx >> 5) * 3; const uint32_t sh = oldIdx & 31;
-			x.b0 = __funnelshift_r(wp[0], wp[3], sh); x.b1 = __funnelshift_r(wp[1], wp[4], sh); x.b2 = __funnelshift_r(wp[2], wp[5], sh);
-		}
-		if (runRem) cell_insert(x, 0, runRem < FT_CH ? runRem : FT_CH, runSym);
-		for (uint32_t k = k0; k < kEnd; ++k) {
-			const uint32_t qq = (uint32_t)S.sKey[k] - rel, len = ((uint32_t)S.sLS[k] >> 3) + 1;
-			cell_insert(x, qq, len < FT_CH - qq ? len : FT_CH - qq, S.sLS[k] & 7u);
-		}
-		// symbols behind the end of the array (last tile) are zero
-		const uint32_t nv = rel >= tileLen ? 0u : (tileLen - rel < FT_CH ? tileLen - rel : FT_CH);
-		const uint32_t vm = low_mask(nv);
-		x.b0 &= vm; x.b1 &= vm; x.b2 &= vm;
-		S.out[tid * 3] = x.b0; S.out[tid * 3 + 1] = x.b1; S.out[tid * 3 + 2] = x.b2;
+		const uint4 ma = reinterpret_cast<const uint4*>(&W.mask[0][0])[2 * lane], mb = reinterpret_cast<const uint4*>(&W.mask[0][0])[2 * lane + 1];
+		const uint32_t ca = __popc(ma.x), cnt = ca + __popc(mb.x);
+		const uint32_t ex = warp_incl_scan(cnt, lane) - cnt;            // new symbols of the slice in front of cell 2l
+		const uint32_t mka[4] = { ma.x, ma.y, ma.z, ma.w }, mkb[4] = { mb.x, mb.y, mb.z, mb.w };
+		Cell xa = slice_cell(in.old, skip + 64u * lane - ex, mka);
+		Cell xb = slice_cell(in.old, skip + 64u * lane + 32u - ex - ca, mkb);
+		// symbols behind the end of the array (last slice) are zero
+		const uint32_t rel = 64u * lane;
+		const uint32_t na = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
+		const uint32_t nb = rel + FT_CH >= sliceLen ? 0u : (sliceLen - rel - FT_CH < FT_CH ? sliceLen - rel - FT_CH : FT_CH);
+		const uint32_t va = low_mask(na), vb = low_mask(nb);
+		xa.b0 &= va; xa.b1 &= va; xa.b2 &= va; xb.b0 &= vb; xb.b1 &= vb; xb.b2 &= vb;
+		uint32_t *o = W.out + lane * 6;
+		reinterpret_cast<uint2*>(o)[0] = make_uint2(xa.b0, xa.b1); reinterpret_cast<uint2*>(o)[1] = make_uint2(xa.b2, xb.b0); reinterpret_cast<uint2*>(o)[2] = make_uint2(xb.b1, xb.b2);
 		fence_proxy_async();
-		// raw counts of the warp's 32 output cells (two warps = one FT_DIR sub-tile)
+		// ---- (4) symbol counts of the slice = one directory tile of the new array ---------------------------
+		Raw6 r = raw_of_cell(xa, va, na);
+		raw_addto(r, raw_of_cell(xb, vb, nb));
 		uint32_t pk[3];
-		raw_pack16(raw_of_cell(x, vm, nv), pk);
+		raw_pack16(r, pk);
 #pragma unroll
 		for (int k = 0; k < 3; ++k) pk[k] = warp_redux_add(pk[k]);
-		if (lane == 0) { S.warpCnt[wid][0] = pk[0]; S.warpCnt[wid][1] = pk[1]; S.warpCnt[wid][2] = pk[2]; }
+		if (lane < 6 && (o0 < A.nNew || slice == 0)) A.newTileCnt[(uint64_t)slice * 6 + lane] = raw_symbol(raw_unpack16(pk[0], pk[1], pk[2]), (uint32_t)lane);
 	}
-	RB2_NAMED_BAR(FT_BAR_WORK, 256);
-	// ---- phase C: the tile leaves through one bulk store ------------------------------------------------
-	if (tid == 0) { bulk_s2g(A.newS + (uint64_t)tile * (FT_TILEW * 4), S.out, FT_TILEW * 4); bulk_commit(); }
-	// symbol counts of the four FT_DIR sub-tiles (warp 1)
-	if (tid >= 32 && tid < 32 + FT_SUB * 6) {
-		const uint32_t sb = (uint32_t)(tid - 32) / 6u, f = (uint32_t)(tid - 32) % 6u;
-		const uint64_t dt = (uint64_t)tile * FT_SUB + sb;
-		if (dt * FT_DIR < A.nNew || dt == 0) {
-			const Raw6 r = raw_unpack16(S.warpCnt[2 * sb][0] + S.warpCnt[2 * sb + 1][0], S.warpCnt[2 * sb][1] + S.warpCnt[2 * sb + 1][1],
-			                            S.warpCnt[2 * sb][2] + S.warpCnt[2 * sb + 1][2]);
-			A.newTileCnt[dt * 6 + f] = raw_symbol(r, f);
-		}
-	}
-	// rank(a, P) for the records that start in this tile (taken from the last warp downwards)
+	__syncwarp();
+	if (lane == 0) { bulk_s2g(A.newS + (uint64_t)slice * (FS_OUTW * 4), W.out, FS_OUTW * 4); bulk_commit(); }
+	// ---- (5) rank(a, P) for the records that start in this slice ------------------------------------------------
 	{
 		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
-		for (uint32_t k = 255 - tid; k < r1 - r0; k += 256) {
+		for (uint32_t k = lane; k < nr; k += 32) {
 			const uint32_t dst = in.dst[k];
 			if (dst == NONE32) continue;
-			const uint32_t e = nCarry + k, a = S.sLS[e] & 7u;
-			const uint32_t xo = (uint32_t)S.sKey[e] - S.sPre[e] + skip; // old symbols of the load window in front of the record
+			const uint32_t a = GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k];
+			const uint32_t xo = (uint32_t)((uint64_t)in.P[k] - a0); // old symbols of the window in front of the record
 			const uint32_t c = xo / FT_CH;
-			const Raw6 rr = raw_unpack16(S.chunkPre[c][0], S.chunkPre[c][1], S.chunkPre[c][2]);
+			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
 			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
 			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a) + part;
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
@@ -330,118 +316,98 @@ __device__ __forceinline__ void flat_merge_tile(const FlatArgs &A, FlatWorkT<CAP
 			A.gLNext[dst] = g;
 		}
 	}
-	if (tid == 0) bulk_wait_read(); // the store has read S.out
-	RB2_NAMED_BAR(FT_BAR_WORK, 256); // the working set and the inputs may be reused
+	__syncwarp(); // the inputs and W.mask / W.pre may be reused
 }
 
-// ---- main kernel: persistent CTAs, warp-specialised -----------------------------------------------------------
-// 8 worker warps + 1 producer warp.  The producer (one thread) walks the CTA's tiles ahead of the workers: it
-// reads the tile's geometry and fetches everything the tile needs -- the old symbols and the tile's slice of
-// every record array -- into one of FP_STAGES shared-memory stages with TMA bulk copies that complete on the
-// stage's `full` mbarrier; the workers merge the tile of one stage while the next one is in flight and hand
-// the stage back through its `empty` mbarrier.  Tiles with more records than a stage holds go to the overflow list.
-struct alignas(16) FlatStage {
-	alignas(16) uint32_t old[FT_OLDW];
-	alignas(16) int64_t P[FP_CAP + 3];       // slices start at a 16-byte boundary of the source array: up to 1 / 3 / 15 elements of slack in front
-	alignas(16) uint32_t pre[FP_CAP + 9], sc[FP_CAP + 9], dst[FP_CAP + 9];
-	alignas(16) uint8_t asym[FP_CAP + 33];
-	TileDesc d0, d1; uint32_t tile, offP, off4, off1;
-};
-struct FlatPSmem {
-	FlatStage st[FP_STAGES];
-	FlatWorkT<FP_CAP> W;
-	alignas(8) uint64_t full[FP_STAGES], empty[FP_STAGES];
-};
-
-__global__ void __launch_bounds__(288, 3) k_flat_merge(FlatArgs A, uint32_t nTiles)
+// main kernel: persistent warps, each its own producer
+template <bool GENERAL>
+__global__ void __launch_bounds__(FS_WARPS * 32) k_flat_merge(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
-	FlatPSmem &S = *reinterpret_cast<FlatPSmem*>(smraw);
-	if (threadIdx.x == 0) {
-		for (int s = 0; s < FP_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-	}
-	__syncthreads();
-	if (threadIdx.x >= 256) {
-		// ---- producer ----
-		if (threadIdx.x != 256) return;
-		uint32_t n = 0;
-		for (uint32_t tile = blockIdx.x; ; tile += gridDim.x) {
-			const bool last = tile >= nTiles;
-			TileDesc d0, d1;
-			if (!last) {
-				d0 = A.desc[tile]; d1 = A.desc[tile + 1];
-				if (d1.r0 - d0.r0 + 1 > FP_CAP) { A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = tile; continue; } // (+1: a run carried in from the left)
-			}
-			const uint32_t s = n % FP_STAGES, ph = (n / FP_STAGES) & 1u;
-			mbar_wait(&S.empty[s], ph ^ 1u);
-			FlatStage &st = S.st[s];
-			if (last) { st.tile = NONE32; mbar_arrive(&S.full[s]); break; }
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	SliceWarpSmem<GENERAL> &S = reinterpret_cast<SliceWarpSmem<GENERAL>*>(smraw)[wid];
+	const uint32_t nWarps = gridDim.x * FS_WARPS;
+	if (lane == 0) { for (int s = 0; s < FS_STAGES; ++s) mbar_init(&S.full[s], 1); }
+	__syncwarp();
+	uint32_t cand = blockIdx.x * FS_WARPS + wid; // next slice this warp looks at
+	// fetch the next slice of this warp that fits a stage (others go to the overflow list) into stage s; NONE32 when there is none
+	auto issue = [&](uint32_t s) {
+		if (lane != 0) return;
+		SliceStage<GENERAL> &st = S.st[s];
+		for (;; cand += nWarps) {
+			if (cand >= A.nSlices) { st.slice = NONE32; mbar_arrive(&S.full[s]); return; }
+			const TileDesc d0 = A.desc[cand], d1 = A.desc[cand + 1];
+			const uint32_t nr = d1.r0 - d0.r0;
+			if (nr > FS_CAP) { A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = cand; continue; }
 			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
 			const uint32_t nLoad = (uint32_t)(d1.i0 - a0) / FT_CH + 2;
 			const uint32_t bOld = (nLoad * 12u + 15u) & ~15u;
-			const uint32_t r0 = d0.r0, nr = d1.r0 - d0.r0;
-			// slices of the record arrays, widened to 16-byte boundaries of the source
-			const uint32_t rP = r0 & ~1u, r4 = r0 & ~3u, r1b = r0 & ~15u;
+			const uint32_t r0 = d0.r0;
+			const uint32_t rP = r0 & ~1u, r4 = r0 & ~3u, r1b = r0 & ~15u; // record slices widened to 16-byte boundaries of the source
 			const uint32_t bP = nr ? (((r0 + nr - rP) * 8u + 15u) & ~15u) : 0u;
 			const uint32_t b4 = nr ? (((r0 + nr - r4) * 4u + 15u) & ~15u) : 0u;
 			const uint32_t b1 = nr ? ((r0 + nr - r1b + 15u) & ~15u) : 0u;
-			st.d0 = d0; st.d1 = d1; st.tile = tile; st.offP = r0 - rP; st.off4 = r0 - r4; st.off1 = r0 - r1b;
-			mbar_expect_tx(&S.full[s], bOld + bP + b4 + (A.V.pre ? b4 : 0u) + (A.V.sc ? b4 : b1));
+			st.d0 = d0; st.d1 = d1; st.slice = cand; st.offP = r0 - rP; st.off4 = r0 - r4; st.off1 = r0 - r1b;
+			mbar_expect_tx(&S.full[s], bOld + bP + b4 + (GENERAL ? 2 * b4 : b1));
 			bulk_g2s(st.old, A.oldS + (a0 / FT_CH) * 12, bOld, &S.full[s]);
 			if (nr) {
 				bulk_g2s(st.P, A.V.P + rP, bP, &S.full[s]);
 				bulk_g2s(st.dst, A.recDst + r4, b4, &S.full[s]);
-				if (A.V.pre) bulk_g2s(st.pre, A.V.pre + r4, b4, &S.full[s]);
-				if (A.V.sc) bulk_g2s(st.sc, A.V.sc + r4, b4, &S.full[s]);
-				else bulk_g2s(st.asym, A.V.asym + r1b, b1, &S.full[s]);
+				if (GENERAL) { bulk_g2s(st.pre, A.V.pre + r4, b4, &S.full[s]); bulk_g2s(st.sc, A.V.sc + r4, b4, &S.full[s]); }
+				else bulk_g2s(st.sc, A.V.asym + r1b, b1, &S.full[s]);
 			}
-			++n;
+			cand += nWarps;
+			return;
 		}
-		return;
-	}
-	// ---- workers ----
+	};
+	for (uint32_t s = 0; s < FS_STAGES; ++s) issue(s);
 	for (uint32_t n = 0; ; ++n) {
-		const uint32_t s = n % FP_STAGES, ph = (n / FP_STAGES) & 1u;
+		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
 		mbar_wait(&S.full[s], ph);
-		const FlatStage &st = S.st[s];
-		const uint32_t tile = st.tile;
-		if (tile == NONE32) break;
-		TileIn in = { st.old, st.P + st.offP, A.V.pre ? st.pre + st.off4 : (const uint32_t*)0, A.V.sc ? st.sc + st.off4 : (const uint32_t*)0,
-		              st.dst + st.off4, st.asym + st.off1, st.d0.r0 };
-		flat_merge_tile<FP_CAP>(A, S.W, in, tile, st.d0, st.d1);
-		if (threadIdx.x == 0) mbar_arrive(&S.empty[s]); // (behind the tile's closing barrier: every worker is done with the stage)
+		const SliceStage<GENERAL> &st = S.st[s];
+		const uint32_t slice = st.slice;
+		if (slice == NONE32) break;
+		SliceIn in = { st.old, st.P + st.offP, GENERAL ? st.pre + st.off4 : (const uint32_t*)0, GENERAL ? st.sc + st.off4 : (const uint32_t*)0,
+		               st.dst + st.off4, reinterpret_cast<const uint8_t*>(st.sc) + st.off1, st.d0.r0 };
+		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane);
+		issue(s); // (behind the slice's closing __syncwarp: every lane is done with the stage)
 	}
+	if (lane == 0) bulk_wait_read();
 }
 
-// overflow kernel (persistent, no prefetch): tiles where records are dense -- small indexes, first columns of a batch
-template <int CAP> struct FlatDSmemT { alignas(16) uint32_t old[FT_OLDW]; FlatWorkT<CAP> W; alignas(8) uint64_t mbar; uint32_t tile; };
-__global__ void __launch_bounds__(256) k_flat_merge_dense(FlatArgs A)
+// overflow kernel: slices where records are dense -- small indexes, the first columns of a batch.  One warp per
+// slice off a work counter; the old symbols by TMA, the records straight from global memory.
+struct SliceDenseSmem { alignas(16) uint32_t old[FS_OLDW]; SliceWork W; alignas(8) uint64_t mbar; };
+__global__ void __launch_bounds__(FS_WARPS * 32) k_flat_merge_dense(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
-	FlatDSmemT<FT_OUT> &S = *reinterpret_cast<FlatDSmemT<FT_OUT>*>(smraw);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	SliceDenseSmem &S = reinterpret_cast<SliceDenseSmem*>(smraw)[wid];
 	const uint32_t n = A.ovf[0];
-	if (threadIdx.x == 0) mbar_init(&S.mbar, 1);
-	uint32_t parity = 0;
-	for (;;) {
-		if (threadIdx.x == 0) S.tile = atomicAdd(&A.ovf[1], 1u);
-		__syncthreads();
-		const uint32_t qi = S.tile;
+	if (lane == 0) mbar_init(&S.mbar, 1);
+	__syncwarp();
+	const bool general = A.V.sc != 0;
+	for (uint32_t parity = 0;; parity ^= 1u) {
+		uint32_t qi = 0;
+		if (lane == 0) qi = atomicAdd(&A.ovf[1], 1u);
+		qi = __shfl_sync(FULLMASK, qi, 0);
 		if (qi >= n) break;
-		const uint32_t tile = A.ovf[2 + qi];
-		const TileDesc d0 = A.desc[tile], d1 = A.desc[tile + 1];
-		if (threadIdx.x == 0) {
+		const uint32_t slice = A.ovf[2 + qi];
+		const TileDesc d0 = A.desc[slice], d1 = A.desc[slice + 1];
+		if (lane == 0) {
 			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
 			const uint32_t bytes = (((uint32_t)(d1.i0 - a0) / FT_CH + 2) * 12u + 15u) & ~15u;
 			mbar_expect_tx(&S.mbar, bytes);
 			bulk_g2s(S.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.mbar);
 		}
 		mbar_wait(&S.mbar, parity);
-		parity ^= 1u;
 		const uint32_t r0 = d0.r0;
-		TileIn in = { S.old, A.V.P + r0, A.V.pre ? A.V.pre + r0 : (const uint32_t*)0, A.V.sc ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
-		              A.V.asym ? A.V.asym + r0 : (const uint8_t*)0, r0 };
-		flat_merge_tile<FT_OUT>(A, S.W, in, tile, d0, d1);
+		SliceIn in = { S.old, A.V.P + r0, A.V.pre ? A.V.pre + r0 : (const uint32_t*)0, A.V.sc ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
+		               A.V.asym ? A.V.asym + r0 : (const uint8_t*)0, r0 };
+		if (general) flat_merge_slice<true>(A, S.W, in, slice, d0, d1, lane);
+		else flat_merge_slice<false>(A, S.W, in, slice, d0, d1, lane);
 	}
+	if (lane == 0) bulk_wait_read();
 }
 
 struct FlatDirScan { // K=6 (int64): per-tile symbol counts -> counts in front of every tile

@@ -83,7 +83,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 	}
 	f.s[f.cur ^ 1].need(flat_bytes(cap)); f.dir[f.cur ^ 1].need((cap / FT_DIR + 3) * 6);
 	f.tileCnt.need((cap / FT_DIR + 3) * 6);
-	f.desc.need(cap / FT_OUT + 4); f.ovf.need(cap / FT_OUT + 8);
+	f.desc.need(cap / FS_SLICE + 4); f.ovf.need(cap / FS_SLICE + 8);
 	if (!f.valid) {
 		f.n = n0;
 		if (n0 > 0) {
@@ -104,19 +104,21 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0, const uint8_t *asym = 0)
 {
 	FlatState &f = e->flat;
-	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FT_OUT - 1) / FT_OUT;
+	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FS_SLICE - 1) / FS_SLICE; // slices: one warp each
 	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
-	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.desc.need(nNew / FT_OUT + 4); f.ovf.need(nTiles + 8);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.desc.need(nNew / FS_SLICE + 4); f.ovf.need(nTiles + 8);
 	ph_begin(e, PH_MERGE);
 	// leanP: all-singleton column -- the records are the state arrays themselves (position = leanP[r], symbol = asym[r], count 1, r symbols in front)
 	const RecView V = leanP ? RecView{ leanP, 0, 0, asym ? asym : e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
 	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, f.desc.p);
 	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
+	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
-	                f.desc.p, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	LAUNCH(e, k_flat_merge, (uint32_t)std::min<uint64_t>(nTiles, (uint64_t)e->nSM * 3), 288, sizeof(FlatPSmem), fa, (uint32_t)nTiles);
-	LAUNCH(e, k_flat_merge_dense, e->nSM * 3, 256, sizeof(FlatDSmemT<FT_OUT>), fa);
+	                f.desc.p, (uint32_t)nTiles, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
+	if (V.sc) LAUNCH(e, (k_flat_merge<true>), (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 3), FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem<true>), fa);
+	else LAUNCH(e, (k_flat_merge<false>), (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 4), FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem<false>), fa);
+	LAUNCH(e, k_flat_merge_dense, e->nSM * 4, FS_WARPS * 32, FS_WARPS * sizeof(SliceDenseSmem), fa);
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);
