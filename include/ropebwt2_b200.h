@@ -70,6 +70,9 @@ int  rb2_device_count(void);
 
 /* Create an engine on CUDA device `device` with an empty six-bucket index. */
 rb2_engine_t *rb2_create(int device, int sorting_order);
+/* The engine behind an mrope_t (mr_init): like rb2_create, but with RB2_GPUS=P (P > 1) in the environment it is a
+ * proxy over P sharded engines, one per GPU, so the unmodified reference driver uses every GPU of the node. */
+rb2_engine_t *rb2_create_auto(int device, int sorting_order);
 void rb2_destroy(rb2_engine_t *e);
 int  rb2_sorting_order(const rb2_engine_t *e);
 /* Empty the index (six empty buckets, as after rb2_create) but keep all HBM allocations. */

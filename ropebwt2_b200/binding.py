@@ -18,7 +18,7 @@ MROPE_SYMBOLS = ["mr_init", "mr_destroy", "mr_thr_min", "mr_insert1", "mr_insert
 ROPE_SYMBOLS = ["rope_init", "rope_destroy", "rope_insert_run", "rope_rank2a", "rope_itr_first",
                 "rope_itr_next_block", "rope_print_node", "rope_dump", "rope_restore"]
 RLE_SYMBOLS = ["rle_count", "rle_print"]
-RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_destroy", "rb2_sorting_order", "rb2_insert_multi",
+RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_create_auto", "rb2_destroy", "rb2_sorting_order", "rb2_insert_multi",
                "rb2_insert_multi_dev", "rb2_counts", "rb2_rank2a", "rb2_num_blocks", "rb2_fetch_blocks",
                "rb2_load_blocks", "rb2_get_stats", "rb2_reset_stats", "rb2_stream", "rb2_dev_alloc",
                "rb2_dev_free", "rb2_dev_upload", "rb2_reset", "rb2_host_alloc", "rb2_host_free", "rb2_insert_run",

@@ -35,6 +35,7 @@ typedef struct {
 	int max_nodes, block_len;
 	uint8_t *itbuf;    /* ITR_CHUNK * 512 bytes */
 	int64_t *itcnt;    /* ITR_CHUNK * 6 */
+	const void *it_owner; int it_bucket; int64_t it_first; /* which iterator / bucket / first block the staging buffer holds */
 	int standalone;    /* 1: owned by a rope_t created with rope_init/rope_restore */
 } rb2_priv_t;
 
@@ -43,10 +44,11 @@ typedef struct { /* iterator cursor, overlaid on rpitr_t::pa (640 bytes) */
 	int64_t chunk_first, chunk_n;
 } itr_state_t;
 
-static rb2_priv_t *priv_new(int device, int so, int max_nodes, int block_len)
+/* multi: the engine behind an mrope_t may be a proxy over several GPUs (RB2_GPUS=P); a bare rope_t never is */
+static rb2_priv_t *priv_new(int device, int so, int max_nodes, int block_len, int multi)
 {
 	rb2_priv_t *p = (rb2_priv_t*)calloc(1, sizeof(rb2_priv_t));
-	p->eng = rb2_create(device, so);
+	p->eng = multi? rb2_create_auto(device, so) : rb2_create(device, so);
 	p->max_nodes = (max_nodes + 1) >> 1 << 1;        /* reference rope.c:60 */
 	if (p->max_nodes < 4) p->max_nodes = 4;
 	if (p->max_nodes > 510) p->max_nodes = 510;      /* rpnode_t::n has 9 bits (reference rope.h:13) */
@@ -101,7 +103,7 @@ mrope_t *mr_init(int max_nodes, int block_len, int sorting_order)
 	mr = (mrope_t*)calloc(1, sizeof(mrope_t));
 	mr->so = (uint8_t)sorting_order;
 	mr->thr_min = 1000; /* reference mrope.c:21 */
-	mr->priv = priv_new(env_device(), sorting_order, max_nodes, block_len);
+	mr->priv = priv_new(env_device(), sorting_order, max_nodes, block_len, 1);
 	for (a = 0; a < 6; ++a) mr->r[a] = rope_handle((rb2_priv_t*)mr->priv, a);
 	return mr;
 }
@@ -169,9 +171,12 @@ static const uint8_t *itr_step(rb2_priv_t *p, int bucket, rpitr_t *i, const int6
 	itr_state_t *s = (itr_state_t*)i->pa;
 	const uint8_t *ret;
 	if (s->next >= s->nblk) return 0;
-	if (s->next >= s->chunk_first + s->chunk_n) {
+	/* all iterators of an index share one staging buffer: (re)fetch when this iterator's chunk is exhausted or
+	 * another iterator (or a dump / print running in between) has used the buffer since */
+	if (s->next >= s->chunk_first + s->chunk_n || p->it_owner != (const void*)i || p->it_bucket != bucket || p->it_first != s->chunk_first) {
 		s->chunk_first = s->next;
 		s->chunk_n = rb2_fetch_blocks(p->eng, bucket, s->chunk_first, ITR_CHUNK, p->itbuf, p->itcnt);
+		p->it_owner = i; p->it_bucket = bucket; p->it_first = s->chunk_first;
 	}
 	ret = p->itbuf + (size_t)(s->next - s->chunk_first) * RB2_BLOCK_BYTES;
 	if (cnt) *cnt = p->itcnt + (size_t)(s->next - s->chunk_first) * 6;
@@ -220,8 +225,9 @@ static void dump_subtree(dump_t *D, int d, int64_t n)
 	fwrite(&k, 2, 1, D->fp);
 	if (is_bottom) {
 		for (j = 0; j < n; ++j) {
-			const int64_t *c;
+			const int64_t *c = 0;
 			const uint8_t *blk = itr_step(D->p, D->bucket, &D->it, &c);
+			if (blk == 0 || c == 0) mr_fatal("mr_dump: bucket %d ended after %lld of %lld leaf blocks", D->bucket, (long long)j, (long long)n);
 			fwrite(c, 8, 6, D->fp);
 			fwrite(blk, 1, *rle_nptr(blk) + 2, D->fp);
 		}
@@ -341,7 +347,7 @@ mrope_t *mr_restore(FILE *fp)
 	if (magic[3] > 2) mr_fatal("mr_restore: bad sorting order byte %d", magic[3]);
 	mr = (mrope_t*)calloc(1, sizeof(mrope_t));
 	mr->so = magic[3]; /* thr_min stays 0, as in the reference (mrope.c:152) */
-	mr->priv = p = priv_new(env_device(), mr->so, ROPE_DEF_MAX_NODES, ROPE_DEF_BLOCK_LEN);
+	mr->priv = p = priv_new(env_device(), mr->so, ROPE_DEF_MAX_NODES, ROPE_DEF_BLOCK_LEN, 1);
 	for (a = 0; a < 6; ++a) {
 		restore_bucket(p, a, fp, &mn, &bl);
 		if (a == 0) {
@@ -412,7 +418,7 @@ void rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_t y, int64_
 
 rope_t *rope_init(int max_nodes, int block_len)
 {
-	rb2_priv_t *p = priv_new(env_device(), RB2_SO_IO, max_nodes, block_len);
+	rb2_priv_t *p = priv_new(env_device(), RB2_SO_IO, max_nodes, block_len, 0);
 	p->standalone = 1;
 	return rope_handle(p, 0);
 }
@@ -465,7 +471,7 @@ void rope_dump(const rope_t *r, FILE *fp)
 
 rope_t *rope_restore(FILE *fp)
 {
-	rb2_priv_t *p = priv_new(env_device(), RB2_SO_IO, ROPE_DEF_MAX_NODES, ROPE_DEF_BLOCK_LEN);
+	rb2_priv_t *p = priv_new(env_device(), RB2_SO_IO, ROPE_DEF_MAX_NODES, ROPE_DEF_BLOCK_LEN, 0);
 	int32_t mn, bl;
 	int64_t c[36];
 	rope_t *r;

@@ -1,6 +1,6 @@
 // rb2_cluster.inl -- several GPUs behind the ONE-engine C-ABI; included by rb2_engine.cu.
 //
-// With RB2_GPUS=P (P > 1) in the environment rb2_create() returns a proxy engine that owns P sharded
+// With RB2_GPUS=P (P > 1) in the environment rb2_create_auto() (what mr_init calls) returns a proxy engine that owns P sharded
 // engines (ranks = threads of this process, LocalComm over peer copies; one GPU each, or all on one
 // device with RB2_GPUS_SAME_DEVICE=1).  The reference-facing API on top (mrope.h: mr_insert_multi, the
 // block iterator, mr_dump, mr_rank2a, the count mirrors) works unchanged: a bucket of the reference is
@@ -8,22 +8,19 @@
 // reference driver (main.c) uses every GPU of a node:  RB2_GPUS=8 ropebwt2_b200 -LRs reads.txt
 #include <thread>
 
-static thread_local int t_inCluster = 0; // rb2_create_sharded() calls rb2_create(): no recursion
 
 static void cluster_attach(rb2_engine *e, int device, int sorting_order)
 {
 	const char *s = getenv("RB2_GPUS");
 	const int P = s && *s ? atoi(s) : 0;
-	if (t_inCluster || P <= 1) return;
+	if (P <= 1) return;
 	if (P > RB2_MAX_RANKS) RB2_FATAL("RB2_GPUS=%d: at most %d", P, RB2_MAX_RANKS);
 	const char *same = getenv("RB2_GPUS_SAME_DEVICE");
 	const int nd = rb2_device_count();
 	if (!(same && *same && *same != '0') && P > nd) RB2_FATAL("RB2_GPUS=%d but only %d CUDA devices are visible", P, nd);
 	e->grp = rb2_group_create(P);
-	t_inCluster = 1;
 	for (int r = 0; r < P; ++r)
 		e->child[r] = rb2_create_sharded(same && *same && *same != '0' ? device : (device + r) % nd, sorting_order, r, P, e->grp, 0);
-	t_inCluster = 0;
 	e->nChild = P;
 	RB2_CUDA(cudaSetDevice(e->dev));
 }

@@ -1818,9 +1818,9 @@ enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, P
 struct FlatState {
 	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
 	bool valid = false, blocksStale = false; // the array holds the current index (resident between dense batches) / the leaf blocks do not
-	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt, ovf; DevBuf<TileDesc> desc;
+	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt; DevBuf<TileDesc> desc;
 	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
-	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); ovf.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
 };
 
 struct rb2_engine {
@@ -2013,7 +2013,11 @@ static int64_t cluster_fetch_blocks(rb2_engine *e, int bucket, int64_t first, in
 static void cluster_rank1(rb2_engine *e, int64_t x, int64_t c[6]);
 #define RB2_NO_CLUSTER(e, what) do { if ((e)->nChild) RB2_FATAL(what " is not available with RB2_GPUS > 1"); } while (0)
 
-extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
+static rb2_engine *engine_create(int device, int sorting_order, bool multi);
+extern "C" rb2_engine_t *rb2_create(int device, int sorting_order) { return engine_create(device, sorting_order, false); }
+// what mr_init uses: with RB2_GPUS=P (P > 1) the engine is a proxy over P sharded engines (rb2_cluster.inl)
+extern "C" rb2_engine_t *rb2_create_auto(int device, int sorting_order) { return engine_create(device, sorting_order, true); }
+static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 {
 	if (sorting_order < 0 || sorting_order > 2) RB2_FATAL("sorting order must be 0, 1 or 2 (mrope.c:18)");
 	int n = rb2_device_count();
@@ -2039,9 +2043,8 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceDenseSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem<true>))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem<false>))));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem))));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);
@@ -2055,7 +2058,7 @@ extern "C" rb2_engine_t *rb2_create(int device, int sorting_order)
 	ctl_push(e);
 	rebuild_directory(e, false);
 	pull_totals(e);
-	cluster_attach(e, device, sorting_order);
+	if (multi) cluster_attach(e, device, sorting_order);
 	return e;
 }
 

@@ -54,14 +54,9 @@ struct Cell { uint32_t b0, b1, b2; };
 __device__ __forceinline__ Cell cell_load(const uint32_t *w) { Cell c = { w[0], w[1], w[2] }; return c; }
 __device__ __forceinline__ uint32_t cell_match(const Cell &c, uint32_t a)
 {
-	switch (a) {
-	case 0: return ~(c.b0 | c.b1 | c.b2);
-	case 1: return c.b0 & ~(c.b1 | c.b2);
-	case 2: return c.b1 & ~c.b0;
-	case 3: return c.b0 & c.b1;
-	case 4: return c.b2 & ~c.b0;
-	default: return c.b0 & c.b2;
-	}
+	// positions whose code equals a: every plane agrees with the corresponding bit of a (branch-free: a differs from lane to lane)
+	const uint32_t m0 = 0u - (a & 1u), m1 = 0u - ((a >> 1) & 1u), m2 = 0u - ((a >> 2) & 1u);
+	return ~((c.b0 ^ m0) | (c.b1 ^ m1) | (c.b2 ^ m2));
 }
 // raw counts of the symbols selected by mask m (n = number of selected positions)
 __device__ __forceinline__ Raw6 raw_of_cell(const Cell &c, uint32_t m, uint32_t n)
@@ -75,14 +70,10 @@ __device__ __forceinline__ uint32_t low_mask(uint32_t n) { return n >= 32 ? 0xff
 __device__ __forceinline__ uint32_t raw_symbol(const Raw6 &r, uint32_t a)
 {
 	const uint32_t A = r.s0 - r.s01 - r.s02, Cc = r.s1 - r.s01, G = r.s01, T = r.s2 - r.s02, N = r.s02;
-	switch (a) {
-	case 0: return r.n - (A + Cc + G + T + N);
-	case 1: return A;
-	case 2: return Cc;
-	case 3: return G;
-	case 4: return T;
-	default: return N;
-	}
+	const uint32_t D = r.n - (A + Cc + G + T + N);
+	uint32_t v = D; // selects, not branches: a differs from lane to lane
+	v = a == 1 ? A : v; v = a == 2 ? Cc : v; v = a == 3 ? G : v; v = a == 4 ? T : v; v = a == 5 ? N : v;
+	return v;
 }
 __device__ __forceinline__ void raw_addto(Raw6 &a, const Raw6 &b) { a.s0 += b.s0; a.s1 += b.s1; a.s2 += b.s2; a.s01 += b.s01; a.s02 += b.s02; a.n += b.n; }
 // six raw counts as three words of two 16-bit fields (sums stay below 2^16 inside one tile)
@@ -137,7 +128,6 @@ struct FlatArgs {
 	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its per-FT_DIR-tile symbol counts
 	RecView V; const uint32_t *recDst; uint32_t R;
 	const TileDesc *desc; uint32_t nSlices;
-	uint32_t *ovf;           // [0] slices left to k_flat_merge_dense, [1] its work counter, [2..] the slices
 	int64_t *gLNext; const Ctl *ctl;
 	// sharded engines: records carry whole-index positions; bucket b of this rank sits recOff[b*7+6]
 	// symbols (recOff[b*7+a] symbols a) further right in the whole index than in the local array
@@ -154,31 +144,23 @@ struct FlatArgs {
 //       zero bit pushed in per new position, the new symbols' planes OR-ed on top,
 //   (4) sends the slice off with one TMA bulk store, writes the slice's symbol counts (= one directory tile),
 //   (5) returns rank(a, P) = directory row + prefix count + partial cell count for each of its records.
-// The main kernel is persistent: every warp owns two shared-memory stages and fetches slice i+2 while it merges
-// slice i (its lane 0 is the producer); slices with more records than a stage holds go to the overflow list,
-// which k_flat_merge_dense works off with the same code reading the records from global memory.
+// The kernel is persistent: every warp owns two shared-memory stages and fetches the old symbols of its slice
+// i+2 while it merges slice i (its lane 0 is the producer); the slice's records are read straight from the
+// record arrays (consecutive records in consecutive lanes).  No block-wide barrier anywhere.
 #define FS_CELLS (FS_SLICE / FT_CH)                 // 64 output cells, two per lane
 #define FS_OLDC  (FS_SLICE / FT_CH + FT_DIR / FT_CH + 2) // cells of old symbols a slice can need (+ funnel-shift partner)
 #define FS_OLDW  ((FS_OLDC * 3 + 3) & ~3)           // ... as words, a multiple of 16 bytes
 #define FS_OUTW  (FS_CELLS * 3)                     // words of one output slice
-#define FS_CAP   255                                // records per slice the main kernel stages
 #define FS_STAGES 2
 #define FS_WARPS 4                                  // warps per CTA of the main kernel
 
-template <bool GENERAL> struct SliceStage {
-	alignas(16) uint32_t old[FS_OLDW];
-	alignas(16) int64_t P[FS_CAP + 3];              // slices start at a 16-byte boundary of the source array: up to 1 / 3 / 15 elements of slack in front
-	alignas(16) uint32_t dst[FS_CAP + 9];
-	alignas(16) uint32_t sc[GENERAL ? FS_CAP + 9 : (FS_CAP + 33 + 3) / 4]; // GENERAL: count << 3 | symbol; otherwise the asym bytes
-	alignas(16) uint32_t pre[GENERAL ? FS_CAP + 9 : 4];
-	TileDesc d0, d1; uint32_t slice, offP, off4, off1;
-};
+struct SliceStage { alignas(16) uint32_t old[FS_OLDW]; TileDesc d0, d1; uint32_t slice, pad[3]; };
 struct SliceWork {
 	alignas(16) uint32_t out[FS_OUTW];              // the finished slice (TMA bulk store)
 	alignas(16) uint32_t mask[FS_CELLS][4];         // per output cell: new positions, and planes 0..2 of the new symbols
 	uint32_t pre[FS_OLDC][3];                       // raw counts in front of every old cell, from a0 (16-bit fields)
 };
-template <bool GENERAL> struct SliceWarpSmem { SliceStage<GENERAL> st[FS_STAGES]; SliceWork W; alignas(8) uint64_t full[FS_STAGES]; };
+struct SliceWarpSmem { SliceStage st[FS_STAGES]; SliceWork W; alignas(8) uint64_t full[FS_STAGES]; };
 
 // where the records of one slice are, indexed from 0 (shared memory or global memory)
 struct SliceIn {
@@ -280,11 +262,14 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 		Cell xa = slice_cell(in.old, skip + 64u * lane - ex, mka);
 		Cell xb = slice_cell(in.old, skip + 64u * lane + 32u - ex - ca, mkb);
 		// symbols behind the end of the array (last slice) are zero
-		const uint32_t rel = 64u * lane;
-		const uint32_t na = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
-		const uint32_t nb = rel + FT_CH >= sliceLen ? 0u : (sliceLen - rel - FT_CH < FT_CH ? sliceLen - rel - FT_CH : FT_CH);
-		const uint32_t va = low_mask(na), vb = low_mask(nb);
-		xa.b0 &= va; xa.b1 &= va; xa.b2 &= va; xb.b0 &= vb; xb.b1 &= vb; xb.b2 &= vb;
+		uint32_t na = FT_CH, nb = FT_CH, va = 0xffffffffu, vb = 0xffffffffu;
+		if (sliceLen < FS_SLICE) { // (warp-uniform: the last slice only)
+			const uint32_t rel = 64u * lane;
+			na = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
+			nb = rel + FT_CH >= sliceLen ? 0u : (sliceLen - rel - FT_CH < FT_CH ? sliceLen - rel - FT_CH : FT_CH);
+			va = low_mask(na); vb = low_mask(nb);
+			xa.b0 &= va; xa.b1 &= va; xa.b2 &= va; xb.b0 &= vb; xb.b1 &= vb; xb.b2 &= vb;
+		}
 		uint32_t *o = W.out + lane * 6;
 		reinterpret_cast<uint2*>(o)[0] = make_uint2(xa.b0, xa.b1); reinterpret_cast<uint2*>(o)[1] = make_uint2(xa.b2, xb.b0); reinterpret_cast<uint2*>(o)[2] = make_uint2(xb.b1, xb.b2);
 		fence_proxy_async();
@@ -295,7 +280,7 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 		raw_pack16(r, pk);
 #pragma unroll
 		for (int k = 0; k < 3; ++k) pk[k] = warp_redux_add(pk[k]);
-		if (lane < 6 && (o0 < A.nNew || slice == 0)) A.newTileCnt[(uint64_t)slice * 6 + lane] = raw_symbol(raw_unpack16(pk[0], pk[1], pk[2]), (uint32_t)lane);
+		if (lane < 3 && (o0 < A.nNew || slice == 0)) A.newTileCnt[(uint64_t)slice * 3 + lane] = lane == 0 ? pk[0] : (lane == 1 ? pk[1] : pk[2]); // raw counts, converted by FlatDirScan
 	}
 	__syncwarp();
 	if (lane == 0) { bulk_s2g(A.newS + (uint64_t)slice * (FS_OUTW * 4), W.out, FS_OUTW * 4); bulk_commit(); }
@@ -319,102 +304,60 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	__syncwarp(); // the inputs and W.mask / W.pre may be reused
 }
 
-// main kernel: persistent warps, each its own producer
+// main kernel: persistent warps, each its own producer for the old symbols (the bulk of the bytes); the slice's
+// records are read straight from the record arrays (coalesced: consecutive records, consecutive lanes)
 template <bool GENERAL>
-__global__ void __launch_bounds__(FS_WARPS * 32) k_flat_merge(FlatArgs A)
+__global__ void __launch_bounds__(FS_WARPS * 32, 8) k_flat_merge(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	SliceWarpSmem<GENERAL> &S = reinterpret_cast<SliceWarpSmem<GENERAL>*>(smraw)[wid];
+	SliceWarpSmem &S = reinterpret_cast<SliceWarpSmem*>(smraw)[wid];
 	const uint32_t nWarps = gridDim.x * FS_WARPS;
 	if (lane == 0) { for (int s = 0; s < FS_STAGES; ++s) mbar_init(&S.full[s], 1); }
 	__syncwarp();
-	uint32_t cand = blockIdx.x * FS_WARPS + wid; // next slice this warp looks at
-	// fetch the next slice of this warp that fits a stage (others go to the overflow list) into stage s; NONE32 when there is none
-	auto issue = [&](uint32_t s) {
+	// fetch the old symbols of slice `sl` into stage s (lane 0); a slice index behind the last one ends the ring
+	auto issue = [&](uint32_t s, uint32_t sl, const TileDesc d0, const TileDesc d1) {
 		if (lane != 0) return;
-		SliceStage<GENERAL> &st = S.st[s];
-		for (;; cand += nWarps) {
-			if (cand >= A.nSlices) { st.slice = NONE32; mbar_arrive(&S.full[s]); return; }
-			const TileDesc d0 = A.desc[cand], d1 = A.desc[cand + 1];
-			const uint32_t nr = d1.r0 - d0.r0;
-			if (nr > FS_CAP) { A.ovf[2 + atomicAdd(&A.ovf[0], 1u)] = cand; continue; }
-			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
-			const uint32_t nLoad = (uint32_t)(d1.i0 - a0) / FT_CH + 2;
-			const uint32_t bOld = (nLoad * 12u + 15u) & ~15u;
-			const uint32_t r0 = d0.r0;
-			const uint32_t rP = r0 & ~1u, r4 = r0 & ~3u, r1b = r0 & ~15u; // record slices widened to 16-byte boundaries of the source
-			const uint32_t bP = nr ? (((r0 + nr - rP) * 8u + 15u) & ~15u) : 0u;
-			const uint32_t b4 = nr ? (((r0 + nr - r4) * 4u + 15u) & ~15u) : 0u;
-			const uint32_t b1 = nr ? ((r0 + nr - r1b + 15u) & ~15u) : 0u;
-			st.d0 = d0; st.d1 = d1; st.slice = cand; st.offP = r0 - rP; st.off4 = r0 - r4; st.off1 = r0 - r1b;
-			mbar_expect_tx(&S.full[s], bOld + bP + b4 + (GENERAL ? 2 * b4 : b1));
-			bulk_g2s(st.old, A.oldS + (a0 / FT_CH) * 12, bOld, &S.full[s]);
-			if (nr) {
-				bulk_g2s(st.P, A.V.P + rP, bP, &S.full[s]);
-				bulk_g2s(st.dst, A.recDst + r4, b4, &S.full[s]);
-				if (GENERAL) { bulk_g2s(st.pre, A.V.pre + r4, b4, &S.full[s]); bulk_g2s(st.sc, A.V.sc + r4, b4, &S.full[s]); }
-				else bulk_g2s(st.sc, A.V.asym + r1b, b1, &S.full[s]);
-			}
-			cand += nWarps;
-			return;
-		}
+		SliceStage &st = S.st[s];
+		if (sl >= A.nSlices) { st.slice = NONE32; mbar_arrive(&S.full[s]); return; }
+		const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
+		const uint32_t bytes = (((uint32_t)(d1.i0 - a0) / FT_CH + 2) * 12u + 15u) & ~15u;
+		st.d0 = d0; st.d1 = d1; st.slice = sl;
+		mbar_expect_tx(&S.full[s], bytes);
+		bulk_g2s(st.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.full[s]);
 	};
-	for (uint32_t s = 0; s < FS_STAGES; ++s) issue(s);
+	const uint32_t first = blockIdx.x * FS_WARPS + wid;
+	const TileDesc none = { 0, 0, 0 };
+	for (uint32_t s = 0; s < FS_STAGES; ++s) {
+		const uint32_t sl = first + s * nWarps;
+		const bool ok = lane == 0 && sl < A.nSlices;
+		issue(s, sl, ok ? A.desc[sl] : none, ok ? A.desc[sl + 1] : none);
+	}
 	for (uint32_t n = 0; ; ++n) {
 		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
 		mbar_wait(&S.full[s], ph);
-		const SliceStage<GENERAL> &st = S.st[s];
+		const SliceStage &st = S.st[s];
 		const uint32_t slice = st.slice;
 		if (slice == NONE32) break;
-		SliceIn in = { st.old, st.P + st.offP, GENERAL ? st.pre + st.off4 : (const uint32_t*)0, GENERAL ? st.sc + st.off4 : (const uint32_t*)0,
-		               st.dst + st.off4, reinterpret_cast<const uint8_t*>(st.sc) + st.off1, st.d0.r0 };
+		// geometry of the slice this stage gets next: loaded now, used behind the merge (the latency hides under it)
+		const uint32_t nextSl = slice + FS_STAGES * nWarps;
+		const bool ok = lane == 0 && nextSl < A.nSlices;
+		const TileDesc nd0 = ok ? A.desc[nextSl] : none, nd1 = ok ? A.desc[nextSl + 1] : none;
+		const uint32_t r0 = st.d0.r0;
+		SliceIn in = { st.old, A.V.P + r0, GENERAL ? A.V.pre + r0 : (const uint32_t*)0, GENERAL ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
+		               GENERAL ? (const uint8_t*)0 : A.V.asym + r0, r0 };
 		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane);
-		issue(s); // (behind the slice's closing __syncwarp: every lane is done with the stage)
+		issue(s, nextSl, nd0, nd1); // (behind the slice's closing __syncwarp: every lane is done with the stage)
 	}
 	if (lane == 0) bulk_wait_read();
 }
 
-// overflow kernel: slices where records are dense -- small indexes, the first columns of a batch.  One warp per
-// slice off a work counter; the old symbols by TMA, the records straight from global memory.
-struct SliceDenseSmem { alignas(16) uint32_t old[FS_OLDW]; SliceWork W; alignas(8) uint64_t mbar; };
-__global__ void __launch_bounds__(FS_WARPS * 32) k_flat_merge_dense(FlatArgs A)
-{
-	RB2_DYN_SMEM(smraw);
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	SliceDenseSmem &S = reinterpret_cast<SliceDenseSmem*>(smraw)[wid];
-	const uint32_t n = A.ovf[0];
-	if (lane == 0) mbar_init(&S.mbar, 1);
-	__syncwarp();
-	const bool general = A.V.sc != 0;
-	for (uint32_t parity = 0;; parity ^= 1u) {
-		uint32_t qi = 0;
-		if (lane == 0) qi = atomicAdd(&A.ovf[1], 1u);
-		qi = __shfl_sync(FULLMASK, qi, 0);
-		if (qi >= n) break;
-		const uint32_t slice = A.ovf[2 + qi];
-		const TileDesc d0 = A.desc[slice], d1 = A.desc[slice + 1];
-		if (lane == 0) {
-			const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
-			const uint32_t bytes = (((uint32_t)(d1.i0 - a0) / FT_CH + 2) * 12u + 15u) & ~15u;
-			mbar_expect_tx(&S.mbar, bytes);
-			bulk_g2s(S.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.mbar);
-		}
-		mbar_wait(&S.mbar, parity);
-		const uint32_t r0 = d0.r0;
-		SliceIn in = { S.old, A.V.P + r0, A.V.pre ? A.V.pre + r0 : (const uint32_t*)0, A.V.sc ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
-		               A.V.asym ? A.V.asym + r0 : (const uint8_t*)0, r0 };
-		if (general) flat_merge_slice<true>(A, S.W, in, slice, d0, d1, lane);
-		else flat_merge_slice<false>(A, S.W, in, slice, d0, d1, lane);
-	}
-	if (lane == 0) bulk_wait_read();
-}
-
-struct FlatDirScan { // K=6 (int64): per-tile symbol counts -> counts in front of every tile
+struct FlatDirScan { // K=6 (int64): per-tile raw counts (three packed words) -> symbol counts in front of every tile
 	const uint32_t *tileCnt; uint64_t nTile; int64_t *dir;
 	__device__ void load(uint64_t i, int64_t (&v)[6]) const {
+		const Raw6 r = raw_unpack16(tileCnt[i * 3], tileCnt[i * 3 + 1], tileCnt[i * 3 + 2]);
 #pragma unroll
-		for (int a = 0; a < 6; ++a) v[a] = tileCnt[i * 6 + a];
+		for (int a = 0; a < 6; ++a) v[a] = raw_symbol(r, (uint32_t)a);
 	}
 	__device__ void store(uint64_t i, const int64_t (&own)[6], const int64_t (&pre)[6]) const {
 #pragma unroll
@@ -441,7 +384,7 @@ __global__ void __launch_bounds__(256) k_flat_count_tiles(const uint8_t *flat, u
 	if (n0) s = raw_of_cell(cell_load(src), low_mask(n0), n0);
 	if (n1) raw_addto(s, raw_of_cell(cell_load(src + 3), low_mask(n1), n1));
 	s.s0 = warp_sum(s.s0); s.s1 = warp_sum(s.s1); s.s2 = warp_sum(s.s2); s.s01 = warp_sum(s.s01); s.s02 = warp_sum(s.s02); s.n = warp_sum(s.n);
-	if (lane < 6) tileCnt[tile * 6 + lane] = raw_symbol(s, (uint32_t)lane);
+	if (lane < 3) { uint32_t pk[3]; raw_pack16(s, pk); tileCnt[tile * 3 + lane] = lane == 0 ? pk[0] : (lane == 1 ? pk[1] : pk[2]); }
 }
 
 // occ(a, x) on the flat array, all six symbols, one warp; result in every lane

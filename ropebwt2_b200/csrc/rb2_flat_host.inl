@@ -82,8 +82,8 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 		f.s[0].need(flat_bytes(cap)); f.dir[0].need((cap / FT_DIR + 3) * 6);
 	}
 	f.s[f.cur ^ 1].need(flat_bytes(cap)); f.dir[f.cur ^ 1].need((cap / FT_DIR + 3) * 6);
-	f.tileCnt.need((cap / FT_DIR + 3) * 6);
-	f.desc.need(cap / FS_SLICE + 4); f.ovf.need(cap / FS_SLICE + 8);
+	f.tileCnt.need((cap / FT_DIR + 3) * 3);
+	f.desc.need(cap / FS_SLICE + 4);
 	if (!f.valid) {
 		f.n = n0;
 		if (n0 > 0) {
@@ -92,7 +92,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 			LAUNCH(e, k_blocks_to_flat, cdiv(e->nlog, 4), 128, 0, e->pool, d.order, d.cumLen, e->nlog, e->comm ? e->dDirOff : (const int64_t*)0,
 			       e->dctl->blkBkt, e->nb, f.s[0].p, e->dctl);
 			LAUNCH(e, k_flat_count_tiles, cdiv((n0 + FT_DIR - 1) / FT_DIR, 8), 256, 0, f.s[0].p, n0, f.tileCnt.p);
-		} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 24, e->st));
+		} else RB2_CUDA(cudaMemsetAsync(f.tileCnt.p, 0, 12, e->st));
 		flat_scan_dir(e, 0, n0);
 	}
 	ph_end(e, PH_CONVERT);
@@ -107,18 +107,17 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FS_SLICE - 1) / FS_SLICE; // slices: one warp each
 	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
-	f.tileCnt.need((nNew / FT_DIR + 3) * 6); f.desc.need(nNew / FS_SLICE + 4); f.ovf.need(nTiles + 8);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 3); f.desc.need(nNew / FS_SLICE + 4);
 	ph_begin(e, PH_MERGE);
 	// leanP: all-singleton column -- the records are the state arrays themselves (position = leanP[r], symbol = asym[r], count 1, r symbols in front)
 	const RecView V = leanP ? RecView{ leanP, 0, 0, asym ? asym : e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
 	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, f.desc.p);
-	RB2_CUDA(cudaMemsetAsync(f.ovf.p, 0, 8, e->st));
 	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
-	                f.desc.p, (uint32_t)nTiles, f.ovf.p, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	if (V.sc) LAUNCH(e, (k_flat_merge<true>), (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 3), FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem<true>), fa);
-	else LAUNCH(e, (k_flat_merge<false>), (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 4), FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem<false>), fa);
-	LAUNCH(e, k_flat_merge_dense, e->nSM * 4, FS_WARPS * 32, FS_WARPS * sizeof(SliceDenseSmem), fa);
+	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 8);
+	if (V.sc) LAUNCH(e, (k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
+	else LAUNCH(e, (k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);
@@ -180,7 +179,7 @@ static void release_batch_scratch(rb2_engine *e)
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
 	e->strEnd.release(); e->tileA.release(); e->tileB.release(); e->grpCta.release();
 	FlatState &f = e->flat;
-	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.desc.release(); f.ovf.release();
+	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.desc.release();
 }
 
 // flat array -> leaf blocks: buckets are encoded independently
