@@ -86,8 +86,18 @@ void rb2_reset(rb2_engine_t *e);
 void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s_host);
 void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev);
 
-/* c[b*6+a] = number of symbols a in bucket b (bucket b = symbols followed by b) */
+/* c[b*6+a] = number of symbols a in bucket b (bucket b = symbols followed by b).
+ * rb2_insert_multi on a one-GPU engine returns as soon as the batch has been copied to the device (the caller's
+ * buffer is free again, main.c:243); the insertion runs on a worker thread while the caller prepares the next
+ * batch.  The counts cover everything submitted (they follow from the batches alone); every other call first
+ * waits for the queued batches.  RB2_ASYNC=0 makes rb2_insert_multi wait for the insertion itself. */
 void rb2_counts(rb2_engine_t *e, int64_t c[36]);
+/* wait for all queued batches (what every call except rb2_insert_multi / rb2_counts / rb2_reset does implicitly) */
+void rb2_sync(rb2_engine_t *e);
+/* device-timed span of a stream of calls: milliseconds (CUDA events) from rb2_span_begin to the end of the last
+ * insertion queued before rb2_span_ms */
+void rb2_span_begin(rb2_engine_t *e);
+double rb2_span_ms(rb2_engine_t *e);
 
 /* cx[a] = #a in BWT[0,x), cy[a] = #a in BWT[0,y) over the concatenated buckets; y < 0 or
  * cy == NULL skips the second query (mr_rank1a) */

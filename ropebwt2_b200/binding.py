@@ -25,7 +25,7 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_create_auto", "rb2_destroy
                "rb2_bucket_rank2a", "rb2_last_sentinel_rank",
                "rb2_group_create", "rb2_group_destroy", "rb2_nccl_unique_id", "rb2_create_sharded",
                "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets",
-               "rb2_rank_batch"]
+               "rb2_rank_batch", "rb2_sync", "rb2_span_begin", "rb2_span_ms"]
 
 
 class Stats(C.Structure):
@@ -131,6 +131,10 @@ def load(rebuild: bool = False, path: str = None) -> C.CDLL:
     L.rb2_shard_owner.restype = C.c_int
     L.rb2_shard_owner.argtypes = [C.c_int, C.c_int]
     L.rb2_rank_batch.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
+    L.rb2_sync.argtypes = [C.c_void_p]
+    L.rb2_span_begin.argtypes = [C.c_void_p]
+    L.rb2_span_ms.restype = C.c_double
+    L.rb2_span_ms.argtypes = [C.c_void_p]
     L.rb2_num_buckets.restype = C.c_int
     L.rb2_num_buckets.argtypes = [C.c_void_p]
     _lib = L

@@ -26,6 +26,10 @@
 #include <string.h>
 #include <algorithm>
 #include <vector>
+#include <deque>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 #include "rb2_codec.cuh"
 #include "rb2_comm.h"
 #include "../../include/ropebwt2_b200.h"
@@ -127,6 +131,38 @@ __global__ void k_maxlen(const int64_t *strEnd, uint32_t kBase, uint32_t m, unsi
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) { unsigned long long y = __shfl_xor_sync(FULLMASK, l, o); l = y > l ? y : l; }
 	if ((threadIdx.x & 31) == 0 && l) atomicMax(maxlen, l);
+}
+
+// hist[b*6+a] += #positions i with s[i-1] == b (0 in front of the batch) and s[i] == a.  The BWT symbol a = s[i] of a
+// (reversed, NUL-terminated) string sits in bucket b = s[i-1], and a string's sentinel is the pair (last symbol, NUL):
+// these are exactly the marginal counts mr_get_c reports (mrope.h:86-97), available as soon as the batch is on the
+// device -- the insertion itself may still be running (rb2_insert_multi returns once the copy is done).
+// Persistent CTAs; lane-private shared-memory bins (no atomics, no bank conflicts).
+__global__ void __launch_bounds__(256) k_pair_hist(const uint8_t *s, int64_t len, unsigned long long *hist)
+{
+	__shared__ uint32_t bins[36][256];
+	const int tid = threadIdx.x;
+	for (int k = 0; k < 36; ++k) bins[k][tid] = 0;
+	const int64_t nChunk = (len + 15) / 16;
+	for (int64_t c = (int64_t)blockIdx.x * 256 + tid; c < nChunk; c += (int64_t)gridDim.x * 256) {
+		const int64_t off = c * 16;
+		uint32_t prev = off ? s[off - 1] : 0u;
+		uint8_t b[16];
+		if (off + 16 <= len) { const uint4 v = *reinterpret_cast<const uint4*>(s + off); memcpy(b, &v, 16); }
+		else for (int i = 0; i < 16; ++i) b[i] = off + i < len ? s[off + i] : 255;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			const uint32_t a = b[i];
+			if (a < 6u && prev < 6u) ++bins[prev * 6 + a][tid];
+			prev = a;
+		}
+	}
+	__syncthreads();
+	if (tid < 36) {
+		unsigned long long t = 0;
+		for (int k = 0; k < 256; ++k) t += bins[tid][(k + tid) & 255];
+		if (t) atomicAdd(hist + tid, t);
+	}
 }
 
 // Column-major symbol matrix of a batch, 4 bits per symbol: byte T[j*tstride + (k >> 1)], nibble k & 1,
@@ -1857,6 +1893,9 @@ struct rb2_engine {
 	rb2_stats_t stats;
 	int64_t lastP; int lastBkt; // single-string batches: where the sentinel went
 	cudaEvent_t ev[PH_N][2], evTot[2];
+	// asynchronous pipeline of the host entry point (rb2_async.inl): rb2_insert_multi returns when the batch is on the
+	// device; a worker thread runs the insertions in order while the caller prepares / copies the next batch
+	struct AsyncState *as;
 };
 
 static void dir_alloc(Dir &d, size_t cap)
@@ -2002,6 +2041,11 @@ extern "C" int rb2_device_count(void)
 	return n;
 }
 
+static bool async_enabled(const rb2_engine *e); // rb2_async.inl: the host entry point as a pipeline
+static void async_drain(rb2_engine *e);
+static void async_init(rb2_engine *e);
+static void async_destroy(rb2_engine *e);
+static void async_reset(rb2_engine *e);
 static void ensure_blocks(rb2_engine *e);  // rb2_flat_host.inl: rebuild the leaf blocks from the resident flat array if they are stale
 static void blocks_edited(rb2_engine *e);  // ... and drop the array when the blocks change underneath it
 static void cluster_attach(rb2_engine *e, int device, int sorting_order);
@@ -2058,16 +2102,24 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	ctl_push(e);
 	rebuild_directory(e, false);
 	pull_totals(e);
+	e->as = 0;
 	if (multi) cluster_attach(e, device, sorting_order);
+	if (async_enabled(e)) async_init(e);
 	return e;
 }
 
 // Empty the index but keep every allocation (bench steps and tests reuse one engine).
 static void shard_reset_index(rb2_engine *e);
+static void reset_index(rb2_engine *e);
 extern "C" void rb2_reset(rb2_engine_t *e)
 {
 	if (e->nChild) { cluster_reset(e); return; }
 	RB2_CUDA(cudaSetDevice(e->dev));
+	if (async_enabled(e)) { async_reset(e); return; } // queued behind the batches in flight
+	reset_index(e);
+}
+static void reset_index(rb2_engine *e)
+{
 	e->flat.valid = false; e->flat.blocksStale = false;
 	if (e->comm) { shard_reset_index(e); return; }
 	RB2_CUDA(cudaMemsetAsync(e->pool, 0, 6 * RB2_BLK, e->st));
@@ -2095,6 +2147,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	if (!e) return;
 	if (e->nChild) cluster_destroy(e);
 	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e); async_destroy(e);
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->pool) { RB2_CUDA(cudaFree(e->pool)); RB2_CUDA(cudaFree(e->blkCnt)); }
 	dir_free(e->dir[0]); dir_free(e->dir[1]);
@@ -2418,11 +2471,14 @@ static void insert_string_range(rb2_engine *e, const uint8_t *s, uint32_t kBase,
 // huge inputs are processed as several device batches to bound the per-batch working set.
 #define RB2_MAX_BATCH_BYTES (24ll << 30)
 
+#include "rb2_async.inl"
+
 extern "C" void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev)
 {
 	if (len <= 0) RB2_FATAL("mr_insert_multi: empty batch (mrope.c:268)");
 	RB2_NO_CLUSTER(e, "rb2_insert_multi_dev");
 	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e);
 	if (((uintptr_t)s_dev & 15) != 0) RB2_FATAL("device batch must be 16-byte aligned");
 	if (len > RB2_MAX_BATCH_BYTES) RB2_FATAL("device-resident batches are limited to %lld bytes; use the host entry point", (long long)RB2_MAX_BATCH_BYTES);
 	RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
@@ -2431,6 +2487,7 @@ extern "C" void rb2_insert_multi_dev(rb2_engine_t *e, int64_t len, const uint8_t
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	float ms = 0; RB2_CUDA(cudaEventElapsedTime(&ms, e->evTot[0], e->evTot[1]));
 	e->stats.ms_total += ms;
+	if (e->as) memcpy(e->as->pub, e->tot, sizeof(e->tot));
 }
 
 extern "C" void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s)
@@ -2438,6 +2495,8 @@ extern "C" void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s)
 	if (len <= 0 || s[len - 1] != 0) RB2_FATAL("mr_insert_multi: batch must be non-empty and end with NUL (mrope.c:268)");
 	if (e->nChild) { cluster_insert_multi(e, len, s); return; }
 	RB2_CUDA(cudaSetDevice(e->dev));
+	if (async_enabled(e) && len <= RB2_MAX_BATCH_BYTES) { async_insert_multi(e, len, s); return; }
+	async_drain(e);
 	RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
 	int64_t off = 0;
 	while (off < len) {
@@ -2460,11 +2519,38 @@ extern "C" void rb2_insert_multi(rb2_engine_t *e, int64_t len, const uint8_t *s)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	float ms = 0; RB2_CUDA(cudaEventElapsedTime(&ms, e->evTot[0], e->evTot[1]));
 	e->stats.ms_total += ms;
+	if (e->as) memcpy(e->as->pub, e->tot, sizeof(e->tot));
 }
 
+// marginal counts c[b][a] (mr_get_c).  With batches still in flight these are the counts of everything SUBMITTED:
+// they follow from the batches alone (k_pair_hist), so the call does not wait for the insertions.
 extern "C" void rb2_counts(rb2_engine_t *e, int64_t c[36])
 {
+	if (e->as && e->as->started) { for (int b = 0; b < 6; ++b) for (int a = 0; a < 6; ++a) c[b * 6 + a] = e->as->pub[b][a]; return; }
 	for (int b = 0; b < 6; ++b) for (int a = 0; a < 6; ++a) c[b * 6 + a] = e->tot[b][a];
+}
+
+// wait for every queued batch (what any other call does implicitly)
+extern "C" void rb2_sync(rb2_engine_t *e) { RB2_CUDA(cudaSetDevice(e->dev)); async_drain(e); }
+
+// device time of a stream of calls: rb2_span_begin() ... calls ... rb2_span_ms() = milliseconds between the first copy
+// and the end of the last insertion, measured with CUDA events (copies of later batches overlap earlier insertions)
+extern "C" void rb2_span_begin(rb2_engine_t *e)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e);
+	cudaEvent_t ev = e->as ? e->as->evSpan[0] : e->evTot[0];
+	RB2_CUDA(cudaEventRecord(ev, e->as ? e->as->copySt : e->st));
+}
+extern "C" double rb2_span_ms(rb2_engine_t *e)
+{
+	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e);
+	if (!e->as) return 0.0;
+	RB2_CUDA(cudaEventRecord(e->as->evSpan[1], e->st));
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	float ms = 0; RB2_CUDA(cudaEventElapsedTime(&ms, e->as->evSpan[0], e->as->evSpan[1]));
+	return ms;
 }
 
 extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6])
@@ -2476,6 +2562,7 @@ extern "C" void rb2_rank2a(rb2_engine_t *e, int64_t x, int64_t y, int64_t cx[6],
 		return;
 	}
 	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e);
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
 	if (x < 0 || x > total || y > total) RB2_FATAL("rank position out of range");
@@ -2493,6 +2580,7 @@ extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int
 	RB2_CUDA(cudaSetDevice(e->dev));
 	RB2_NO_CLUSTER(e, "rb2_rank_batch");
 	if (e->comm) RB2_FATAL("rb2_rank_batch: not available on a sharded engine yet");
+	async_drain(e);
 	ensure_blocks(e);
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
@@ -2515,6 +2603,7 @@ extern "C" int64_t rb2_num_blocks(rb2_engine_t *e, int bucket)
 	if (bucket < 0 || bucket >= e->nb) RB2_FATAL("bucket out of range");
 	if (e->nChild) return cluster_num_blocks(e, bucket);
 	RB2_CUDA(cudaSetDevice(e->dev));
+	async_drain(e);
 	ensure_blocks(e);
 	return (int64_t)e->blkBkt[bucket + 1] - e->blkBkt[bucket];
 }
@@ -2543,6 +2632,7 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
 	if (n <= 0) return;
+	async_drain(e);
 	ensure_blocks(e); blocks_edited(e);
 	// the bucket's blocks are [blkBkt[b], blkBkt[b+1]); new blocks are inserted at its right end.
 	// An initially empty bucket consists of one empty block, which is replaced.
@@ -2575,11 +2665,19 @@ extern "C" void rb2_load_blocks(rb2_engine_t *e, int bucket, int64_t n, const ui
 	pull_totals(e);
 	e->stats.pool_blocks = e->hctl->poolUsed;
 	e->stats.pool_capacity = e->poolCap;
+	if (e->as) memcpy(e->as->pub, e->tot, sizeof(e->tot));
 }
 
-extern "C" void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st) { *st = e->stats; }
+extern "C" void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st)
+{
+	async_drain(e);
+	*st = e->stats;
+	if (e->as) { st->ms_h2d += e->as->h2dMs; st->ms_total += e->as->h2dMs; } // the copies run on the caller's thread
+}
 extern "C" void rb2_reset_stats(rb2_engine_t *e)
 {
+	async_drain(e);
+	if (e->as) e->as->h2dMs = 0;
 	for (int r = 0; r < e->nChild; ++r) rb2_reset_stats(e->child[r]);
 	int64_t pb = e->stats.pool_blocks, pc = e->stats.pool_capacity;
 	memset(&e->stats, 0, sizeof(e->stats));
@@ -2621,6 +2719,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	RB2_NO_CLUSTER(e, "rope_insert_run");
 	RB2_CUDA(cudaSetDevice(e->dev));
 	if (bucket < 0 || bucket > 5 || a < 0 || a > 5 || rl <= 0) RB2_FATAL("rb2_insert_run: bad argument");
+	async_drain(e);
 	if (x < 0 || x > e->bktLen[bucket]) RB2_FATAL("rb2_insert_run: position out of range");
 	ensure_blocks(e); blocks_edited(e);
 	const uint32_t k = (uint32_t)((rl + RB2_MAXRUN - 1) / RB2_MAXRUN);
@@ -2644,6 +2743,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 	for (int b = 0; b < bucket; ++b) z -= e->tot[b][a];
 	pull_totals(e);
 	e->stats.pool_blocks = e->hctl->poolUsed; e->stats.pool_capacity = e->poolCap;
+	if (e->as) memcpy(e->as->pub, e->tot, sizeof(e->tot));
 	return z;
 }
 
@@ -2651,6 +2751,7 @@ extern "C" int64_t rb2_insert_run(rb2_engine_t *e, int bucket, int64_t x, int a,
 extern "C" void rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_t y, int64_t cx[6], int64_t cy[6])
 {
 	if (bucket < 0 || bucket > 5) RB2_FATAL("bucket out of range");
+	async_drain(e);
 	if (x < 0 || x > e->bktLen[bucket] || y > e->bktLen[bucket]) RB2_FATAL("rope_rank2a: position out of range");
 	const int64_t s = bucket_start(e, bucket);
 	int64_t tmp[6];
@@ -2668,6 +2769,7 @@ extern "C" void rb2_bucket_rank2a(rb2_engine_t *e, int bucket, int64_t x, int64_
 extern "C" int64_t rb2_last_sentinel_rank(rb2_engine_t *e)
 {
 	RB2_NO_CLUSTER(e, "mr_insert1's return value");
+	async_drain(e);
 	int64_t cx[6];
 	rb2_rank2a(e, e->lastP, -1, cx, 0);
 	int64_t z = cx[0];

@@ -70,7 +70,20 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 {
 	FlatState &f = e->flat;
 	ph_begin(e, PH_CONVERT);
-	const uint64_t n0 = local_symbols(e), cap = n0 + addLocal + FT_PAD;
+	const uint64_t n0 = local_symbols(e);
+	uint64_t cap = n0 + addLocal + FT_PAD;
+	// Growing a multi-GB array costs an allocation and a copy: grow in steps of 1.5x while memory is plentiful, or
+	// straight to RB2_RESERVE symbols when the caller knows the final size of the index (the driver knows its input)
+	if (flat_bytes(cap) > f.s[f.cur].cap || flat_bytes(cap) > f.s[f.cur ^ 1].cap) {
+		static uint64_t reserve = ~0ull;
+		if (reserve == ~0ull) { const char *rs = getenv("RB2_RESERVE"); reserve = rs && *rs ? strtoull(rs, 0, 10) : 0; }
+		size_t freeB = 0, totB = 0;
+		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+		const uint64_t have = f.s[0].cap + f.s[1].cap;
+		uint64_t want = cap + cap / 2;
+		if (reserve + FT_PAD > cap) want = reserve + FT_PAD;
+		if (2 * flat_bytes(want) + want / 16 + ((uint64_t)24 << 30) < freeB + have) cap = want;
+	}
 	if (f.valid) {
 		if (f.n != n0) RB2_FATAL("internal: resident flat array holds %llu symbols, the index %llu", (unsigned long long)f.n, (unsigned long long)n0);
 		// the other buffer holds nothing live: release it first so that the peak is old + new current array

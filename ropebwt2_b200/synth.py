@@ -267,6 +267,7 @@ def fill_batch_np(dst: np.ndarray, w: dict, a: int, b: int, chunk: int = 2_000_0
 def fill_batch_torch(dst, w: dict, a: int, b: int, chunk: int = 8_000_000) -> None:
     """The same into a 1-D uint8 torch tensor on a GPU (dst.numel() == (b-a)*(L+1))."""
     import torch
+    chunk = max(1, min(chunk, 400_000_000 // (w["L"] + 1)))  # the generator works on int64 temporaries: bound them
     view = dst.view(b - a, w["L"] + 1)
     for x in range(a, b, chunk):
         y = min(b, x + chunk)

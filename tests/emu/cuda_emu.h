@@ -22,6 +22,13 @@
 #include <string.h>
 #include <functional>
 #include <vector>
+#include <algorithm>
+#include <deque>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <chrono>
+#include <atomic>
 
 #define __global__
 #define __device__

@@ -115,3 +115,30 @@ def test_resident_array_across_batches(monkeypatch, so):
     m.insert_multi(buf)
     assert np.array_equal(text(m), o.text())
     m.close()
+
+
+def test_pipelined_calls_and_eager_counts(monkeypatch):
+    """mr_insert_multi returns when the batch is on the device; the insertion runs behind it on a worker thread.
+    The marginal counts (mr_get_c) must be right immediately -- they are computed from the batch itself -- and a
+    reset queued between batches must take effect in order."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    n = sz(40000, 1500)
+    rd = genome_reads(n, sz(80, 40), 31, coverage=30.0)
+    o, m = orc.Oracle(1), MRope(1)
+    for k in range(4):  # back to back, nothing in between waits for the worker
+        buf = encode_batch(rd[k * n // 4:(k + 1) * n // 4])
+        o.insert_multi(buf)
+        m.insert_multi(buf)
+        assert np.array_equal(m.counts(), o.counts()), k
+    assert np.array_equal(text(m), o.text())
+    # reset + new batches, queued behind each other
+    L = load()
+    o2 = orc.Oracle(1)
+    L.rb2_reset(m.engine_handle)
+    for k in (3, 1):
+        buf = encode_batch(rd[k * n // 4:(k + 1) * n // 4])
+        o2.insert_multi(buf)
+        m.insert_multi(buf)
+    assert np.array_equal(m.counts(), o2.counts())
+    assert np.array_equal(text(m), o2.text())
+    m.close()
