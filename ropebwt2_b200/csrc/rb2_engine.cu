@@ -1958,9 +1958,19 @@ static void ctl_pull(rb2_engine *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	if (e->hctl->err) RB2_FATAL("device error flags 0x%x (1=block pool exhausted, 2=8-byte run in pool, 4=staging overflow, 8=scan mismatch, 16=too many pieces)", e->hctl->err);
 }
+// host copy of the control block -> device.  The block travels as a KERNEL ARGUMENT, not as a host-to-device copy:
+// a DMA copy would queue behind the 10 GB batch that the caller's thread may be uploading at the same time
+// (rb2_async.inl) and stall the column loop for the rest of that transfer.
+static_assert(sizeof(Ctl) <= 4000, "Ctl must fit the kernel parameter space");
+__global__ void __launch_bounds__(256) k_ctl_store(Ctl *dst, const Ctl v)
+{
+	const uint32_t *src = reinterpret_cast<const uint32_t*>(&v);
+	uint32_t *d = reinterpret_cast<uint32_t*>(dst);
+	for (uint32_t i = threadIdx.x; i < sizeof(Ctl) / 4; i += 256) d[i] = src[i];
+}
 static void ctl_push(rb2_engine *e)
 {
-	RB2_CUDA(cudaMemcpyAsync(e->dctl, e->hctl, sizeof(Ctl), cudaMemcpyHostToDevice, e->st));
+	LAUNCH(e, k_ctl_store, 1, 256, 0, e->dctl, *e->hctl);
 }
 
 // rebuild cumLen/cumCnt of the current directory from blkCnt + order

@@ -593,10 +593,11 @@ __global__ void __launch_bounds__(256) k_column_fused(FusedArgs A)
 }
 
 // per-bucket symbol totals of the array: out[k][a] = occ(a, pos[k]) for up to 64 positions (one warp each)
-__global__ void __launch_bounds__(32) k_flat_rank_at(const uint8_t *flat, const int64_t *dir, const int64_t *pos, int64_t *out)
+struct RankAtPos { int64_t pos[8]; };
+__global__ void __launch_bounds__(32) k_flat_rank_at(const uint8_t *flat, const int64_t *dir, const RankAtPos P, int64_t *out)
 {
 	int64_t c[6];
-	flat_rank6(flat, dir, pos[blockIdx.x], threadIdx.x, c);
+	flat_rank6(flat, dir, P.pos[blockIdx.x], threadIdx.x, c);
 	if (threadIdx.x < 6) {
 		int64_t v = 0;
 #pragma unroll

@@ -177,8 +177,8 @@ static void flat_finish(rb2_engine *e)
 	for (int b = 0; b <= 6; ++b) { hpos[b] = acc; if (b < 6) acc += e->bktLen[b]; }
 	if ((uint64_t)acc != f.n) RB2_FATAL("internal: flat array holds %llu symbols, the buckets %lld", (unsigned long long)f.n, (long long)acc);
 	e->stageCnt.need(8 + 8 * 6);
-	RB2_CUDA(cudaMemcpyAsync(e->stageCnt.p, hpos, 7 * 8, cudaMemcpyHostToDevice, e->st));
-	LAUNCH(e, k_flat_rank_at, 7, 32, 0, f.s[f.cur].p, f.dir[f.cur].p, e->stageCnt.p, e->stageCnt.p + 8);
+	RankAtPos rp; for (int b = 0; b < 8; ++b) rp.pos[b] = b <= 6 ? hpos[b] : 0;
+	LAUNCH(e, k_flat_rank_at, 7, 32, 0, f.s[f.cur].p, f.dir[f.cur].p, rp, e->stageCnt.p + 8); // (positions as a kernel argument: no host-to-device copy on this path)
 	RB2_CUDA(cudaMemcpyAsync(hout, e->stageCnt.p + 8, 7 * 6 * 8, cudaMemcpyDeviceToHost, e->st));
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	for (int b = 0; b < 6; ++b) for (int a = 0; a < 6; ++a) e->tot[b][a] = hout[(b + 1) * 6 + a] - hout[b * 6 + a];

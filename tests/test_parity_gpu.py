@@ -324,3 +324,34 @@ def test_one_long_string_among_short_ones(so):
     assert np.array_equal(m.counts(), o.counts())
     assert np.array_equal(gpu_text(m), o.text())
     m.close()
+
+
+@not_on_emu
+def test_beyond_2_32_symbols_md5_vs_reference():
+    """45 M x 101 bp = 4.59 G symbols (> 2^32 positions) in one batch, RLO: md5 of the decoded index against the
+    md5 of the UNMODIFIED reference's output on the same seeded reads (tests/golden/ref_full_runs.json, recorded
+    by tools/ref_full_run.py --workload cfg2 --reads 45000000).  Reads are generated on the GPU with the
+    counter-based generator that tests/test_synth.py pins to the one that fed the reference."""
+    import torch
+    from ropebwt2_b200 import synth
+    w = synth.workload("cfg2", 45_000_000)
+    rec = orc.ref_recorded(w, "-LRs")
+    if rec is None:
+        pytest.skip("no recorded reference run for " + synth.workload_key(w, "-LRs"))
+    nbytes = w["n"] * (w["L"] + 1)
+    host = np.empty(nbytes, dtype=np.uint8)
+    ht = torch.from_numpy(host)
+    step = 3_000_000
+    for a in range(0, w["n"], step):
+        b = min(w["n"], a + step)
+        t = torch.empty((b - a) * (w["L"] + 1), dtype=torch.uint8, device="cuda")
+        synth.fill_batch_torch(t, w, a, b)
+        ht[a * (w["L"] + 1):b * (w["L"] + 1)].copy_(t)
+        del t
+    torch.cuda.empty_cache()
+    m = MRope(1)
+    m.insert_multi(host)
+    assert m.total() == nbytes
+    md5, total = orc.index_md5(load(), m.h)
+    assert total == nbytes and md5 == rec["md5_text"]
+    m.close()
