@@ -98,6 +98,8 @@ void rb2_sync(rb2_engine_t *e);
  * insertion queued before rb2_span_ms */
 void rb2_span_begin(rb2_engine_t *e);
 double rb2_span_ms(rb2_engine_t *e);
+/* per-batch statistics of the last (at most `max`) rb2_insert_multi calls since rb2_reset_stats, oldest first */
+int rb2_job_history(rb2_engine_t *e, rb2_stats_t *out, int max);
 
 /* cx[a] = #a in BWT[0,x), cy[a] = #a in BWT[0,y) over the concatenated buckets; y < 0 or
  * cy == NULL skips the second query (mr_rank1a) */

@@ -25,7 +25,7 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_create_auto", "rb2_destroy
                "rb2_bucket_rank2a", "rb2_last_sentinel_rank",
                "rb2_group_create", "rb2_group_destroy", "rb2_nccl_unique_id", "rb2_create_sharded",
                "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets",
-               "rb2_rank_batch", "rb2_sync", "rb2_span_begin", "rb2_span_ms"]
+               "rb2_rank_batch", "rb2_sync", "rb2_span_begin", "rb2_span_ms", "rb2_job_history"]
 
 
 class Stats(C.Structure):
@@ -135,6 +135,8 @@ def load(rebuild: bool = False, path: str = None) -> C.CDLL:
     L.rb2_span_begin.argtypes = [C.c_void_p]
     L.rb2_span_ms.restype = C.c_double
     L.rb2_span_ms.argtypes = [C.c_void_p]
+    L.rb2_job_history.restype = C.c_int
+    L.rb2_job_history.argtypes = [C.c_void_p, C.POINTER(Stats), C.c_int]
     L.rb2_num_buckets.restype = C.c_int
     L.rb2_num_buckets.argtypes = [C.c_void_p]
     _lib = L
@@ -202,6 +204,12 @@ class MRope:
 
     def reset_stats(self) -> None:
         self.L.rb2_reset_stats(self.engine_handle)
+
+    def job_history(self, n: int = 64):
+        """Per-batch statistics of the last n mr_insert_multi calls (waits for the queued batches)."""
+        arr = (Stats * n)()
+        k = self.L.rb2_job_history(self.engine_handle, arr, n)
+        return [arr[i].as_dict() for i in range(k)]
 
     def dump(self, path: str) -> None:
         libc = _libc()

@@ -24,6 +24,7 @@ struct AsyncState {
 	cudaStream_t copySt = 0; cudaEvent_t evH[2], evSpan[2];
 	unsigned long long *dHist = 0, *hHist = 0;
 	int64_t pub[6][6];   // marginal counts of everything submitted so far (what rb2_counts answers without waiting)
+	std::vector<rb2_stats_t> hist; std::vector<double> histH2d; // per batch: what the insertion added to the statistics, and its copy time
 	double h2dMs = 0;    // copy time of the caller's thread (folded into the statistics when they are read)
 };
 
@@ -32,6 +33,20 @@ static bool async_enabled(const rb2_engine *e)
 	static int pref = -1;
 	if (pref < 0) { const char *s = getenv("RB2_ASYNC"); pref = !(s && *s == '0'); }
 	return pref && !e->comm && !e->nChild;
+}
+
+// b - a, field by field (every field of rb2_stats_t is 8 bytes wide: int64_t or double)
+static rb2_stats_t stats_delta(const rb2_stats_t &a, const rb2_stats_t &b)
+{
+	static_assert(sizeof(rb2_stats_t) == 23 * 8, "rb2_stats_t: 23 fields of 8 bytes");
+	const uint32_t isDouble = 0xffu << 10 | 1u << 19 | 1u << 21; // ms_total .. ms_merge_general, ms_exchange, ms_convert
+	rb2_stats_t d;
+	for (int i = 0; i < 23; ++i) {
+		if (isDouble >> i & 1) ((double*)&d)[i] = ((const double*)&b)[i] - ((const double*)&a)[i];
+		else ((int64_t*)&d)[i] = ((const int64_t*)&b)[i] - ((const int64_t*)&a)[i];
+	}
+	d.pool_blocks = b.pool_blocks; d.pool_capacity = b.pool_capacity;
+	return d;
 }
 
 static void async_worker(rb2_engine *e)
@@ -46,6 +61,7 @@ static void async_worker(rb2_engine *e)
 			if (A.q.empty()) return; // stop
 			j = A.q.front(); A.q.pop_front(); A.busy = true;
 		}
+		const rb2_stats_t before = e->stats;
 		if (j.kind == 0) {
 			RB2_CUDA(cudaEventRecord(e->evTot[0], e->st));
 			insert_device_batch(e, j.len, A.stage[j.stage].p);
@@ -56,7 +72,7 @@ static void async_worker(rb2_engine *e)
 		} else reset_index(e);
 		{
 			std::lock_guard<std::mutex> lk(A.mu);
-			if (j.kind == 0) A.stageBusy[j.stage] = false;
+			if (j.kind == 0) { A.stageBusy[j.stage] = false; A.hist.push_back(stats_delta(before, e->stats)); }
 			A.busy = false;
 		}
 		A.cv.notify_all();
@@ -135,6 +151,7 @@ static void async_insert_multi(rb2_engine *e, int64_t len, const uint8_t *s)
 	for (int k = 0; k < 36; ++k) { A.pub[k / 6][k % 6] += (int64_t)A.hHist[k]; tot += (int64_t)A.hHist[k]; }
 	if (tot != len) RB2_FATAL("mr_insert_multi: the batch holds bytes outside the nt6 alphabet 0..5 (%lld of %lld are valid)", (long long)tot, (long long)len);
 	A.h2dMs += ms;
+	{ std::lock_guard<std::mutex> lk(A.mu); A.histH2d.push_back(ms); }
 	AsyncJob j = { 0, len, b };
 	async_submit(e, j);
 }

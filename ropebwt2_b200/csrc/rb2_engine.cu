@@ -2543,6 +2543,22 @@ extern "C" void rb2_counts(rb2_engine_t *e, int64_t c[36])
 // wait for every queued batch (what any other call does implicitly)
 extern "C" void rb2_sync(rb2_engine_t *e) { RB2_CUDA(cudaSetDevice(e->dev)); async_drain(e); }
 
+// what each of the last batches (oldest first, at most `max`) added to the statistics; ms_h2d = its copy.  Lets a
+// caller that streams batches back to back see per-batch numbers without waiting between the calls.
+extern "C" int rb2_job_history(rb2_engine_t *e, rb2_stats_t *out, int max)
+{
+	async_drain(e);
+	if (!e->as) return 0;
+	AsyncState &A = *e->as;
+	const int n = (int)std::min<size_t>(A.hist.size(), (size_t)max);
+	for (int i = 0; i < n; ++i) {
+		const size_t k = A.hist.size() - n + i;
+		out[i] = A.hist[k];
+		if (k < A.histH2d.size()) { out[i].ms_h2d = A.histH2d[k]; out[i].ms_total += A.histH2d[k]; }
+	}
+	return n;
+}
+
 // device time of a stream of calls: rb2_span_begin() ... calls ... rb2_span_ms() = milliseconds between the first copy
 // and the end of the last insertion, measured with CUDA events (copies of later batches overlap earlier insertions)
 extern "C" void rb2_span_begin(rb2_engine_t *e)
@@ -2687,7 +2703,7 @@ extern "C" void rb2_get_stats(rb2_engine_t *e, rb2_stats_t *st)
 extern "C" void rb2_reset_stats(rb2_engine_t *e)
 {
 	async_drain(e);
-	if (e->as) e->as->h2dMs = 0;
+	if (e->as) { e->as->h2dMs = 0; e->as->hist.clear(); e->as->histH2d.clear(); }
 	for (int r = 0; r < e->nChild; ++r) rb2_reset_stats(e->child[r]);
 	int64_t pb = e->stats.pool_blocks, pc = e->stats.pool_capacity;
 	memset(&e->stats, 0, sizeof(e->stats));

@@ -169,6 +169,9 @@ struct SliceIn {
 	__device__ __forceinline__ uint32_t SC(uint32_t k) const { return sc ? sc[k] : (8u | asym[k]); }
 };
 
+// record k = lane of a slice, fetched one slice ahead (the loads' latency hides under the previous slice's merge)
+struct RecRegs { int64_t P; uint32_t pre, sc, dst; bool have; };
+
 // set the new-symbol masks of output positions [key, key+len) of the slice
 __device__ __forceinline__ void slice_mark(SliceWork &W, uint32_t key, uint32_t len, uint32_t sy)
 {
@@ -201,7 +204,7 @@ __device__ __forceinline__ Cell slice_cell(const uint32_t *old, uint32_t oldIdx,
 }
 
 template <bool GENERAL>
-__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane)
+__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane, const RecRegs &pf)
 {
 	const uint64_t o0 = (uint64_t)slice * FS_SLICE;
 	const uint32_t sliceLen = A.nNew - o0 < FS_SLICE ? (uint32_t)(A.nNew - o0) : FS_SLICE;
@@ -237,14 +240,15 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	// ---- (2) records -> masks ----------------------------------------------------------------------------
 	if (lane == 0 && carryLen) slice_mark(W, 0, carryLen, carrySym);
 	for (uint32_t k = lane; k < nr; k += 32) {
-		const uint32_t key = (uint32_t)((uint64_t)in.P[k] + in.Pre(k) - o0);
+		const bool reg = pf.have && k < 32;
+		const uint32_t key = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) + (reg ? pf.pre : in.Pre(k)) - o0);
 		if (GENERAL) {
-			const uint32_t sc = in.SC(k);
+			const uint32_t sc = reg ? pf.sc : in.SC(k);
 			uint32_t len = sc >> 3;
 			if (len > FS_SLICE - key) len = FS_SLICE - key;
 			slice_mark(W, key, len, sc & 7u);
 		} else {
-			const uint32_t sy = in.asym[k], c = key / FT_CH, bit = 1u << (key & (FT_CH - 1));
+			const uint32_t sy = reg ? pf.sc : (uint32_t)in.asym[k], c = key / FT_CH, bit = 1u << (key & (FT_CH - 1));
 			atomicOr(&W.mask[c][0], bit);
 			if (sy & 1u) atomicOr(&W.mask[c][1], bit);
 			if (sy & 2u) atomicOr(&W.mask[c][2], bit);
@@ -288,10 +292,11 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	{
 		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
 		for (uint32_t k = lane; k < nr; k += 32) {
-			const uint32_t dst = in.dst[k];
+			const bool reg = pf.have && k < 32;
+			const uint32_t dst = reg ? pf.dst : in.dst[k];
 			if (dst == NONE32) continue;
-			const uint32_t a = GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k];
-			const uint32_t xo = (uint32_t)((uint64_t)in.P[k] - a0); // old symbols of the window in front of the record
+			const uint32_t a = reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]);
+			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
 			const uint32_t c = xo / FT_CH;
 			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
 			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
@@ -333,12 +338,28 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 8) k_flat_merge(FlatArgs A)
 		const bool ok = lane == 0 && sl < A.nSlices;
 		issue(s, sl, ok ? A.desc[sl] : none, ok ? A.desc[sl + 1] : none);
 	}
+	__syncwarp();
+	RecRegs pf = { 0, 0, 0, 0, false }, pfNext = { 0, 0, 0, 0, false };
 	for (uint32_t n = 0; ; ++n) {
 		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
 		mbar_wait(&S.full[s], ph);
 		const SliceStage &st = S.st[s];
 		const uint32_t slice = st.slice;
 		if (slice == NONE32) break;
+		{ // records k = lane of the slice in the other stage (merged next; its geometry was stored when it was issued)
+			const SliceStage &sn = S.st[s ^ 1];
+			pfNext.have = false;
+			if (FS_STAGES == 2 && sn.slice != NONE32) {
+				const uint32_t q0 = sn.d0.r0, qn = sn.d1.r0 - q0;
+				pfNext.have = true;
+				if ((uint32_t)lane < qn) {
+					const uint32_t r = q0 + lane;
+					pfNext.P = A.V.P[r]; pfNext.dst = A.recDst[r];
+					pfNext.pre = GENERAL ? A.V.pre[r] : r;
+					pfNext.sc = GENERAL ? A.V.sc[r] : (uint32_t)A.V.asym[r];
+				}
+			}
+		}
 		// geometry of the slice this stage gets next: loaded now, used behind the merge (the latency hides under it)
 		const uint32_t nextSl = slice + FS_STAGES * nWarps;
 		const bool ok = lane == 0 && nextSl < A.nSlices;
@@ -346,8 +367,10 @@ __global__ void __launch_bounds__(FS_WARPS * 32, 8) k_flat_merge(FlatArgs A)
 		const uint32_t r0 = st.d0.r0;
 		SliceIn in = { st.old, A.V.P + r0, GENERAL ? A.V.pre + r0 : (const uint32_t*)0, GENERAL ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
 		               GENERAL ? (const uint8_t*)0 : A.V.asym + r0, r0 };
-		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane);
+		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane, pf);
+		pf = pfNext;
 		issue(s, nextSl, nd0, nd1); // (behind the slice's closing __syncwarp: every lane is done with the stage)
+		__syncwarp();               // the stage's new geometry is visible to every lane (they prefetch its records next time round)
 	}
 	if (lane == 0) bulk_wait_read();
 }
