@@ -481,6 +481,12 @@ def run_multibatch(args, torch, red, rank, world, local):
         bufs.append(buf)
     t_gen = time.time() - t_gen
     torch.cuda.empty_cache()
+    # the driver's batch buffer: ONE pinned buffer, refilled by the host before every call (a host memcpy stands in for
+    # the reference driver's parser) and free again as soon as mr_insert_multi returns (main.c:243)
+    L.rb2_host_alloc.restype = C.c_void_p
+    cap = per * (ln + 1)
+    hptr = L.rb2_host_alloc(cap)
+    pinned = np.ctypeslib.as_array((C.c_uint8 * cap).from_address(hptr))
     mr = MRope(so)
     sampler = ClockSampler(local)
     sampler.start()
@@ -488,7 +494,8 @@ def run_multibatch(args, torch, red, rank, world, local):
     L.rb2_span_begin(mr.engine_handle)
     t0 = time.time()
     for buf in bufs:
-        mr.L.mr_insert_multi(mr.h, buf.size, buf.ctypes.data_as(C.POINTER(C.c_uint8)), 1)
+        np.copyto(pinned[:buf.size], buf)
+        mr.L.mr_insert_multi(mr.h, buf.size, C.cast(hptr, C.POINTER(C.c_uint8)), 1)
         tot = int(mr.counts().sum())   # mr_get_c: current on return (does not wait for the insertion)
     span_ms = L.rb2_span_ms(mr.engine_handle)  # waits for the last insertion
     wall = time.time() - t0
@@ -510,6 +517,7 @@ def run_multibatch(args, torch, red, rank, world, local):
     if not args.no_verify:
         parity = verify_md5(L, mr.h, w, flags)
     mr.close()
+    L.rb2_host_free(C.c_void_p(hptr))
     bp = n * ln
     ms_ins = sum(x["ms_insert"] for x in batches)
     e2e_val = bp / (span_ms * 1e-3) / 1e9
@@ -524,7 +532,8 @@ def run_multibatch(args, torch, red, rank, world, local):
                                % (args.config, synth.workload_key(w, flags), len(batches), per),
                    "l2": "every column streams the whole symbol array (GBs): far beyond the 126 MB L2", "parity": parity["result"],
                    "timing": "value: sum of the insertions' device times (CUDA events around every batch on the engine stream); e2e: one CUDA-event span from the first "
-                             "copy to the end of the last insertion, batches in pageable host memory, copies pipelined under the previous insertion; wall clock %.2f s" % wall,
+                             "copy to the end of the last insertion; every batch is memcpy'd by the host into one pinned buffer (the stand-in for the driver's parser) and handed to "
+                             "mr_insert_multi, whose copy runs under the previous batch's insertion; wall clock %.2f s" % wall,
                    "generation_s": round(t_gen, 1)},
         "parity": parity, "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": per * (ln + 1), "d2h_bytes_per_step": 7 * 48, "ms_per_step": span_ms / len(batches), "ms_job": span_ms,

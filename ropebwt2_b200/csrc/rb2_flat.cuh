@@ -96,11 +96,15 @@ struct RecView {
 };
 
 // ---- slice geometry ----------------------------------------------------------------------------------------
-// The unit of work of the merge is a SLICE: FS_SLICE = FT_DIR output symbols, produced by one warp.  One
+// The unit of work of the merge is a SLICE: FS_SLICE = FS_CPL * 1024 output symbols (FS_CPL output cells per lane),
+// a whole number of directory tiles, produced by one warp.  One
 // thread per slice boundary t (output position min(t*FS_SLICE, nNew)): the first record whose output run
 // starts at or behind it (bisection over the strictly increasing keys key_r = P_r + pre_r), the first old
 // symbol that lands at or behind it, and the record run that reaches across it from the left.
-#define FS_SLICE FT_DIR
+#ifndef FS_CPL
+#define FS_CPL 4                                   // output cells per lane: 2, 4 or 8
+#endif
+#define FS_SLICE (FS_CPL * 1024)
 struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FS_SLICE) << 3 | symbol
 
 __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, TileDesc *desc)
@@ -147,8 +151,12 @@ struct FlatArgs {
 // The kernel is persistent: every warp owns two shared-memory stages and fetches the old symbols of its slice
 // i+2 while it merges slice i (its lane 0 is the producer); the slice's records are read straight from the
 // record arrays (consecutive records in consecutive lanes).  No block-wide barrier anywhere.
-#define FS_CELLS (FS_SLICE / FT_CH)                 // 64 output cells, two per lane
-#define FS_OLDC  (FS_SLICE / FT_CH + FT_DIR / FT_CH + 2) // cells of old symbols a slice can need (+ funnel-shift partner)
+#define FS_CELLS (FS_SLICE / FT_CH)                 // output cells per slice, FS_CPL per lane
+#define FS_TILES (FS_SLICE / FT_DIR)                // directory tiles per slice
+#define FS_LPT   (32 / FS_TILES)                    // lanes per directory tile
+#define FS_PCL   (FS_CPL + FT_DIR / 1024)           // old cells per lane in the prefix pass
+#define FS_OLDC  (FS_PCL * 32 + 2)                  // cells of old symbols a slice can need (+ funnel-shift partner)
+#define FS_MINCTA (FS_CPL == 2 ? 8 : (FS_CPL == 4 ? 5 : 3)) // CTAs per SM the shared memory allows
 #define FS_OLDW  ((FS_OLDC * 3 + 3) & ~3)           // ... as words, a multiple of 16 bytes
 #define FS_OUTW  (FS_CELLS * 3)                     // words of one output slice
 #define FS_STAGES 2
@@ -212,16 +220,16 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < sliceLen ? (d0.carry >> 3) : sliceLen;
 	const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
 	const uint32_t skip = (uint32_t)(d0.i0 - a0);      // old symbols of the window in front of the slice's first one
-	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells 4l .. 4l+3) ---------------------
-	reinterpret_cast<uint4*>(&W.mask[0][0])[lane] = make_uint4(0, 0, 0, 0);
-	reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32] = make_uint4(0, 0, 0, 0);
+	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells l*FS_PCL .. +FS_PCL-1) -----------
+#pragma unroll
+	for (int j = 0; j < FS_CPL; ++j) reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32 * j] = make_uint4(0, 0, 0, 0);
 	{
-		uint32_t pk[4][3], inc[3];
+		uint32_t pk[FS_PCL][3], inc[3];
 		Raw6 r = { 0, 0, 0, 0, 0, 0 };
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+		for (int j = 0; j < FS_PCL; ++j) {
 			raw_pack16(r, pk[j]); // exclusive inside the lane
-			raw_addto(r, raw_of_cell(cell_load(in.old + (lane * 4 + j) * 3), 0xffffffffu, FT_CH));
+			raw_addto(r, raw_of_cell(cell_load(in.old + (lane * FS_PCL + j) * 3), 0xffffffffu, FT_CH));
 		}
 		raw_pack16(r, inc);
 		const uint32_t own[3] = { inc[0], inc[1], inc[2] };
@@ -231,9 +239,9 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			for (int k = 0; k < 3; ++k) { const uint32_t y = __shfl_up_sync(FULLMASK, inc[k], o); if (lane >= o) inc[k] += y; }
 		}
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
+		for (int j = 0; j < FS_PCL; ++j) {
 #pragma unroll
-			for (int k = 0; k < 3; ++k) W.pre[lane * 4 + j][k] = inc[k] - own[k] + pk[j][k];
+			for (int k = 0; k < 3; ++k) W.pre[lane * FS_PCL + j][k] = inc[k] - own[k] + pk[j][k];
 		}
 	}
 	__syncwarp();
@@ -257,34 +265,48 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	}
 	if (lane == 0) bulk_wait_read(); // the previous slice's store has read W.out
 	__syncwarp();
-	// ---- (3) assemble: lane l makes output cells 2l, 2l+1 ---------------------------------------------------
+	// ---- (3) assemble: lane l makes output cells l*FS_CPL .. +FS_CPL-1 ---------------------------------------
 	{
-		const uint4 ma = reinterpret_cast<const uint4*>(&W.mask[0][0])[2 * lane], mb = reinterpret_cast<const uint4*>(&W.mask[0][0])[2 * lane + 1];
-		const uint32_t ca = __popc(ma.x), cnt = ca + __popc(mb.x);
-		const uint32_t ex = warp_incl_scan(cnt, lane) - cnt;            // new symbols of the slice in front of cell 2l
-		const uint32_t mka[4] = { ma.x, ma.y, ma.z, ma.w }, mkb[4] = { mb.x, mb.y, mb.z, mb.w };
-		Cell xa = slice_cell(in.old, skip + 64u * lane - ex, mka);
-		Cell xb = slice_cell(in.old, skip + 64u * lane + 32u - ex - ca, mkb);
-		// symbols behind the end of the array (last slice) are zero
-		uint32_t na = FT_CH, nb = FT_CH, va = 0xffffffffu, vb = 0xffffffffu;
-		if (sliceLen < FS_SLICE) { // (warp-uniform: the last slice only)
-			const uint32_t rel = 64u * lane;
-			na = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
-			nb = rel + FT_CH >= sliceLen ? 0u : (sliceLen - rel - FT_CH < FT_CH ? sliceLen - rel - FT_CH : FT_CH);
-			va = low_mask(na); vb = low_mask(nb);
-			xa.b0 &= va; xa.b1 &= va; xa.b2 &= va; xb.b0 &= vb; xb.b1 &= vb; xb.b2 &= vb;
+		uint4 mk4[FS_CPL];
+		uint32_t cnt = 0;
+#pragma unroll
+		for (int j = 0; j < FS_CPL; ++j) { mk4[j] = reinterpret_cast<const uint4*>(&W.mask[0][0])[lane * FS_CPL + j]; cnt += __popc(mk4[j].x); }
+		uint32_t ex = warp_incl_scan(cnt, lane) - cnt;   // new symbols of the slice in front of this lane's first cell
+		uint32_t ow[FS_CPL * 3];
+		Raw6 r = { 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+		for (int j = 0; j < FS_CPL; ++j) {
+			const uint32_t mk[4] = { mk4[j].x, mk4[j].y, mk4[j].z, mk4[j].w };
+			const uint32_t rel = (uint32_t)(lane * FS_CPL + j) * FT_CH;
+			Cell x = slice_cell(in.old, skip + rel - ex, mk);
+			ex += __popc(mk[0]);
+			uint32_t nv = FT_CH, vm = 0xffffffffu;
+			if (sliceLen < FS_SLICE) { // (warp-uniform: the last slice only) symbols behind the end of the array are zero
+				nv = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
+				vm = low_mask(nv);
+				x.b0 &= vm; x.b1 &= vm; x.b2 &= vm;
+			}
+			ow[3 * j] = x.b0; ow[3 * j + 1] = x.b1; ow[3 * j + 2] = x.b2;
+			raw_addto(r, raw_of_cell(x, vm, nv));
 		}
-		uint32_t *o = W.out + lane * 6;
-		reinterpret_cast<uint2*>(o)[0] = make_uint2(xa.b0, xa.b1); reinterpret_cast<uint2*>(o)[1] = make_uint2(xa.b2, xb.b0); reinterpret_cast<uint2*>(o)[2] = make_uint2(xb.b1, xb.b2);
+		uint32_t *o = W.out + lane * (FS_CPL * 3);
+		if (FS_CPL % 4 == 0) {
+#pragma unroll
+			for (int i = 0; i < FS_CPL * 3; i += 4) *reinterpret_cast<uint4*>(o + i) = make_uint4(ow[i], ow[i + 1], ow[i + 2], ow[i + 3]);
+		} else {
+#pragma unroll
+			for (int i = 0; i < FS_CPL * 3; i += 2) *reinterpret_cast<uint2*>(o + i) = make_uint2(ow[i], ow[i + 1]);
+		}
 		fence_proxy_async();
-		// ---- (4) symbol counts of the slice = one directory tile of the new array ---------------------------
-		Raw6 r = raw_of_cell(xa, va, na);
-		raw_addto(r, raw_of_cell(xb, vb, nb));
+		// ---- (4) symbol counts of the slice's directory tiles (FS_LPT lanes each): raw counts, converted by FlatDirScan ----
 		uint32_t pk[3];
 		raw_pack16(r, pk);
+		const uint32_t gm = FS_LPT == 32 ? FULLMASK : (((1u << (FS_LPT & 31)) - 1u) << ((lane / FS_LPT) * FS_LPT));
 #pragma unroll
-		for (int k = 0; k < 3; ++k) pk[k] = warp_redux_add(pk[k]);
-		if (lane < 3 && (o0 < A.nNew || slice == 0)) A.newTileCnt[(uint64_t)slice * 3 + lane] = lane == 0 ? pk[0] : (lane == 1 ? pk[1] : pk[2]); // raw counts, converted by FlatDirScan
+		for (int k = 0; k < 3; ++k) pk[k] = __reduce_add_sync(gm, pk[k]);
+		const uint64_t dt = (uint64_t)slice * FS_TILES + lane / FS_LPT;
+		const uint32_t gl = lane % FS_LPT;
+		if (gl < 3 && (dt * FT_DIR < A.nNew || dt == 0)) A.newTileCnt[dt * 3 + gl] = gl == 0 ? pk[0] : (gl == 1 ? pk[1] : pk[2]);
 	}
 	__syncwarp();
 	if (lane == 0) { bulk_s2g(A.newS + (uint64_t)slice * (FS_OUTW * 4), W.out, FS_OUTW * 4); bulk_commit(); }
@@ -312,7 +334,7 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 // main kernel: persistent warps, each its own producer for the old symbols (the bulk of the bytes); the slice's
 // records are read straight from the record arrays (coalesced: consecutive records, consecutive lanes)
 template <bool GENERAL>
-__global__ void __launch_bounds__(FS_WARPS * 32, 8) k_flat_merge(FlatArgs A)
+__global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

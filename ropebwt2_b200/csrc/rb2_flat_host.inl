@@ -128,7 +128,7 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
 	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * 8);
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * FS_MINCTA);
 	if (V.sc) LAUNCH(e, (k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
 	else LAUNCH(e, (k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
 	ph_end(e, PH_MERGE);

@@ -19,7 +19,7 @@ def build(force: bool = False) -> str:
     if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return LIB
     opt = os.environ.get("RB2_EMU_OPT", "-O2")
-    common = ["-std=c++17", opt, "-g", "-fPIC", "-DRB2_EMU", "-I", os.path.join(HERE, "stubs"), "-include", os.path.join(HERE, "cuda_emu.h"), "-w"]
+    common = ["-std=c++17"] + opt.split() + ["-g", "-fPIC", "-DRB2_EMU", "-I", os.path.join(HERE, "stubs"), "-include", os.path.join(HERE, "cuda_emu.h"), "-w"]
     cmds = [
         ["g++", "-x", "c++"] + common + ["-c", os.path.join(CSRC, "rb2_engine.cu"), "-o", os.path.join(OUT, "rb2_engine.o")],
         ["g++"] + common + ["-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", os.path.join(OUT, "cuda_emu.o")],
