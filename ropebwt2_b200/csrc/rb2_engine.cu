@@ -2607,7 +2607,8 @@ extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int
 	RB2_NO_CLUSTER(e, "rb2_rank_batch");
 	if (e->comm) RB2_FATAL("rb2_rank_batch: not available on a sharded engine yet");
 	async_drain(e);
-	ensure_blocks(e);
+	const bool onFlat = e->flat.valid; // after dense batches the resident array answers directly (no leaf blocks needed)
+	if (!onFlat) ensure_blocks(e);
 	int64_t total = 0;
 	for (int b = 0; b < 6; ++b) total += e->bktLen[b];
 	const int64_t CH = 1 << 20;
@@ -2617,7 +2618,8 @@ extern "C" void rb2_rank_batch(rb2_engine_t *e, int64_t n, const int64_t *x, int
 		const int64_t m = n - o < CH ? n - o : CH;
 		for (int64_t i = 0; i < m; ++i) if (x[o + i] < 0 || x[o + i] > total) RB2_FATAL("rank position out of range");
 		RB2_CUDA(cudaMemcpyAsync(dx.p, x + o, (size_t)m * 8, cudaMemcpyHostToDevice, e->st));
-		LAUNCH(e, k_rank_batch, std::min<uint32_t>(cdiv(m, 4), (uint32_t)e->nSM * 16), 128, 0, e->pool, e->dir[e->cur], e->nlog, (uint32_t)m, dx.p, dout.p, e->dctl);
+		if (onFlat) LAUNCH(e, k_flat_rank_batch, std::min<uint32_t>(cdiv(m, 4), (uint32_t)e->nSM * 16), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, (uint32_t)m, dx.p, dout.p);
+		else LAUNCH(e, k_rank_batch, std::min<uint32_t>(cdiv(m, 4), (uint32_t)e->nSM * 16), 128, 0, e->pool, e->dir[e->cur], e->nlog, (uint32_t)m, dx.p, dout.p, e->dctl);
 		RB2_CUDA(cudaMemcpyAsync(out + o * 6, dout.p, (size_t)m * 48, cudaMemcpyDeviceToHost, e->st));
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 	}

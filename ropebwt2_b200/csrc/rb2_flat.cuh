@@ -637,6 +637,22 @@ __global__ void __launch_bounds__(256) k_column_fused(FusedArgs A)
 	}
 }
 
+// batched rank queries on the resident array (rb2_rank_batch): one warp per position, grid-stride
+__global__ void __launch_bounds__(128) k_flat_rank_batch(const uint8_t *flat, const int64_t *dir, uint32_t n, const int64_t *x, int64_t *out)
+{
+	const int lane = threadIdx.x & 31;
+	for (uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5); q < n; q += gridDim.x * 4) {
+		int64_t c[6];
+		flat_rank6(flat, dir, x[q], lane, c);
+		if (lane < 6) {
+			int64_t v = 0;
+#pragma unroll
+			for (int a = 0; a < 6; ++a) if (lane == a) v = c[a];
+			out[(size_t)q * 6 + lane] = v;
+		}
+	}
+}
+
 // per-bucket symbol totals of the array: out[k][a] = occ(a, pos[k]) for up to 64 positions (one warp each)
 struct RankAtPos { int64_t pos[8]; };
 __global__ void __launch_bounds__(32) k_flat_rank_at(const uint8_t *flat, const int64_t *dir, const RankAtPos P, int64_t *out)
