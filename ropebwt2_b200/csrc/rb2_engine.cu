@@ -111,15 +111,20 @@ __global__ void __launch_bounds__(256) k_string_ends(const uint8_t *s, int64_t l
 {
 	__shared__ uint32_t sm[8];
 	int64_t off = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 16;
-	uint32_t c = 0;
-	uint8_t b[16];
+	uint32_t nul = 0; // bit i: byte off+i is a NUL
+	if (off + 16 <= len) {
+		const uint4 v = *reinterpret_cast<const uint4*>(s + off);
+		const uint32_t w[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-	for (int i = 0; i < 16; ++i) { b[i] = off + i < len ? s[off + i] : 1; c += b[i] == 0; }
-	uint32_t v[1] = { c }, tot[1];
+		for (int j = 0; j < 4; ++j) {
+			const uint32_t z = __vcmpeq4(w[j], 0) & 0x01010101u;      // one flag bit per byte
+			nul |= (((z * 0x00204081u) >> 21) & 0xfu) << (4 * j);     // gather the four flags (bits 0, 8, 16, 24) into a nibble
+		}
+	} else for (int i = 0; i < 16; ++i) if (off + i < len && s[off + i] == 0) nul |= 1u << i;
+	uint32_t v[1] = { (uint32_t)__popc(nul) }, tot[1];
 	cta_excl_scan<1, 256, uint32_t>(v, tot, sm);
 	uint32_t k = tilePre[blockIdx.x] + v[0];
-#pragma unroll
-	for (int i = 0; i < 16; ++i) if (b[i] == 0) strEnd[k++] = off + i;
+	while (nul) { strEnd[k++] = off + (__ffs(nul) - 1); nul &= nul - 1; }
 }
 
 // (strings kBase .. kBase+m-1 of the batch: a batch whose symbol matrix would not fit is processed in ranges)
@@ -2097,8 +2102,10 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(SliceWarpSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(fs2::k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs2::SliceWarpSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(fs2::k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs2::SliceWarpSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(fs4::k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs4::SliceWarpSmem))));
+	RB2_CUDA(cudaFuncSetAttribute(fs4::k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs4::SliceWarpSmem))));
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);

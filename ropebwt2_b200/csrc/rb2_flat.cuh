@@ -96,31 +96,27 @@ struct RecView {
 };
 
 // ---- slice geometry ----------------------------------------------------------------------------------------
-// The unit of work of the merge is a SLICE: FS_SLICE = FS_CPL * 1024 output symbols (FS_CPL output cells per lane),
-// a whole number of directory tiles, produced by one warp.  One
-// thread per slice boundary t (output position min(t*FS_SLICE, nNew)): the first record whose output run
-// starts at or behind it (bisection over the strictly increasing keys key_r = P_r + pre_r), the first old
-// symbol that lands at or behind it, and the record run that reaches across it from the left.
-#ifndef FS_CPL
-#define FS_CPL 4                                   // output cells per lane: 2, 4 or 8
-#endif
-#define FS_SLICE (FS_CPL * 1024)
-struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at FS_SLICE) << 3 | symbol
+// The unit of work of the merge is a SLICE: `slice` = 2048 or 4096 output symbols (2 or 4 output cells per lane),
+// a whole number of directory tiles, produced by one warp.  One thread per slice boundary t (output position
+// min(t*slice, nNew)): the first record whose output run starts at or behind it (bisection over the strictly
+// increasing keys key_r = P_r + pre_r), the first old symbol that lands at or behind it, and the record run that
+// reaches across it from the left.
+struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at the slice size) << 3 | symbol
 
-__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, TileDesc *desc)
+__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, uint32_t slice, TileDesc *desc)
 {
 	const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (t > nSlices) return;
-	const uint64_t o0 = t * FS_SLICE < nNew ? t * FS_SLICE : nNew;
-	uint32_t lo = 0, hi = R; // first r with Key(r) >= t*FS_SLICE (R if none)
+	const uint64_t o0 = t * slice < nNew ? t * slice : nNew;
+	uint32_t lo = 0, hi = R; // first r with Key(r) >= t*slice (R if none)
 	if (t == nSlices) lo = R;
-	while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (V.Key(mid) >= t * FS_SLICE) hi = mid; else lo = mid + 1; }
+	while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (V.Key(mid) >= t * slice) hi = mid; else lo = mid + 1; }
 	const uint32_t r0 = lo;
 	uint64_t before = 0; uint32_t carry = 0;
 	if (r0 > 0) {
 		const uint64_t pre = V.Pre(r0 - 1), key = (uint64_t)V.P[r0 - 1] + pre; const uint32_t sc = V.SC(r0 - 1);
 		const uint64_t end = key + (sc >> 3);
-		if (end > o0) { before = pre + (o0 - key); const uint64_t rem = end - o0; carry = (uint32_t)(rem < FS_SLICE ? rem : FS_SLICE) << 3 | (sc & 7u); }
+		if (end > o0) { before = pre + (o0 - key); const uint64_t rem = end - o0; carry = (uint32_t)(rem < slice ? rem : slice) << 3 | (sc & 7u); }
 		else before = pre + (sc >> 3);
 	}
 	TileDesc d; d.i0 = o0 - before; d.r0 = r0; d.carry = carry;
@@ -151,24 +147,8 @@ struct FlatArgs {
 // The kernel is persistent: every warp owns two shared-memory stages and fetches the old symbols of its slice
 // i+2 while it merges slice i (its lane 0 is the producer); the slice's records are read straight from the
 // record arrays (consecutive records in consecutive lanes).  No block-wide barrier anywhere.
-#define FS_CELLS (FS_SLICE / FT_CH)                 // output cells per slice, FS_CPL per lane
-#define FS_TILES (FS_SLICE / FT_DIR)                // directory tiles per slice
-#define FS_LPT   (32 / FS_TILES)                    // lanes per directory tile
-#define FS_PCL   (FS_CPL + FT_DIR / 1024)           // old cells per lane in the prefix pass
-#define FS_OLDC  (FS_PCL * 32 + 2)                  // cells of old symbols a slice can need (+ funnel-shift partner)
-#define FS_MINCTA (FS_CPL == 2 ? 8 : (FS_CPL == 4 ? 5 : 3)) // CTAs per SM the shared memory allows
-#define FS_OLDW  ((FS_OLDC * 3 + 3) & ~3)           // ... as words, a multiple of 16 bytes
-#define FS_OUTW  (FS_CELLS * 3)                     // words of one output slice
 #define FS_STAGES 2
-#define FS_WARPS 4                                  // warps per CTA of the main kernel
-
-struct SliceStage { alignas(16) uint32_t old[FS_OLDW]; TileDesc d0, d1; uint32_t slice, pad[3]; };
-struct SliceWork {
-	alignas(16) uint32_t out[FS_OUTW];              // the finished slice (TMA bulk store)
-	alignas(16) uint32_t mask[FS_CELLS][4];         // per output cell: new positions, and planes 0..2 of the new symbols
-	uint32_t pre[FS_OLDC][3];                       // raw counts in front of every old cell, from a0 (16-bit fields)
-};
-struct SliceWarpSmem { SliceStage st[FS_STAGES]; SliceWork W; alignas(8) uint64_t full[FS_STAGES]; };
+#define FS_WARPS 4                                  // warps per CTA of the merge kernel
 
 // where the records of one slice are, indexed from 0 (shared memory or global memory)
 struct SliceIn {
@@ -179,20 +159,6 @@ struct SliceIn {
 
 // record k = lane of a slice, fetched one slice ahead (the loads' latency hides under the previous slice's merge)
 struct RecRegs { int64_t P; uint32_t pre, sc, dst; bool have; };
-
-// set the new-symbol masks of output positions [key, key+len) of the slice
-__device__ __forceinline__ void slice_mark(SliceWork &W, uint32_t key, uint32_t len, uint32_t sy)
-{
-	while (len) {
-		const uint32_t c = key / FT_CH, q = key & (FT_CH - 1), n = len < FT_CH - q ? len : FT_CH - q;
-		const uint32_t bits = low_mask(n) << q;
-		atomicOr(&W.mask[c][0], bits);
-		if (sy & 1u) atomicOr(&W.mask[c][1], bits);
-		if (sy & 2u) atomicOr(&W.mask[c][2], bits);
-		if (sy & 4u) atomicOr(&W.mask[c][3], bits);
-		key += n; len -= n;
-	}
-}
 
 // one output cell: 32 old symbols from local index oldIdx on, a gap pushed in at every bit of m, the new planes on top
 __device__ __forceinline__ Cell slice_cell(const uint32_t *old, uint32_t oldIdx, const uint32_t (&mk)[4])
@@ -211,190 +177,13 @@ __device__ __forceinline__ Cell slice_cell(const uint32_t *old, uint32_t oldIdx,
 	return x;
 }
 
-template <bool GENERAL>
-__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane, const RecRegs &pf)
-{
-	const uint64_t o0 = (uint64_t)slice * FS_SLICE;
-	const uint32_t sliceLen = A.nNew - o0 < FS_SLICE ? (uint32_t)(A.nNew - o0) : FS_SLICE;
-	const uint32_t r0 = d0.r0, nr = d1.r0 - d0.r0;
-	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < sliceLen ? (d0.carry >> 3) : sliceLen;
-	const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
-	const uint32_t skip = (uint32_t)(d0.i0 - a0);      // old symbols of the window in front of the slice's first one
-	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells l*FS_PCL .. +FS_PCL-1) -----------
-#pragma unroll
-	for (int j = 0; j < FS_CPL; ++j) reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32 * j] = make_uint4(0, 0, 0, 0);
-	{
-		uint32_t pk[FS_PCL][3], inc[3];
-		Raw6 r = { 0, 0, 0, 0, 0, 0 };
-#pragma unroll
-		for (int j = 0; j < FS_PCL; ++j) {
-			raw_pack16(r, pk[j]); // exclusive inside the lane
-			raw_addto(r, raw_of_cell(cell_load(in.old + (lane * FS_PCL + j) * 3), 0xffffffffu, FT_CH));
-		}
-		raw_pack16(r, inc);
-		const uint32_t own[3] = { inc[0], inc[1], inc[2] };
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-			for (int k = 0; k < 3; ++k) { const uint32_t y = __shfl_up_sync(FULLMASK, inc[k], o); if (lane >= o) inc[k] += y; }
-		}
-#pragma unroll
-		for (int j = 0; j < FS_PCL; ++j) {
-#pragma unroll
-			for (int k = 0; k < 3; ++k) W.pre[lane * FS_PCL + j][k] = inc[k] - own[k] + pk[j][k];
-		}
-	}
-	__syncwarp();
-	// ---- (2) records -> masks ----------------------------------------------------------------------------
-	if (lane == 0 && carryLen) slice_mark(W, 0, carryLen, carrySym);
-	for (uint32_t k = lane; k < nr; k += 32) {
-		const bool reg = pf.have && k < 32;
-		const uint32_t key = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) + (reg ? pf.pre : in.Pre(k)) - o0);
-		if (GENERAL) {
-			const uint32_t sc = reg ? pf.sc : in.SC(k);
-			uint32_t len = sc >> 3;
-			if (len > FS_SLICE - key) len = FS_SLICE - key;
-			slice_mark(W, key, len, sc & 7u);
-		} else {
-			const uint32_t sy = reg ? pf.sc : (uint32_t)in.asym[k], c = key / FT_CH, bit = 1u << (key & (FT_CH - 1));
-			atomicOr(&W.mask[c][0], bit);
-			if (sy & 1u) atomicOr(&W.mask[c][1], bit);
-			if (sy & 2u) atomicOr(&W.mask[c][2], bit);
-			if (sy & 4u) atomicOr(&W.mask[c][3], bit);
-		}
-	}
-	if (lane == 0) bulk_wait_read(); // the previous slice's store has read W.out
-	__syncwarp();
-	// ---- (3) assemble: lane l makes output cells l*FS_CPL .. +FS_CPL-1 ---------------------------------------
-	{
-		uint4 mk4[FS_CPL];
-		uint32_t cnt = 0;
-#pragma unroll
-		for (int j = 0; j < FS_CPL; ++j) { mk4[j] = reinterpret_cast<const uint4*>(&W.mask[0][0])[lane * FS_CPL + j]; cnt += __popc(mk4[j].x); }
-		uint32_t ex = warp_incl_scan(cnt, lane) - cnt;   // new symbols of the slice in front of this lane's first cell
-		uint32_t ow[FS_CPL * 3];
-		Raw6 r = { 0, 0, 0, 0, 0, 0 };
-#pragma unroll
-		for (int j = 0; j < FS_CPL; ++j) {
-			const uint32_t mk[4] = { mk4[j].x, mk4[j].y, mk4[j].z, mk4[j].w };
-			const uint32_t rel = (uint32_t)(lane * FS_CPL + j) * FT_CH;
-			Cell x = slice_cell(in.old, skip + rel - ex, mk);
-			ex += __popc(mk[0]);
-			uint32_t nv = FT_CH, vm = 0xffffffffu;
-			if (sliceLen < FS_SLICE) { // (warp-uniform: the last slice only) symbols behind the end of the array are zero
-				nv = rel >= sliceLen ? 0u : (sliceLen - rel < FT_CH ? sliceLen - rel : FT_CH);
-				vm = low_mask(nv);
-				x.b0 &= vm; x.b1 &= vm; x.b2 &= vm;
-			}
-			ow[3 * j] = x.b0; ow[3 * j + 1] = x.b1; ow[3 * j + 2] = x.b2;
-			raw_addto(r, raw_of_cell(x, vm, nv));
-		}
-		uint32_t *o = W.out + lane * (FS_CPL * 3);
-		if (FS_CPL % 4 == 0) {
-#pragma unroll
-			for (int i = 0; i < FS_CPL * 3; i += 4) *reinterpret_cast<uint4*>(o + i) = make_uint4(ow[i], ow[i + 1], ow[i + 2], ow[i + 3]);
-		} else {
-#pragma unroll
-			for (int i = 0; i < FS_CPL * 3; i += 2) *reinterpret_cast<uint2*>(o + i) = make_uint2(ow[i], ow[i + 1]);
-		}
-		fence_proxy_async();
-		// ---- (4) symbol counts of the slice's directory tiles (FS_LPT lanes each): raw counts, converted by FlatDirScan ----
-		uint32_t pk[3];
-		raw_pack16(r, pk);
-		const uint32_t gm = FS_LPT == 32 ? FULLMASK : (((1u << (FS_LPT & 31)) - 1u) << ((lane / FS_LPT) * FS_LPT));
-#pragma unroll
-		for (int k = 0; k < 3; ++k) pk[k] = __reduce_add_sync(gm, pk[k]);
-		const uint64_t dt = (uint64_t)slice * FS_TILES + lane / FS_LPT;
-		const uint32_t gl = lane % FS_LPT;
-		if (gl < 3 && (dt * FT_DIR < A.nNew || dt == 0)) A.newTileCnt[dt * 3 + gl] = gl == 0 ? pk[0] : (gl == 1 ? pk[1] : pk[2]);
-	}
-	__syncwarp();
-	if (lane == 0) { bulk_s2g(A.newS + (uint64_t)slice * (FS_OUTW * 4), W.out, FS_OUTW * 4); bulk_commit(); }
-	// ---- (5) rank(a, P) for the records that start in this slice ------------------------------------------------
-	{
-		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
-		for (uint32_t k = lane; k < nr; k += 32) {
-			const bool reg = pf.have && k < 32;
-			const uint32_t dst = reg ? pf.dst : in.dst[k];
-			if (dst == NONE32) continue;
-			const uint32_t a = reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]);
-			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
-			const uint32_t c = xo / FT_CH;
-			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
-			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
-			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a) + part;
-			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
-				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k) * 7 + a];
-			A.gLNext[dst] = g;
-		}
-	}
-	__syncwarp(); // the inputs and W.mask / W.pre may be reused
+#define FS_CPL 2
+namespace fs2 {
+#include "rb2_flat_merge.inl"
 }
-
-// main kernel: persistent warps, each its own producer for the old symbols (the bulk of the bytes); the slice's
-// records are read straight from the record arrays (coalesced: consecutive records, consecutive lanes)
-template <bool GENERAL>
-__global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArgs A)
-{
-	RB2_DYN_SMEM(smraw);
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	SliceWarpSmem &S = reinterpret_cast<SliceWarpSmem*>(smraw)[wid];
-	const uint32_t nWarps = gridDim.x * FS_WARPS;
-	if (lane == 0) { for (int s = 0; s < FS_STAGES; ++s) mbar_init(&S.full[s], 1); }
-	__syncwarp();
-	// fetch the old symbols of slice `sl` into stage s (lane 0); a slice index behind the last one ends the ring
-	auto issue = [&](uint32_t s, uint32_t sl, const TileDesc d0, const TileDesc d1) {
-		if (lane != 0) return;
-		SliceStage &st = S.st[s];
-		if (sl >= A.nSlices) { st.slice = NONE32; mbar_arrive(&S.full[s]); return; }
-		const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
-		const uint32_t bytes = (((uint32_t)(d1.i0 - a0) / FT_CH + 2) * 12u + 15u) & ~15u;
-		st.d0 = d0; st.d1 = d1; st.slice = sl;
-		mbar_expect_tx(&S.full[s], bytes);
-		bulk_g2s(st.old, A.oldS + (a0 / FT_CH) * 12, bytes, &S.full[s]);
-	};
-	const uint32_t first = blockIdx.x * FS_WARPS + wid;
-	const TileDesc none = { 0, 0, 0 };
-	for (uint32_t s = 0; s < FS_STAGES; ++s) {
-		const uint32_t sl = first + s * nWarps;
-		const bool ok = lane == 0 && sl < A.nSlices;
-		issue(s, sl, ok ? A.desc[sl] : none, ok ? A.desc[sl + 1] : none);
-	}
-	__syncwarp();
-	RecRegs pf = { 0, 0, 0, 0, false }, pfNext = { 0, 0, 0, 0, false };
-	for (uint32_t n = 0; ; ++n) {
-		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
-		mbar_wait(&S.full[s], ph);
-		const SliceStage &st = S.st[s];
-		const uint32_t slice = st.slice;
-		if (slice == NONE32) break;
-		{ // records k = lane of the slice in the other stage (merged next; its geometry was stored when it was issued)
-			const SliceStage &sn = S.st[s ^ 1];
-			pfNext.have = false;
-			if (FS_STAGES == 2 && sn.slice != NONE32) {
-				const uint32_t q0 = sn.d0.r0, qn = sn.d1.r0 - q0;
-				pfNext.have = true;
-				if ((uint32_t)lane < qn) {
-					const uint32_t r = q0 + lane;
-					pfNext.P = A.V.P[r]; pfNext.dst = A.recDst[r];
-					pfNext.pre = GENERAL ? A.V.pre[r] : r;
-					pfNext.sc = GENERAL ? A.V.sc[r] : (uint32_t)A.V.asym[r];
-				}
-			}
-		}
-		// geometry of the slice this stage gets next: loaded now, used behind the merge (the latency hides under it)
-		const uint32_t nextSl = slice + FS_STAGES * nWarps;
-		const bool ok = lane == 0 && nextSl < A.nSlices;
-		const TileDesc nd0 = ok ? A.desc[nextSl] : none, nd1 = ok ? A.desc[nextSl + 1] : none;
-		const uint32_t r0 = st.d0.r0;
-		SliceIn in = { st.old, A.V.P + r0, GENERAL ? A.V.pre + r0 : (const uint32_t*)0, GENERAL ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
-		               GENERAL ? (const uint8_t*)0 : A.V.asym + r0, r0 };
-		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane, pf);
-		pf = pfNext;
-		issue(s, nextSl, nd0, nd1); // (behind the slice's closing __syncwarp: every lane is done with the stage)
-		__syncwarp();               // the stage's new geometry is visible to every lane (they prefetch its records next time round)
-	}
-	if (lane == 0) bulk_wait_read();
+#define FS_CPL 4
+namespace fs4 {
+#include "rb2_flat_merge.inl"
 }
 
 struct FlatDirScan { // K=6 (int64): per-tile raw counts (three packed words) -> symbol counts in front of every tile

@@ -96,7 +96,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 	}
 	f.s[f.cur ^ 1].need(flat_bytes(cap)); f.dir[f.cur ^ 1].need((cap / FT_DIR + 3) * 6);
 	f.tileCnt.need((cap / FT_DIR + 3) * 3);
-	f.desc.need(cap / FS_SLICE + 4);
+	f.desc.need(cap / fs2::kSlice + 4);
 	if (!f.valid) {
 		f.n = n0;
 		if (n0 > 0) {
@@ -117,20 +117,32 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0, const uint8_t *asym = 0)
 {
 	FlatState &f = e->flat;
-	const uint64_t nNew = f.n + inserted, nTiles = (nNew + FS_SLICE - 1) / FS_SLICE; // slices: one warp each
+	const uint64_t nNew = f.n + inserted;
+	// slice size: 2048 symbols per warp while the column inserts many symbols per slice, 4096 once the array is large
+	// against the batch (RB2_WIDE_RATIO symbols per record; measured crossover, profiles/README.md)
+	static double wideRatio = -1;
+	if (wideRatio < 0) { const char *ws = getenv("RB2_WIDE_RATIO"); wideRatio = ws && *ws ? atof(ws) : 192.0; }
+	const bool wide = (double)nNew > wideRatio * (double)(nrec ? nrec : 1);
+	const uint32_t slice = wide ? fs4::kSlice : fs2::kSlice;
+	const uint64_t nTiles = (nNew + slice - 1) / slice; // slices: one warp each
 	// the target buffers hold nothing live: grow them if this rank receives more than was estimated
 	f.s[f.cur ^ 1].need(flat_bytes(nNew + FT_PAD)); f.dir[f.cur ^ 1].need((nNew / FT_DIR + 3) * 6);
-	f.tileCnt.need((nNew / FT_DIR + 3) * 3); f.desc.need(nNew / FS_SLICE + 4);
+	f.tileCnt.need((nNew / FT_DIR + 3) * 3); f.desc.need(nNew / fs2::kSlice + 4);
 	ph_begin(e, PH_MERGE);
 	// leanP: all-singleton column -- the records are the state arrays themselves (position = leanP[r], symbol = asym[r], count 1, r symbols in front)
 	const RecView V = leanP ? RecView{ leanP, 0, 0, asym ? asym : e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
-	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, f.desc.p);
+	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, slice, f.desc.p);
 	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
 	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb };
-	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * FS_MINCTA);
-	if (V.sc) LAUNCH(e, (k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
-	else LAUNCH(e, (k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(SliceWarpSmem), fa);
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * (wide ? fs4::kMinCta : fs2::kMinCta));
+	if (wide) {
+		if (V.sc) LAUNCH(e, (fs4::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);
+		else LAUNCH(e, (fs4::k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);
+	} else {
+		if (V.sc) LAUNCH(e, (fs2::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs2::SliceWarpSmem), fa);
+		else LAUNCH(e, (fs2::k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs2::SliceWarpSmem), fa);
+	}
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);
