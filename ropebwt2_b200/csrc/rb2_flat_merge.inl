@@ -37,7 +37,7 @@ __device__ __forceinline__ void slice_mark(SliceWork &W, uint32_t key, uint32_t 
 }
 
 template <bool GENERAL>
-__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane, const RecRegs &pf)
+__device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane, const RecRegs &pf, const int64_t cpostLane)
 {
 	const uint64_t o0 = (uint64_t)slice * FS_SLICE;
 	const uint32_t sliceLen = A.nNew - o0 < FS_SLICE ? (uint32_t)(A.nNew - o0) : FS_SLICE;
@@ -45,6 +45,9 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	const uint32_t carrySym = d0.carry & 7u, carryLen = (d0.carry >> 3) < sliceLen ? (d0.carry >> 3) : sliceLen;
 	const uint64_t a0 = d0.i0 & ~(uint64_t)(FT_DIR - 1);
 	const uint32_t skip = (uint32_t)(d0.i0 - a0);      // old symbols of the window in front of the slice's first one
+	// lane a < 6: start of bucket a behind this column + #a in front of the directory boundary (fetched now, used by the
+	// rank epilogue: the load's latency hides under the merge)
+	const int64_t baseLane = lane < 6 ? cpostLane + A.oldDir[(a0 / FT_DIR) * 6 + lane] : 0;
 	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells l*FS_PCL .. +FS_PCL-1) -----------
 #pragma unroll
 	for (int j = 0; j < FS_CPL; ++j) reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32 * j] = make_uint4(0, 0, 0, 0);
@@ -137,17 +140,18 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	if (lane == 0) { bulk_s2g(A.newS + (uint64_t)slice * (FS_OUTW * 4), W.out, FS_OUTW * 4); bulk_commit(); }
 	// ---- (5) rank(a, P) for the records that start in this slice ------------------------------------------------
 	{
-		const int64_t *dirRow = A.oldDir + (a0 / FT_DIR) * 6;
-		for (uint32_t k = lane; k < nr; k += 32) {
-			const bool reg = pf.have && k < 32;
-			const uint32_t dst = reg ? pf.dst : in.dst[k];
+		for (uint32_t k0 = 0; k0 < nr; k0 += 32) { // (uniform trip count: the shuffle below needs every lane)
+			const uint32_t k = k0 + lane;
+			const bool valid = k < nr, reg = pf.have && k < 32;
+			const uint32_t dst = !valid ? NONE32 : (reg ? pf.dst : in.dst[k]);
+			const uint32_t a = !valid ? 0u : (reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]));
+			const int64_t base = __shfl_sync(FULLMASK, baseLane, (int)a);
 			if (dst == NONE32) continue;
-			const uint32_t a = reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]);
 			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
 			const uint32_t c = xo / FT_CH;
 			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
 			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
-			int64_t g = A.ctl->cpost[a] + dirRow[a] + raw_symbol(rr, a) + part;
+			int64_t g = base + raw_symbol(rr, a) + part;
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
 				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k) * 7 + a];
 			A.gLNext[dst] = g;
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 	}
 	__syncwarp();
 	RecRegs pf = { 0, 0, 0, 0, false }, pfNext = { 0, 0, 0, 0, false };
+	const int64_t cpostLane = lane < 8 ? A.ctl->cpost[lane] : 0; // start of bucket `lane` behind this column
 	for (uint32_t n = 0; ; ++n) {
 		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
 		mbar_wait(&S.full[s], ph);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 		const uint32_t r0 = st.d0.r0;
 		SliceIn in = { st.old, A.V.P + r0, GENERAL ? A.V.pre + r0 : (const uint32_t*)0, GENERAL ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
 		               GENERAL ? (const uint8_t*)0 : A.V.asym + r0, r0 };
-		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane, pf);
+		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane, pf, cpostLane);
 		pf = pfNext;
 		issue(s, nextSl, nd0, nd1); // (behind the slice's closing __syncwarp: every lane is done with the stage)
 		__syncwarp();               // the stage's new geometry is visible to every lane (they prefetch its records next time round)

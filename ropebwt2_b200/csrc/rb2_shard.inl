@@ -229,7 +229,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	bool flat = true;
 	for (int r = 0; r < P; ++r) flat = flat && votes[r] != 0;
 	if (flat) flat_begin(e, addLocal);
-	else reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
+	else { ensure_blocks(e); blocks_edited(e); } // a sparse batch edits the leaf blocks
+	if (!flat) reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
 	uint32_t G = 0, M = 0;
 	uint32_t gBkt[NBA], mBkt[NBA];
 	uint64_t mglob[NBMAX];
@@ -463,8 +464,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (flat) {
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		ph_collect(e, e->flat.pending); e->flat.pending = 0;
-		flat_finish(e); flat_to_blocks(e); // sharded engines re-encode at the end of every batch
-		e->flat.valid = false; e->flat.blocksStale = false;
+		flat_finish(e); // the array stays resident; the leaf blocks of my sub-buckets are rebuilt when somebody fetches them
 		++e->stats.flat_batches;
 	}
 	shard_publish_totals(e);

@@ -18,8 +18,8 @@ host = np.ctypeslib.as_array((C.c_uint8 * cap).from_address(hptr))
 m = MRope(1)
 for k in range(nb):
     bench.fill_host_batch(host, w, k * per, (k + 1) * per, torch.device("cuda", 0))
-    L.rb2_sync(m.engine_handle)
     m.L.mr_insert_multi(m.h, cap, C.cast(hptr, C.POINTER(C.c_uint8)), 1)
+    L.rb2_sync(m.engine_handle)   # (the generator runs on the same GPU: keep it out of the insertion's way)
 for k, st in enumerate(m.job_history(nb)):
     print(json.dumps({"batch": k, "ms": round(st["ms_total"] - st["ms_h2d"], 1), "ms_merge": round(st["ms_merge"], 1), "merge_GB/s": round(st["merge_bytes_rw"] / max(st["ms_merge"], 1e-9) / 1e6),
                       "ms_groups": round(st["ms_groups"], 1), "ms_members": round(st["ms_members"], 1), "ms_convert": round(st["ms_convert"], 1), "ms_dir": round(st["ms_directory"], 1)}))
