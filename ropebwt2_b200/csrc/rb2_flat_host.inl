@@ -24,10 +24,12 @@ static uint64_t local_symbols(const rb2_engine *e)
 	return n;
 }
 
-// Dense or sparse?  One dense column streams the whole local array (3 bits per symbol, read + written:
-// ~0.2 ps per symbol at the measured merge rate); one sparse column costs ~0.22 ns per record on an index that
-// sits in L2 and more on a large one (profiles/README.md).  `strings` = records per column at the start of
-// the batch, `addLocal` = symbols this engine expects to receive.  RB2_FLAT_RATIO overrides the crossover.
+// Dense or sparse?  One dense column streams the whole local array (3 bits per symbol, read + written: ~0.34 ps per
+// symbol at the measured merge rate); one sparse column costs ~1 ns per record plus a directory rebuild that is
+// itself proportional to the index (~0.12 ps per symbol: the flat directory is re-scanned every column).  Sparse
+// therefore only wins when the index holds more than ~5000 symbols per record of the column (measured on
+// configs 2 and 4, profiles/README.md).  `strings` = records per column at the start of the batch, `addLocal` =
+// symbols this engine expects to receive.  RB2_FLAT_RATIO overrides the crossover.
 static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
 {
 	const int pref = flat_pref();
@@ -40,7 +42,7 @@ static bool flat_choose(rb2_engine *e, uint64_t strings, uint64_t addLocal)
 	if (need > freeB + have) return false; // does not fit: block-wise updates need far less
 	if (pref == 1) return true;
 	static double ratio = -1;
-	if (ratio < 0) { const char *s = getenv("RB2_FLAT_RATIO"); ratio = s && *s ? atof(s) : 2048.0; }
+	if (ratio < 0) { const char *s = getenv("RB2_FLAT_RATIO"); ratio = s && *s ? atof(s) : 6000.0; }
 	return strings >= 65536 && (double)n0 + 0.5 * (double)addLocal < ratio * (double)strings;
 }
 

@@ -142,3 +142,19 @@ def test_pipelined_calls_and_eager_counts(monkeypatch):
     assert np.array_equal(m.counts(), o2.counts())
     assert np.array_equal(text(m), o2.text())
     m.close()
+
+
+@pytest.mark.parametrize("so", [0, 1])
+def test_long_reads_in_the_dense_regime(monkeypatch, so):
+    """Config-4 shape (many columns, all strings live until the end) forced through the dense regime, which is
+    what the cost model picks for 1 M x 10 kbp: thousands of k_column_fused / k_flat_merge columns on one array."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    rd = uniform_reads(sz(300, 40), sz(4000, 300), 14)
+    o, m = orc.Oracle(so), MRope(so)
+    for part in (rd[:len(rd) * 2 // 3], rd[len(rd) * 2 // 3:]):
+        buf = encode_batch(part)
+        o.insert_multi(buf)
+        m.insert_multi(buf)
+    assert np.array_equal(m.counts(), o.counts())
+    assert np.array_equal(text(m), o.text())
+    m.close()
