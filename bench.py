@@ -276,6 +276,62 @@ def verify_md5(L, mr_handle, w, flags):
     return out
 
 
+def verify_sharded_md5(L, eng, args, torch, rank, world, local, hptr, host):
+    """Bit-exactness of the sharded build on real NCCL, at the one-GPU bench size: the N ranks build ONE index of the
+    config-2 read set together (rank r inserts reads [r*n/N, (r+1)*n/N)), the sub-buckets travel to rank 0 in
+    sub-bucket order, and the md5 of the decoded text must equal the recorded reference run.  Outside the timed region."""
+    import hashlib
+    import torch.distributed as dist
+    from oracle import oracle as orc  # the checker
+    from ropebwt2_b200 import synth
+    flags = FLAGS[args.config]
+    w = synth.workload(args.config, args.reads or 0)   # the ONE-GPU workload
+    rec = orc.ref_recorded(w, flags)
+    if rec is None:
+        return {"result": "unpinned: no recorded reference run for " + synth.workload_key(w, flags)}
+    t0 = time.time()
+    n, ln = w["n"], w["L"]
+    share = n // world
+    dev = torch.device("cuda", local)
+    fill_host_batch(host, w, rank * share, (rank + 1) * share, dev)
+    eng.reset()
+    eng.insert_multi_ptr(hptr, share * (ln + 1))
+    md5, total = hashlib.md5(), 0
+    for s in range(36):
+        owner = L.rb2_shard_owner(world, s)
+        blocks = eng.fetch_subbucket(s) if rank == owner else None
+        nb = torch.tensor([blocks.shape[0] if blocks is not None else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(nb, src=owner)
+        k = int(nb.item())
+        if k == 0:
+            continue
+        if rank == owner and rank == 0:
+            got = blocks
+        elif rank == owner or rank == 0:
+            t = torch.empty((k, 512), dtype=torch.uint8, device=dev)
+            if rank == owner:
+                t.copy_(torch.from_numpy(blocks))
+                dist.send(t, dst=0)
+            else:
+                dist.recv(t, src=owner)
+            got = t.cpu().numpy() if rank == 0 else None
+            del t
+        else:
+            got = None
+        if rank == 0:
+            txt = orc.blocks_ascii(got, n * (ln + 1))
+            md5.update(memoryview(txt))
+            total += txt.size
+    if rank != 0:
+        return {"result": "checked on rank 0"}
+    md5.update(b"\n")
+    if md5.hexdigest() != rec["md5_text"] or total + 1 != rec["text_bytes"]:
+        raise SystemExit("PARITY FAILURE (sharded build, %d ranks): md5 %s (%d symbols) != reference %s" % (world, md5.hexdigest(), total, rec["md5_text"]))
+    return {"md5": md5.hexdigest(), "symbols": total, "seconds": round(time.time() - t0, 1),
+            "result": "md5 == reference for ONE index of %s built by %d ranks over NCCL (%d reads per rank; oracle/_ref/ropebwt2 %s, recorded %s); "
+                      "the timed weak-scaling index (%d reads) is checked for symbol conservation" % (synth.workload_key(w, flags), world, share, flags, rec["when"], n * world)}
+
+
 def main():
     args = parse()
     # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) go to stderr
@@ -408,9 +464,10 @@ def run_single_batch(args, torch, red, rank, world, local):
     if not args.no_verify:
         if mr is not None:
             parity = verify_md5(L, mr.h, w, flags)
+        elif sharded and args.config == "cfg2" and n % world == 0:
+            parity = verify_sharded_md5(L, eng, args, torch, rank, world, local, hptr, host)
         else:
-            parity = {"result": "symbol conservation checked in-run at this N; bit-exactness of the sharded build: tests/test_sharded_gpu.py, tests/test_sharded_nccl.py and "
-                                "the --config cfg2 md5 check at N=1 (the sharded path runs the same kernels)"}
+            parity = {"result": "symbol conservation checked in-run at this N; bit-exactness of the sharded build: tests/test_sharded_gpu.py, tests/test_sharded_nccl.py"}
     if sharded:
         eng.close()
     else:

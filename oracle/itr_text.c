@@ -153,3 +153,20 @@ int64_t itr_stream_read(void *s_, uint8_t *out, int64_t cap, int ascii)
 }
 
 void itr_stream_close(void *s) { free(s); }
+
+/* blocks_text with a choice of output alphabet: nt6 codes (ascii == 0) or the characters "$ACGTN" */
+int64_t blocks_text2(const uint8_t *blocks, int64_t n_blocks, uint8_t *out, int64_t cap, int ascii)
+{
+	int64_t n = 0, b;
+	for (b = 0; b < n_blocks; ++b) {
+		const uint8_t *blk = blocks + b * 512;
+		const uint8_t *q = blk + 2, *end = blk + 2 + *(const uint16_t*)blk;
+		while (q < end) {
+			int c; int64_t l;
+			q = dec_run(q, &c, &l);
+			if (n + l <= cap) memset(out + n, ascii? "$ACGTN"[c] : c, (size_t)l);
+			n += l;
+		}
+	}
+	return n <= cap? n : -n;
+}

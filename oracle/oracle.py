@@ -143,6 +143,19 @@ def decode_blocks(blocks: np.ndarray, total: int) -> np.ndarray:
     return out[:total]
 
 
+def blocks_ascii(blocks: np.ndarray, cap: int) -> np.ndarray:
+    """Decode an [n, 512] uint8 array of leaf blocks into the characters the reference prints (at most cap)."""
+    il = _itrlib()
+    il.blocks_text2.restype = C.c_int64
+    il.blocks_text2.argtypes = [_u8p, C.c_int64, _u8p, C.c_int64, C.c_int]
+    blocks = np.ascontiguousarray(blocks, dtype=np.uint8)
+    out = np.empty(max(cap, 1), dtype=np.uint8)
+    n = il.blocks_text2(blocks.ctypes.data_as(_u8p), blocks.shape[0], out.ctypes.data_as(_u8p), cap, 1)
+    if n < 0:
+        raise AssertionError(f"blocks decode to {-n} symbols, more than {cap}")
+    return out[:n]
+
+
 def decode_index(lib: C.CDLL, mr, total: int, to_free: int = 0, ascii: bool = False):
     """Decode the index behind ``mr`` (an ``mrope_t*`` of ``lib``) into ``total`` symbols by
     walking ``lib``'s own mr_itr_first / mr_itr_next_block.  Returns (text, n_blocks, n_runs)."""
