@@ -14,23 +14,20 @@
 // which is exactly the stable merge rope_insert_run performs one run at a time (rope.c:114-148;
 // new symbols go in FRONT of the old symbol at the same position, mrope.c:206-218), and
 // rank(a, P_r) -- the return value of rope_insert_run / rle_insert_cached (rle.c:10-89) -- is
-// directory[P_r / FT_DIR][a] + a count over < FT_DIR + FT_OUT symbols held in shared memory.
+// directory[P_r / FT_DIR][a] + a count over < FT_DIR + one slice of symbols held in shared memory.
 // Why planes: counting a symbol over 32 codes is one AND/ANDN pair + one POPC (nibbles needed ~50
-// instructions), inserting a run at a bit position is shift/mask work on three words, and the array
-// is 25 % smaller than at 4 bits per symbol -- the kernel is bound by HBM, not by instruction issue.
-// Output-stationary: CTA t produces new[t*FT_OUT, (t+1)*FT_OUT): the old symbols it needs are one
-// contiguous range, fetched into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier), and
-// the finished tile leaves through one TMA bulk store.  The array stays resident between batches; it
-// is re-encoded into leaf blocks of the reference's format (k_flat_encode) only when something needs
-// blocks (iterator, dump, rank queries, a sparse batch).
+// instructions), inserting a symbol at a bit position is shift/mask work on three words, and the array
+// is 25 % smaller than at 4 bits per symbol.
+// Output-stationary: one warp produces one slice new[t*slice, (t+1)*slice) (2048 or 4096 symbols): the old
+// symbols it needs are one contiguous range, fetched into shared memory by one TMA bulk copy
+// (cp.async.bulk + mbarrier, a two-stage ring per warp), and the finished slice leaves through one TMA bulk
+// store (rb2_flat_merge.inl).  The array stays resident between batches; it is re-encoded into leaf blocks of
+// the reference's format (k_flat_encode) only when something needs blocks (iterator, dump, a sparse batch).
 #pragma once
 #include "rb2_codec.cuh"
 
-#define FT_OUT   8192  // output symbols per CTA of k_flat_merge: 256 threads x one cell
 #define FT_DIR   2048  // directory granularity (48 bytes of counts per 768 bytes of symbols)
-#define FT_SUB   (FT_OUT / FT_DIR)
-#define FT_OLDMAX (FT_OUT + FT_DIR) // old symbols one CTA can need: from the directory tile of its first one
-#define FT_PAD   (FT_OLDMAX + 256)  // readable / writable slack (symbols) behind a flat array
+#define FT_PAD   (8192 + FT_DIR + 256)  // readable / writable slack (symbols) behind a flat array (> one slice + one directory tile)
 #define FT_CH    32    // symbols per cell (three words)
 #define FE_CHUNK 64    // flat -> blocks: symbols encoded by one thread (<= 64 bytes of runs)
 #define FE_T     (RB2_FILL - FE_CHUNK + 1) // block k of a bucket takes the chunks that start in bytes [k*FE_T, (k+1)*FE_T)
@@ -136,13 +133,12 @@ struct FlatArgs {
 
 // ---- the merge: one warp per slice, no block-wide synchronisation ---------------------------------------------
 // A slice needs: the old symbols that land in it, from the directory boundary a0 in front of its first one
-// (<= FT_DIR + FS_SLICE symbols = 128 cells, one TMA bulk copy), and its records (the slice of every record
-// array, TMA bulk copies widened to 16-byte boundaries).  The warp
+// (<= FT_DIR + slice symbols, one TMA bulk copy), and its records (read from the record arrays).  The warp
 //   (1) counts the old symbols cell by cell (raw prefix counts from a0: what rank() needs),
 //   (2) scatters its records into per-output-cell bit masks (which output positions are new, and their planes),
-//   (3) assembles its 64 output cells, two per lane: 32 old symbols from the right offset (funnel shift), one
-//       zero bit pushed in per new position, the new symbols' planes OR-ed on top,
-//   (4) sends the slice off with one TMA bulk store, writes the slice's symbol counts (= one directory tile),
+//   (3) assembles its output cells, two or four per lane: 32 old symbols from the right offset (funnel shift),
+//       one zero bit pushed in per new position, the new symbols' planes OR-ed on top,
+//   (4) sends the slice off with one TMA bulk store, writes the raw symbol counts of its directory tiles,
 //   (5) returns rank(a, P) = directory row + prefix count + partial cell count for each of its records.
 // The kernel is persistent: every warp owns two shared-memory stages and fetches the old symbols of its slice
 // i+2 while it merges slice i (its lane 0 is the producer); the slice's records are read straight from the
