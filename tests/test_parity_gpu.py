@@ -327,17 +327,20 @@ def test_one_long_string_among_short_ones(so):
 
 
 @not_on_emu
-def test_beyond_2_32_symbols_md5_vs_reference():
-    """45 M x 101 bp = 4.59 G symbols (> 2^32 positions) in one batch, RLO: md5 of the decoded index against the
-    md5 of the UNMODIFIED reference's output on the same seeded reads (tests/golden/ref_full_runs.json, recorded
-    by tools/ref_full_run.py --workload cfg2 --reads 45000000).  Reads are generated on the GPU with the
-    counter-based generator that tests/test_synth.py pins to the one that fed the reference."""
+@pytest.mark.parametrize("flags", ["-LRs", "-LR", "-LRr"])
+def test_beyond_2_32_symbols_md5_vs_reference(flags):
+    """45 M x 101 bp = 4.59 G symbols (> 2^32 positions) in one batch, RLO / input order / RCLO: md5 of the decoded
+    index against the md5 of the UNMODIFIED reference's output on the same seeded reads (tests/golden/
+    ref_full_runs.json, recorded by tools/ref_full_run.py --workload cfg2 --reads 45000000 --flags ...).  Reads are
+    generated on the GPU with the counter-based generator that tests/test_synth.py pins to the one that fed the reference."""
     import torch
     from ropebwt2_b200 import synth
     w = synth.workload("cfg2", 45_000_000)
-    rec = orc.ref_recorded(w, "-LRs")
+    rec = orc.ref_recorded(w, flags)
     if rec is None:
-        pytest.skip("no recorded reference run for " + synth.workload_key(w, "-LRs"))
+        pytest.skip("no recorded reference run for " + synth.workload_key(w, flags))
+    so, fwd, rev = flags_to_mode(flags)
+    assert fwd and not rev
     nbytes = w["n"] * (w["L"] + 1)
     host = np.empty(nbytes, dtype=np.uint8)
     ht = torch.from_numpy(host)
@@ -349,7 +352,7 @@ def test_beyond_2_32_symbols_md5_vs_reference():
         ht[a * (w["L"] + 1):b * (w["L"] + 1)].copy_(t)
         del t
     torch.cuda.empty_cache()
-    m = MRope(1)
+    m = MRope(so)
     m.insert_multi(host)
     assert m.total() == nbytes
     md5, total = orc.index_md5(load(), m.h)
