@@ -486,7 +486,9 @@ def run_single_batch(args, torch, red, rank, world, local):
         "config": {"workload": "BASELINE %s: %s (%d reads per GPU), forward strand, %s, one batch into an empty index" % (args.config, synth.workload_key(w, flags), n, "RLO" if so else "input order"),
                    "reads_per_gpu": n, "read_length": ln, "sorting_order": "RLO" if so else "IO",
                    "parallelism": (f"sharded x{world}: ONE index of {world * n} reads, 36 sub-buckets over {world} GPUs, "
-                                   "per column one count all-gather + one string-state exchange (NCCL send/recv)") if sharded
+                                   "per column one count all-gather + the string ids by NCCL send/recv under the merge + "
+                                   + ("the new interval starts stored by the merge kernel straight into the peers' HBM (CUDA IPC mappings over NVLink)"
+                                      if st.get("p2p_batches", 0) else "the interval starts by NCCL send/recv behind the merge")) if sharded
                    else (f"replicas x{world}" if world > 1 else "one GPU"),
                    "l2": "inputs (%.1f GB batch, multi-GB symbol array) far exceed the 126 MB L2" % (nbytes / 1e9),
                    "timing": "CUDA events on the engine stream around each call; wall-clock cross-check %.3f s/step" % (wall_value / args.steps),
@@ -505,7 +507,10 @@ def run_single_batch(args, torch, red, rank, world, local):
     }
     if sharded:
         out["exchange"] = {"ms_per_step_max_over_ranks": ms_exch / args.steps, "bytes_received_per_step_rank0": int(st["exch_bytes"] / args.steps),
-                           "collectives_per_column": "1 all-gather (1.8 KB/rank) + 1 grouped send/recv of the string state"}
+                           "interval_starts": "direct delivery: peer stores from the k_flat_merge epilogue + a 16-byte stream barrier" if st.get("p2p_batches", 0)
+                           else "ncclSend/ncclRecv behind the merge (RB2_P2P=0, or the peers' buffers could not be mapped)",
+                           "collectives_per_column": "1 all-gather (1.8 KB/rank) + 1 grouped send/recv of the string ids"
+                           + (" + 1 16-byte all-gather as barrier" if st.get("p2p_batches", 0) else " + 1 grouped send/recv of the interval starts")}
     if not args.no_cpu_baseline and ref_binary() is not None and world == 1:
         out["cpu_baseline"] = cpu_sample(args, flags)
     else:

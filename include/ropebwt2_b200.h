@@ -64,6 +64,7 @@ typedef struct {
 	int64_t exch_bytes;                 /* sharded build: bytes of string state this rank received */
 	double  ms_convert;                 /* dense regime: leaf blocks <-> flat symbol array at the ends of a batch */
 	int64_t flat_batches;               /* batches that ran in the dense regime (k_flat_merge instead of the block merges) */
+	int64_t p2p_batches;                /* sharded build: batches whose merge kernels stored the new interval starts straight into the peer GPUs' memory */
 } rb2_stats_t;
 
 int  rb2_device_count(void);

@@ -229,7 +229,9 @@ def ref_stream_run(w: dict, flags: str = "-LRs", batch: str = "", want_md5: bool
     to.start(), te.start()
     try:
         for lines in synth.stream_lines(w, threads=gen_threads):
-            p.stdin.write(lines)
+            mv = memoryview(lines)
+            while len(mv):  # (an unbuffered pipe write may be partial: one write() moves at most 2^31 - 4096 bytes)
+                mv = mv[p.stdin.write(mv):]
         p.stdin.close()
     except BrokenPipeError:
         pass
@@ -240,6 +242,8 @@ def ref_stream_run(w: dict, flags: str = "-LRs", batch: str = "", want_md5: bool
     if rc != 0:
         raise RuntimeError("reference failed: " + stderr[-500:])
     hot = [float(ln.split(" symbols in ")[1].split(" sec")[0]) for ln in stderr.splitlines() if "] inserted " in ln]
+    if nout[0] and nout[0] != w["n"] * (w["L"] + 1) * (2 if "R" not in flags else 1) + 1:
+        raise RuntimeError(f"reference printed {nout[0]} symbols for {w['n']} reads of {w['L']}")
     return {"workload": w, "flags": flags, "batch": batch or "default (-m 10415295693 bytes, main.c:94)",
             "md5_text": md5.hexdigest() if want_md5 else None, "text_bytes": nout[0], "hot_path_s": sum(hot), "hot_path_s_per_batch": hot,
             "wall_s": wall, "host_cores": os.cpu_count(), "threads": "4 workers + master",

@@ -33,7 +33,8 @@ class Stats(C.Structure):
                                          "merge_blocks", "merge_bytes_rw", "n_records", "pool_blocks", "pool_capacity")] + \
                [(n, C.c_double) for n in ("ms_total", "ms_h2d", "ms_transpose", "ms_members", "ms_groups", "ms_merge", "ms_directory",
                                           "ms_merge_general")] + [("general_items", C.c_int64), ("ms_exchange", C.c_double),
-                                                                  ("exch_bytes", C.c_int64), ("ms_convert", C.c_double), ("flat_batches", C.c_int64)]
+                                                                  ("exch_bytes", C.c_int64), ("ms_convert", C.c_double), ("flat_batches", C.c_int64),
+                                                                  ("p2p_batches", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -38,10 +38,10 @@ static bool async_enabled(const rb2_engine *e)
 // b - a, field by field (every field of rb2_stats_t is 8 bytes wide: int64_t or double)
 static rb2_stats_t stats_delta(const rb2_stats_t &a, const rb2_stats_t &b)
 {
-	static_assert(sizeof(rb2_stats_t) == 23 * 8, "rb2_stats_t: 23 fields of 8 bytes");
+	static_assert(sizeof(rb2_stats_t) == 24 * 8, "rb2_stats_t: 24 fields of 8 bytes");
 	const uint32_t isDouble = 0xffu << 10 | 1u << 19 | 1u << 21; // ms_total .. ms_merge_general, ms_exchange, ms_convert
 	rb2_stats_t d;
-	for (int i = 0; i < 23; ++i) {
+	for (int i = 0; i < 24; ++i) {
 		if (isDouble >> i & 1) ((double*)&d)[i] = ((const double*)&b)[i] - ((const double*)&a)[i];
 		else ((int64_t*)&d)[i] = ((const int64_t*)&b)[i] - ((const int64_t*)&a)[i];
 	}

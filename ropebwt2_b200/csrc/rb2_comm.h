@@ -9,6 +9,11 @@
 //                    source offset / destination offset / length known to every rank from the
 //                    gathered counts
 //   gather_blocks  : once per batch, every rank's column-major symbol matrix is replicated
+//   p2p_map / barrier_stream : direct delivery -- every rank maps the other ranks' receive buffers
+//                    (CUDA IPC between processes, plain pointers between threads), so that the merge
+//                    kernel's epilogue stores each rank it computes straight into the memory of the
+//                    rank that needs it next (NVLink stores issued under the merge), and a
+//                    stream-ordered barrier replaces the send/recv of those 8 bytes per string
 //
 // Two back ends behind one interface:
 //   NcclComm  : one process per GPU (torchrun); ncclSend/ncclRecv/ncclBroadcast/ncclAllGather over
@@ -38,6 +43,13 @@ struct Comm {
 	// dst[r] (in MY memory) receives rank r's block of bytes[r] bytes; dst[rank] already holds mine
 	virtual void gather_blocks(uint8_t *const *dst, const size_t *bytes, cudaStream_t st) = 0;
 	virtual void barrier(cudaStream_t st) = 0;
+	// Collective.  peers[r] = an address in MY address space of rank r's buffer `mine` (peers[rank] = mine), writable
+	// by my kernels.  false (on every rank alike) when some rank cannot map some buffer: nothing stays mapped.
+	virtual bool p2p_map(void *mine, void **peers, cudaStream_t st) = 0;
+	virtual void p2p_unmap(void **peers) = 0;
+	// Collective, stream ordered: what any rank queued on its stream before this call has completed (peer stores
+	// included) before anything a rank queues behind it starts.
+	virtual void barrier_stream(cudaStream_t st) = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -80,6 +92,22 @@ struct LocalComm : Comm {
 		RB2_CUDA(cudaStreamSynchronize(st));
 		sync_threads(); // everybody has pulled: send buffers may be reused
 	}
+	bool p2p_map(void *mine, void **peers, cudaStream_t st) override {
+		struct Ad { void *p; int dev; } me_, all[RB2_MAX_RANKS];
+		me_.p = mine; RB2_CUDA(cudaGetDevice(&me_.dev));
+		allgather_host(&me_, sizeof(me_), all, st);
+		int ok = 1, oks[RB2_MAX_RANKS];
+		for (int r = 0; r < n; ++r) {
+			peers[r] = all[r].p;
+			if (all[r].dev != me_.dev) { int can = 0; if (cudaDeviceCanAccessPeer(&can, me_.dev, all[r].dev) != cudaSuccess || !can) ok = 0; } // (enabled by rb2_group_create)
+		}
+		cudaGetLastError();
+		allgather_host(&ok, sizeof(ok), oks, st);
+		for (int r = 0; r < n; ++r) ok = ok && oks[r];
+		return ok != 0;
+	}
+	void p2p_unmap(void **) override {}
+	void barrier_stream(cudaStream_t st) override { barrier(st); }
 	void gather_blocks(uint8_t *const *dst, const size_t *bytes, cudaStream_t st) override {
 		RB2_CUDA(cudaStreamSynchronize(st));
 		g->slot[rank] = dst[rank];
@@ -130,6 +158,7 @@ static NcclApi *nccl_api(void)
 struct NcclComm : Comm {
 	NcclApi *api; ncclComm_t comm;
 	uint8_t *hSend, *hRecv, *dSend, *dRecv; // staging of the small all-gather
+	uint8_t *dBar; // send + receive words of barrier_stream
 	enum { SMALL = 4096 };
 	NcclComm(int rank_, int n_, const void *uid) {
 		rank = rank_; n = n_;
@@ -142,10 +171,11 @@ struct NcclComm : Comm {
 		RB2_NCCL(api->CommInitRank(&comm, n, id, rank));
 		RB2_CUDA(cudaMallocHost(&hSend, SMALL)); RB2_CUDA(cudaMallocHost(&hRecv, SMALL * RB2_MAX_RANKS));
 		RB2_CUDA(cudaMalloc(&dSend, SMALL)); RB2_CUDA(cudaMalloc(&dRecv, SMALL * RB2_MAX_RANKS));
+		RB2_CUDA(cudaMalloc(&dBar, 16 * (RB2_MAX_RANKS + 1))); RB2_CUDA(cudaMemset(dBar, 0, 16 * (RB2_MAX_RANKS + 1)));
 	}
 	~NcclComm() override {
 		api->CommDestroy(comm);
-		cudaFreeHost(hSend); cudaFreeHost(hRecv); cudaFree(dSend); cudaFree(dRecv);
+		cudaFreeHost(hSend); cudaFreeHost(hRecv); cudaFree(dSend); cudaFree(dRecv); cudaFree(dBar);
 	}
 	void allgather_host(const void *send, size_t bytes, void *recv, cudaStream_t st) override {
 		if (bytes > SMALL) RB2_FATAL("NcclComm: small all-gather of %zu bytes", bytes);
@@ -175,4 +205,30 @@ struct NcclComm : Comm {
 		RB2_NCCL(api->GroupEnd());
 	}
 	void barrier(cudaStream_t st) override { uint32_t x = 0, all[RB2_MAX_RANKS]; allgather_host(&x, 4, all, st); }
+	// CUDA IPC: the buffer must be a whole cudaMalloc allocation.  The handles travel through the small all-gather.
+	bool p2p_map(void *mine, void **peers, cudaStream_t st) override {
+		struct Msg { cudaIpcMemHandle_t h; int ok; } me_, all[RB2_MAX_RANKS];
+		memset(&me_, 0, sizeof(me_));
+		me_.ok = cudaIpcGetMemHandle(&me_.h, mine) == cudaSuccess;
+		cudaGetLastError();
+		allgather_host(&me_, sizeof(me_), all, st);
+		int ok = 1, oks[RB2_MAX_RANKS];
+		for (int r = 0; r < n; ++r) { peers[r] = 0; ok = ok && all[r].ok; }
+		for (int r = 0; r < n && ok; ++r) {
+			if (r == rank) { peers[r] = mine; continue; }
+			if (cudaIpcOpenMemHandle(&peers[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peers[r] = 0; ok = 0; }
+		}
+		cudaGetLastError();
+		allgather_host(&ok, sizeof(ok), oks, st);
+		for (int r = 0; r < n; ++r) ok = ok && oks[r];
+		if (!ok) p2p_unmap(peers);
+		return ok != 0;
+	}
+	void p2p_unmap(void **peers) override {
+		for (int r = 0; r < n; ++r) { if (r != rank && peers[r]) cudaIpcCloseMemHandle(peers[r]); peers[r] = 0; }
+		cudaGetLastError();
+	}
+	// a 16-byte all-gather: its kernel on one rank cannot finish before every other rank's has started, i.e. before
+	// everything they queued in front of it (their merge kernels and the peer stores those issued) has completed
+	void barrier_stream(cudaStream_t st) override { RB2_NCCL(api->AllGather(dBar, dBar + 16, 16, ncclUint8, comm, st)); }
 };

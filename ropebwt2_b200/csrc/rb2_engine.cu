@@ -1880,6 +1880,8 @@ struct rb2_engine {
 	int64_t *dDirOffPre, *hDirOffPre; // the same in front of the column (dense regime: record positions are pre-column)
 	uint32_t *hPlan; DevBuf<uint32_t> plan;
 	cudaStream_t st2; cudaEvent_t evEarly, evMerge; // second stream: the part of the exchange that overlaps the merge
+	DevBuf<int64_t> gLrx[2]; // sharded: interval starts of the current / the next column (alternating)
+	PeerRoute *dRoute;       // direct delivery: the merge epilogue's routing table of the column
 	// RB2_GPUS > 1 (rb2_cluster.inl): this engine is a proxy in front of nChild sharded engines
 	int nChild; rb2_engine *child[RB2_MAX_RANKS]; rb2_group *grp;
 	FlatState flat; DevBuf<uint32_t> recPre;
@@ -2087,7 +2089,7 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
 	e->nChild = 0; e->grp = 0;
-	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0;
+	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0; e->dRoute = 0;
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
 	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
@@ -2177,7 +2179,7 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
-	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); }
+	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); e->gLrx[0].release(); e->gLrx[1].release(); if (e->dRoute) RB2_CUDA(cudaFree(e->dRoute)); }
 	e->flat.release(); e->recPre.release();
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
 	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);

@@ -120,6 +120,27 @@ __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, u
 	desc[t] = d;
 }
 
+// Sharded build, direct delivery: entry dst of this rank's column output (the rank of a string after this column)
+// belongs in the state array of the rank that owns the string's next sub-bucket.  The output order is cut into at
+// most 5 x 36 pieces (symbol x source sub-bucket), each contiguous on both sides; base[k] is the address in THIS
+// rank's address space (a peer mapping over NVLink, rb2_comm.h p2p_map) of where entry 0 WOULD go if piece k
+// started there, so that the store is base[k][dst].
+#define ROUTE_MAXPC 192
+struct PeerRoute { uint32_t np, pad; uint32_t so[ROUTE_MAXPC]; int64_t *base[ROUTE_MAXPC]; };
+
+__device__ __forceinline__ void route_store(const PeerRoute *rt, uint32_t dst, int64_t g)
+{
+	int lo = 0, hi = (int)rt->np - 1; // last piece that starts at or in front of dst
+	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(rt->so + mid) <= dst) lo = mid; else hi = mid - 1; }
+	rt->base[lo][dst] = g;
+}
+
+__global__ void k_route_store(PeerRoute *dst, const PeerRoute v)
+{
+	if (threadIdx.x == 0) { dst->np = v.np; dst->pad = 0; }
+	for (uint32_t k = threadIdx.x; k < ROUTE_MAXPC; k += blockDim.x) { dst->so[k] = v.so[k]; dst->base[k] = v.base[k]; }
+}
+
 struct FlatArgs {
 	const uint8_t *oldS; const int64_t *oldDir;   // old array, counts in front of every FT_DIR-th old symbol
 	uint8_t *newS; uint64_t nNew; uint32_t *newTileCnt; // new array and its per-FT_DIR-tile symbol counts
@@ -129,6 +150,7 @@ struct FlatArgs {
 	// sharded engines: records carry whole-index positions; bucket b of this rank sits recOff[b*7+6]
 	// symbols (recOff[b*7+a] symbols a) further right in the whole index than in the local array
 	const int64_t *recOff; int nb;
+	const PeerRoute *route; // sharded, direct delivery: where gLNext[dst] really lives (null: gLNext is a local array)
 };
 
 // ---- the merge: one warp per slice, no block-wide synchronisation ---------------------------------------------

@@ -154,7 +154,8 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			int64_t g = base + raw_symbol(rr, a) + part;
 			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
 				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k) * 7 + a];
-			A.gLNext[dst] = g;
+			if (A.route) route_store(A.route, dst, g); // straight into the next owner's state array (a peer store)
+			else A.gLNext[dst] = g;
 		}
 	}
 	__syncwarp(); // the inputs and W.mask / W.pre may be reused

@@ -231,15 +231,39 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (flat) flat_begin(e, addLocal);
 	else { ensure_blocks(e); blocks_edited(e); } // a sparse batch edits the leaf blocks
 	if (!flat) reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
+	// ---- direct delivery of the interval starts (dense regime): every rank maps every rank's two state buffers ----
+	// The buffers are sized for the worst case once (no rank ever holds more than every string of the batch), so
+	// the mappings stay valid for the whole batch.
+	int64_t *peerGL[2][RB2_MAX_RANKS];
+	bool direct = false;
+	if (P > 1) {
+		static int want = -1;
+		if (want < 0) { const char *ws = getenv("RB2_P2P"); want = ws && *ws ? atoi(ws) : 1; }
+		const size_t capG = (size_t)mAll + 64;
+		size_t freeB = 0, totB = 0;
+		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
+		const size_t extra = (e->gLrx[0].cap < capG ? capG * 9 : 0) + (e->gLrx[1].cap < capG ? capG * 9 : 0);
+		uint32_t okMine = want && flat && extra + ((size_t)2 << 30) < freeB, oks[RB2_MAX_RANKS];
+		cm->allgather_host(&okMine, 4, oks, e->st);
+		direct = true;
+		for (int r = 0; r < P; ++r) direct = direct && oks[r] != 0;
+		if (direct) {
+			e->gLrx[0].need(capG); e->gLrx[1].need(capG);
+			if (!e->dRoute) RB2_CUDA(cudaMalloc(&e->dRoute, sizeof(PeerRoute)));
+			if (!cm->p2p_map(e->gLrx[0].p, (void**)peerGL[0], e->st)) direct = false;
+			else if (!cm->p2p_map(e->gLrx[1].p, (void**)peerGL[1], e->st)) { cm->p2p_unmap((void**)peerGL[0]); direct = false; }
+		}
+	}
 	uint32_t G = 0, M = 0;
 	uint32_t gBkt[NBA], mBkt[NBA];
 	uint64_t mglob[NBMAX];
 	memset(mglob, 0, sizeof(mglob)); mglob[0] = mAll;
 	uint64_t Gglob = sorted ? 1 : mAll, Mglob = mAll;
 	const int cs = 0; // current state lives in buffer 0; buffer 1 receives a column's output in source order
+	int gcur = 0;     // (the interval starts alternate between gLrx[0] and gLrx[1]: peers may write the next while I read the current)
 	if (e->owner[0] == me) {
-		e->gL[0].need(Gglob + 64); e->gSize[0].need(Gglob + 64); e->gOff[0].need(Gglob + 64); e->sid[0].need(mAll + 64);
-		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gL[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
+		e->gLrx[0].need(Gglob + 64); e->gSize[0].need(Gglob + 64); e->gOff[0].need(Gglob + 64); e->sid[0].need(mAll + 64);
+		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gLrx[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
 		G = (uint32_t)Gglob; M = (uint32_t)mAll;
 	}
 	for (int b = 0; b < NBA; ++b) { gBkt[b] = b == 0 ? 0 : G; mBkt[b] = b == 0 ? 0 : M; }
@@ -252,6 +276,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	for (int64_t col = 0; Mglob > 0; ++col) {
 		if ((uint64_t)col >= ncolAll) RB2_FATAL("internal: live strings beyond the last column");
 		Dir &d = e->dir[e->cur];
+		int64_t *const gLc = e->gLrx[gcur].p; // interval starts of this column (null on a rank without groups)
 		// ---- per-column capacity (contents of these buffers are dead here) ---------------------
 		// (a group yields at most one next group and one record per symbol, plus records for counts above the run limit)
 		const size_t gnMax = std::min<uint64_t>(M, 6ull * G);
@@ -306,13 +331,13 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			if (!lean) wait_late(); // the group kernels read the interval starts
 			ph_begin(e, PH_GROUPS);
 			if (useSizes) {
-				if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, e->gL[cs].p, e->gSize[cs].p,
+				if (flat) LAUNCH(e, k_flat_rank_groups, cdiv(G, 128), 128, 0, e->flat.s[e->flat.cur].p, e->flat.dir[e->flat.cur].p, G, gLc, e->gSize[cs].p,
 				                 e->sizes6.p, e->dctl, e->dDirOffPre, e->nb);
-				else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, e->gL[cs].p, e->gSize[cs].p, e->sizes6.p, e->dctl);
+				else LAUNCH(e, k_rank_groups, cdiv(G, 128), 128, 0, e->pool, d, e->nlog, G, gLc, e->gSize[cs].p, e->sizes6.p, e->dctl);
 			}
 			if (G == M) {
 				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M, flat ? e->recPre.p : (uint32_t*)0);
-				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
+				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, gLc, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
 				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 				else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
@@ -321,7 +346,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			} else {
 				const uint32_t nGC = cdiv(G, 256);
 				e->grpCta.need((size_t)nGC * NGC + NGC);
-				GroupArgs ga = { e->gOff[cs].p, e->gL[cs].p, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
+				GroupArgs ga = { e->gOff[cs].p, gLc, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->asym.p, e->tileB.p, G,
 				                 e->grpCta.p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, e->dctl, flat ? e->recPre.p : (uint32_t*)0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_group_pass<0, true>), nGC, 256, 0, ga);
 				else LAUNCH(e, (k_group_pass<0, false>), nGC, 256, 0, ga);
@@ -339,7 +364,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			e->flat.pending = 0;
 			nrec = h->nrec;
 			wait_late();
-			if (flat && nrec) LAUNCH(e, k_flat_localize, cdiv(nrec, 256), 256, 0, lean ? e->gL[cs].p : e->recP.p, nrec, e->dctl, e->dDirOffPre, e->nb);
+			if (flat && nrec) LAUNCH(e, k_flat_localize, cdiv(nrec, 256), 256, 0, lean ? gLc : e->recP.p, nrec, e->dctl, e->dDirOffPre, e->nb);
 		}
 		// ---- gather every rank's tables -----------------------------------------------------------
 		ShardTab mineT;
@@ -416,8 +441,23 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			cm->group_end(e->st2);
 			RB2_CUDA(cudaEventRecord(e->evEarly, e->st2));
 		};
+		// direct delivery: the pieces of MY output order and where each lands (the next column's buffer of its target rank)
+		const bool deliver = direct && MglobN > 0;
+		if (deliver && nrec > 0) {
+			PeerRoute rt; memset(&rt, 0, sizeof(rt));
+			for (size_t k = 0; k < pcG.size(); ++k) if (pcG[k].src == me && pcG[k].n) {
+				if (rt.np >= ROUTE_MAXPC) RB2_FATAL("internal: more than %d output pieces", ROUTE_MAXPC);
+				rt.so[rt.np] = (uint32_t)pcG[k].so;
+				rt.base[rt.np] = peerGL[gcur ^ 1][pcG[k].dst] + (int64_t)pcG[k].dof - (int64_t)pcG[k].so;
+				++rt.np;
+			}
+			// (no piece at all: every record of mine ends its string -- none has a target)
+			LAUNCH(e, k_route_store, 1, 128, 0, e->dRoute, rt);
+		}
 		auto merge = [&]() {
-			if (flat) { if (nrec > 0) flat_apply_records(e, nrec, M, e->gL[1].p, lean ? e->gL[cs].p : (const int64_t*)0); } // (no records: my array does not change)
+			if (flat) { // (no records: my array does not change)
+				if (nrec > 0) flat_apply_records(e, nrec, M, deliver ? (int64_t*)0 : e->gL[1].p, lean ? gLc : (const int64_t*)0, 0, deliver ? e->dRoute : (const PeerRoute*)0);
+			}
 			else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
 			else rebuild_directory(e, false);
 		};
@@ -429,17 +469,24 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
 		if (MglobN > 0) {
-			// interval starts: behind the merge, on the second stream -- the next column only needs them when its
-			// records are merged (all-singleton columns) or its groups are scanned
-			RB2_CUDA(cudaEventRecord(e->evMerge, e->st));
-			e->gL[cs].need((size_t)Gn + 64);
-			RB2_CUDA(cudaStreamWaitEvent(e->st2, e->evMerge, 0));
-			RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][0], e->st2));
-			cm->group_begin();
-			cm->exchange(e->gL[1].p, e->gL[cs].p, 8, pcG.data(), (int)pcG.size(), e->st2);
-			cm->group_end(e->st2);
-			RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][1], e->st2));
-			latePending = true;
+			if (deliver) {
+				// interval starts: the merge kernels have stored them where they belong; once every rank's merge
+				// is through, every rank's next-column buffer is complete
+				cm->barrier_stream(e->st);
+			} else {
+				// interval starts: behind the merge, on the second stream -- the next column only needs them when
+				// its records are merged (all-singleton columns) or its groups are scanned
+				RB2_CUDA(cudaEventRecord(e->evMerge, e->st));
+				e->gLrx[gcur ^ 1].need((size_t)Gn + 64);
+				RB2_CUDA(cudaStreamWaitEvent(e->st2, e->evMerge, 0));
+				RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][0], e->st2));
+				cm->group_begin();
+				cm->exchange(e->gL[1].p, e->gLrx[gcur ^ 1].p, 8, pcG.data(), (int)pcG.size(), e->st2);
+				cm->group_end(e->st2);
+				RB2_CUDA(cudaEventRecord(e->ev[PH_EXCH][1], e->st2));
+				latePending = true;
+			}
+			gcur ^= 1;
 			// member ids / ranges arrived on the second stream: finish the member ranges on the main one
 			RB2_CUDA(cudaStreamWaitEvent(e->st, e->evEarly, 0));
 			if (singles) { if (Gn + 1 > 0) LAUNCH(e, k_fill_u32, cdiv((uint64_t)Gn + 1, 256), 256, 0, e->gOff[cs].p, Gn + 1, 0u, 1u); }
@@ -460,6 +507,11 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int b = 0; b < NBA; ++b) { gBkt[b] = gBktN[b]; mBkt[b] = mBktN[b]; }
 		memcpy(mglob, mglobNext, sizeof(mglob));
 		Gglob = GglobN; Mglob = MglobN;
+	}
+	if (direct) { // (every rank left the loop behind the same column, the barrier of the one before is behind all of them)
+		cm->barrier(e->st);
+		cm->p2p_unmap((void**)peerGL[0]); cm->p2p_unmap((void**)peerGL[1]);
+		++e->stats.p2p_batches;
 	}
 	if (flat) {
 		RB2_CUDA(cudaStreamSynchronize(e->st));

@@ -243,6 +243,7 @@ def hash_reads(w: dict, a: int, b: int, device=None):
 def stream_lines(w: dict, chunk: int = 2_000_000, threads: int = 2):
     """The workload as `-L` text (one read per line, main.c:180-186), chunk by chunk (bytes)."""
     lib = c_generator()
+    chunk = max(1, min(chunk, 256_000_000 // (w["L"] + 1)))  # (bounded in bytes: long reads)
     for a in range(0, w["n"], chunk):
         b = min(w["n"], a + chunk)
         if lib is not None:

@@ -37,4 +37,7 @@ def test_nccl_two_ranks_torchrun():
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "shard_nccl_check.py")],
                        capture_output=True, text=True, timeout=800)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("bit-exact") == 3
+    assert r.stdout.count("bit-exact") == 6, r.stdout[-2000:]
+    assert r.stdout.count("dense batches 2") == 3, r.stdout[-2000:]
+    if os.environ.get("RB2_P2P", "1") != "0":
+        assert r.stdout.count("direct delivery 2") == 3, r.stdout[-2000:]  # the peer mappings were really used

@@ -22,7 +22,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
     bad = 0
-    for so in (1, 0, 2):
+    # each order twice: regime by cost estimate (sparse at this size), then the dense regime forced -- whose merge
+    # kernels store the new interval starts straight into the peer's memory (CUDA IPC mappings, RB2_P2P)
+    for so, dense in ((1, 0), (0, 0), (2, 0), (1, 1), (0, 1), (2, 1)):
+        if dense:
+            os.environ["RB2_FLAT"] = "1"
+        else:
+            os.environ.pop("RB2_FLAT", None)
         uid = broadcast_bytes(nccl_unique_id() if rank == 0 else None)
         e = ShardedEngine(local, so, rank, world, nccl_uid=uid)
         batches = [uniform_reads(n, 60, 5 + so, n_frac=0.005), genome_reads(n // 2, 45, 6, coverage=40.0)]
@@ -38,7 +44,8 @@ def main():
             ok = np.array_equal(got, o.text()) and np.array_equal(e.counts(), o.counts())
             st = e.stats()
             print(f"so={so} world={world}: {e.total()} symbols {'bit-exact' if ok else 'MISMATCH'}; "
-                  f"exchange {st['ms_exchange']:.1f} ms of {st['ms_total']:.1f} ms, {st['exch_bytes']} bytes received", flush=True)
+                  f"exchange {st['ms_exchange']:.1f} ms of {st['ms_total']:.1f} ms, {st['exch_bytes']} bytes received, "
+                  f"dense batches {st['flat_batches']}, {'direct delivery' if st['p2p_batches'] else 'send/recv'} {st['p2p_batches']}", flush=True)
             bad += not ok
         e.close()
     flag = torch.tensor([bad], device="cuda")
