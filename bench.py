@@ -469,6 +469,7 @@ def run_single_batch(args, torch, red, rank, world, local):
         else:
             parity = {"result": "symbol conservation checked in-run at this N; bit-exactness of the sharded build: tests/test_sharded_gpu.py, tests/test_sharded_nccl.py"}
     if sharded:
+        eng.quiesce()  # collective: the ranks close the mappings of each other's state buffers before anybody frees them
         eng.close()
     else:
         mr.close()

@@ -148,6 +148,11 @@ int64_t rb2_last_sentinel_rank(rb2_engine_t *e);
  * be 0); the strings are ordered by (rank, position in the rank's buffer).  rb2_counts, rb2_reset,
  * rb2_get_stats work as before; rb2_num_blocks / rb2_fetch_blocks address sub-bucket x*6+y (blocks
  * exist only on its owner, rb2_shard_owner()); the whole BWT is the concatenation over sub-buckets.
+ *
+ * Dense batches deliver the new interval starts directly: every rank maps the other ranks' state buffers (CUDA IPC
+ * between processes) and the merge kernel stores into them; the mappings are kept from batch to batch.
+ * rb2_sharded_quiesce (collective) closes them in an ordered way -- call it on every rank before the ranks destroy
+ * their engines at different times; the next dense batch maps again.  RB2_P2P=0 keeps to ncclSend/ncclRecv.
  */
 typedef struct rb2_group rb2_group_t;
 rb2_group_t *rb2_group_create(int nranks);
@@ -156,6 +161,7 @@ void rb2_nccl_unique_id(uint8_t out[128]);
 rb2_engine_t *rb2_create_sharded(int device, int sorting_order, int rank, int nranks, rb2_group_t *group, const uint8_t *nccl_uid);
 void rb2_insert_multi_sharded(rb2_engine_t *e, int64_t len, const uint8_t *s_host);
 void rb2_insert_multi_sharded_dev(rb2_engine_t *e, int64_t len, const uint8_t *s_dev);
+void rb2_sharded_quiesce(rb2_engine_t *e);
 int  rb2_shard_owner(int nranks, int subbucket);
 int  rb2_num_buckets(const rb2_engine_t *e); /* 6, or 36 for a sharded engine */
 

@@ -24,7 +24,7 @@ RB2_SYMBOLS = ["rb2_device_count", "rb2_create", "rb2_create_auto", "rb2_destroy
                "rb2_dev_free", "rb2_dev_upload", "rb2_reset", "rb2_host_alloc", "rb2_host_free", "rb2_insert_run",
                "rb2_bucket_rank2a", "rb2_last_sentinel_rank",
                "rb2_group_create", "rb2_group_destroy", "rb2_nccl_unique_id", "rb2_create_sharded",
-               "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_shard_owner", "rb2_num_buckets",
+               "rb2_insert_multi_sharded", "rb2_insert_multi_sharded_dev", "rb2_sharded_quiesce", "rb2_shard_owner", "rb2_num_buckets",
                "rb2_rank_batch", "rb2_sync", "rb2_span_begin", "rb2_span_ms", "rb2_job_history"]
 
 
@@ -129,6 +129,8 @@ def load(rebuild: bool = False, path: str = None) -> C.CDLL:
     L.rb2_create_sharded.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.rb2_insert_multi_sharded.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.rb2_insert_multi_sharded_dev.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L.rb2_sharded_quiesce.restype = None
+    L.rb2_sharded_quiesce.argtypes = [C.c_void_p]
     L.rb2_shard_owner.restype = C.c_int
     L.rb2_shard_owner.argtypes = [C.c_int, C.c_int]
     L.rb2_rank_batch.argtypes = [C.c_void_p, C.c_int64, _i64p, _i64p]
@@ -341,6 +343,10 @@ class ShardedEngine(Engine):
 
     def insert_multi_dev(self, dev_ptr: int, n: int) -> None:
         self.L.rb2_insert_multi_sharded_dev(self.h, n, dev_ptr)
+
+    def quiesce(self) -> None:
+        """Collective: close the peer mappings of the direct delivery (before ranks close at different times)."""
+        self.L.rb2_sharded_quiesce(self.h)
 
     def owned(self):
         return [s for s in range(36) if self.L.rb2_shard_owner(self.nranks, s) == self.rank]

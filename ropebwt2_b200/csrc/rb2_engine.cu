@@ -24,6 +24,7 @@
 //      directory rebuild (prefix sums).
 //  * No CPU fallback: every failure aborts.
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <vector>
 #include <deque>
@@ -1882,6 +1883,7 @@ struct rb2_engine {
 	cudaStream_t st2; cudaEvent_t evEarly, evMerge; // second stream: the part of the exchange that overlaps the merge
 	DevBuf<int64_t> gLrx[2]; // sharded: interval starts of the current / the next column (alternating)
 	PeerRoute *dRoute;       // direct delivery: the merge epilogue's routing table of the column
+	int64_t *peerGL[2][RB2_MAX_RANKS]; bool p2pMapped; // every rank's gLrx[k] in my address space (kept across batches)
 	// RB2_GPUS > 1 (rb2_cluster.inl): this engine is a proxy in front of nChild sharded engines
 	int nChild; rb2_engine *child[RB2_MAX_RANKS]; rb2_group *grp;
 	FlatState flat; DevBuf<uint32_t> recPre;
@@ -2089,7 +2091,7 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
 	e->nChild = 0; e->grp = 0;
-	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0; e->dRoute = 0;
+	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0; e->dRoute = 0; e->p2pMapped = false; memset(e->peerGL, 0, sizeof(e->peerGL));
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
 	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
@@ -2179,6 +2181,9 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dctl)); RB2_CUDA(cudaFreeHost(e->hctl));
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
+	if (e->comm && e->p2pMapped) { // not collective: close what I imported; my own buffers are freed below (rb2_sharded_quiesce is the collective, ordered way)
+		e->comm->p2p_unmap((void**)e->peerGL[0]); e->comm->p2p_unmap((void**)e->peerGL[1]); e->p2pMapped = false;
+	}
 	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); e->gLrx[0].release(); e->gLrx[1].release(); if (e->dRoute) RB2_CUDA(cudaFree(e->dRoute)); }
 	e->flat.release(); e->recPre.release();
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);

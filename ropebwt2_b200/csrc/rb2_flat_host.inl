@@ -205,7 +205,7 @@ static void release_batch_scratch(rb2_engine *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	e->sbuf.release(); e->T.release(); e->asym.release(); e->sizes6.release(); e->recP.release(); e->recSC.release(); e->recDst.release(); e->recPre.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
-	if (e->comm) { e->gLrx[0].release(); e->gLrx[1].release(); } // (mapped by peers only for the duration of a batch)
+	if (e->comm && !e->p2pMapped) { e->gLrx[0].release(); e->gLrx[1].release(); } // (not while peers map them)
 	e->strEnd.release(); e->tileA.release(); e->tileB.release(); e->grpCta.release();
 	FlatState &f = e->flat;
 	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.desc.release();

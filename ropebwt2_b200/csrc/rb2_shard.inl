@@ -162,6 +162,24 @@ __global__ void k_rebase_goff(uint32_t *gOff, uint32_t G, uint32_t M, const uint
 
 struct ShardTab { uint32_t grp[(NBMAX + 1) * 6], mem[(NBMAX + 1) * 6]; };
 
+// Collective (every rank holds mappings or none does): close my mappings of the peers' state buffers.  Behind the
+// barrier nobody maps anybody's buffers: they may be freed or grown.
+static void shard_unmap_peers(rb2_engine *e)
+{
+	if (!e->p2pMapped) return;
+	RB2_CUDA(cudaStreamSynchronize(e->st));
+	e->comm->p2p_unmap((void**)e->peerGL[0]); e->comm->p2p_unmap((void**)e->peerGL[1]);
+	e->comm->barrier(e->st);
+	e->p2pMapped = false;
+}
+
+extern "C" void rb2_sharded_quiesce(rb2_engine_t *e)
+{
+	if (!e->comm) RB2_FATAL("rb2_sharded_quiesce: engine was not created with rb2_create_sharded");
+	RB2_CUDA(cudaSetDevice(e->dev));
+	shard_unmap_peers(e);
+}
+
 // One batch: every rank passes ITS strings (device resident, NUL-terminated, reversed; len may be 0).
 // Collective: all ranks of the communicator must call it.
 static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
@@ -170,6 +188,13 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	const int P = cm->n, me = cm->rank;
 	const int sorted = e->so != RB2_SO_IO;
 	Ctl *h = e->hctl;
+	// RB2_TRACE=1: host wall-clock of the batch's stages on stderr (developer aid)
+	static const bool trace = getenv("RB2_TRACE") && atoi(getenv("RB2_TRACE"));
+	double tr[8]; int ntr = 0;
+	auto mark = [&]() { if (trace && ntr < 8) { RB2_CUDA(cudaStreamSynchronize(e->st)); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); tr[ntr++] = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; } };
+	mark();
+	double trCtl = 0, trGather = 0; // host time blocked in the column loop: waiting for the column's counts / in the table all-gather
+	auto now_ms = [&]() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
 
 	// ---- my strings: split, lengths ----------------------------------------------------------
 	ph_begin(e, PH_TRANSPOSE);
@@ -231,34 +256,41 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (flat) flat_begin(e, addLocal);
 	else { ensure_blocks(e); blocks_edited(e); } // a sparse batch edits the leaf blocks
 	if (!flat) reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
+	mark();
 	// ---- direct delivery of the interval starts (dense regime): every rank maps every rank's two state buffers ----
-	// The buffers are sized for the worst case once (no rank ever holds more than every string of the batch), so
-	// the mappings stay valid for the whole batch.
-	int64_t *peerGL[2][RB2_MAX_RANKS];
+	// The buffers are sized for the worst case (no rank ever holds more than every string of the batch), so the
+	// mappings stay valid for the whole batch -- and for the batches after it, as long as no rank needs larger
+	// buffers (mapping costs 30-90 ms, measured): the ranks vote, and re-map together when one of them must grow.
 	bool direct = false;
 	if (P > 1) {
-		static int want = -1;
-		if (want < 0) { const char *ws = getenv("RB2_P2P"); want = ws && *ws ? atoi(ws) : 1; }
+		const char *ws = getenv("RB2_P2P");
+		const int want = ws && *ws ? atoi(ws) : 1;
 		const size_t capG = (size_t)mAll + 64;
+		const bool fits = e->gLrx[0].cap >= capG && e->gLrx[1].cap >= capG;
 		size_t freeB = 0, totB = 0;
 		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
 		const size_t extra = (e->gLrx[0].cap < capG ? capG * 9 : 0) + (e->gLrx[1].cap < capG ? capG * 9 : 0);
-		uint32_t okMine = want && flat && extra + ((size_t)2 << 30) < freeB, oks[RB2_MAX_RANKS];
-		cm->allgather_host(&okMine, 4, oks, e->st);
+		uint32_t mine = (want && flat && extra + ((size_t)2 << 30) < freeB ? 1u : 0u) | (e->p2pMapped && fits ? 2u : 0u), got[RB2_MAX_RANKS];
+		cm->allgather_host(&mine, 4, got, e->st);
+		bool keep = true;
 		direct = true;
-		for (int r = 0; r < P; ++r) direct = direct && oks[r] != 0;
-		if (direct) {
+		for (int r = 0; r < P; ++r) { direct = direct && (got[r] & 1u); keep = keep && (got[r] & 2u); }
+		if (!direct || !keep) shard_unmap_peers(e); // (a send/recv batch grows these buffers on demand: they must not stay mapped)
+		if (direct && !e->p2pMapped) {
 			e->gLrx[0].need(capG); e->gLrx[1].need(capG);
 			if (!e->dRoute) RB2_CUDA(cudaMalloc(&e->dRoute, sizeof(PeerRoute)));
-			if (!cm->p2p_map(e->gLrx[0].p, (void**)peerGL[0], e->st)) direct = false;
-			else if (!cm->p2p_map(e->gLrx[1].p, (void**)peerGL[1], e->st)) { cm->p2p_unmap((void**)peerGL[0]); direct = false; }
+			if (!cm->p2p_map(e->gLrx[0].p, (void**)e->peerGL[0], e->st)) direct = false;
+			else if (!cm->p2p_map(e->gLrx[1].p, (void**)e->peerGL[1], e->st)) { cm->p2p_unmap((void**)e->peerGL[0]); direct = false; }
+			e->p2pMapped = direct;
 		}
 	}
+	int64_t *(*const peerGL)[RB2_MAX_RANKS] = e->peerGL;
 	uint32_t G = 0, M = 0;
 	uint32_t gBkt[NBA], mBkt[NBA];
 	uint64_t mglob[NBMAX];
 	memset(mglob, 0, sizeof(mglob)); mglob[0] = mAll;
 	uint64_t Gglob = sorted ? 1 : mAll, Mglob = mAll;
+	mark();
 	const int cs = 0; // current state lives in buffer 0; buffer 1 receives a column's output in source order
 	int gcur = 0;     // (the interval starts alternate between gLrx[0] and gLrx[1]: peers may write the next while I read the current)
 	if (e->owner[0] == me) {
@@ -359,7 +391,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[1].p);
 				ph_end(e, PH_MEMBERS2);
 			}
-			ctl_pull(e);
+			{ const double t0 = trace ? now_ms() : 0; ctl_pull(e); if (trace) trCtl += now_ms() - t0; }
 			ph_collect(e, (1u << PH_MEMBERS) | (1u << PH_GROUPS) | (1u << PH_MEMBERS2) | e->flat.pending);
 			e->flat.pending = 0;
 			nrec = h->nrec;
@@ -370,7 +402,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		ShardTab mineT;
 		memcpy(mineT.mem, h->memPre, sizeof(mineT.mem));
 		memcpy(mineT.grp, (M > 0 && G == M) ? h->memPre : h->grpPre, sizeof(mineT.grp));
-		cm->allgather_host(&mineT, sizeof(ShardTab), tabs.data(), e->st);
+		{ const double t0 = trace ? now_ms() : 0; cm->allgather_host(&mineT, sizeof(ShardTab), tabs.data(), e->st); if (trace) trGather += now_ms() - t0; }
 		// post-column totals; symbol bases of every rank's output arrays
 		uint32_t gSym[RB2_MAX_RANKS][8], mSym[RB2_MAX_RANKS][8];
 		for (int r = 0; r < P; ++r) {
@@ -508,11 +540,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		memcpy(mglob, mglobNext, sizeof(mglob));
 		Gglob = GglobN; Mglob = MglobN;
 	}
-	if (direct) { // (every rank left the loop behind the same column, the barrier of the one before is behind all of them)
-		cm->barrier(e->st);
-		cm->p2p_unmap((void**)peerGL[0]); cm->p2p_unmap((void**)peerGL[1]);
-		++e->stats.p2p_batches;
-	}
+	mark();
+	if (direct) ++e->stats.p2p_batches; // (the peer mappings stay for the next batch)
 	if (flat) {
 		RB2_CUDA(cudaStreamSynchronize(e->st));
 		ph_collect(e, e->flat.pending); e->flat.pending = 0;
@@ -520,6 +549,10 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		++e->stats.flat_batches;
 	}
 	shard_publish_totals(e);
+	mark();
+	if (trace) fprintf(stderr, "[rb2 trace] rank %d: split+replicate+regime %.1f ms, peer mappings %.1f ms, columns %.1f ms, unmap+finish %.1f ms (direct=%d); "
+	                   "in the column loop the host waited %.1f ms for the columns' counts and %.1f ms in the table all-gathers\n",
+	                   me, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], (int)direct, trCtl, trGather);
 	e->stats.n_strings += m;
 	e->stats.n_symbols += len;
 	e->stats.pool_blocks = e->hctl->poolUsed;

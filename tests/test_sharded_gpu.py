@@ -12,6 +12,7 @@ from oracle import oracle as orc
 from ropebwt2_b200 import load
 from ropebwt2_b200.binding import ShardedEngine, local_group
 from ropebwt2_b200.synth import encode_batch, genome_reads, uniform_reads, varlen_reads
+from conftest import sz
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
@@ -127,4 +128,26 @@ def test_medium_rlo_matches_single_gpu_engine():
     c = Cluster(1, 4)
     c.insert([encode_batch(p) for p in split(rd, 4)])
     assert np.array_equal(c.text(), want)
+    c.close()
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_direct_delivery_across_batches(so, monkeypatch):
+    """Dense batches: the merge kernels store the new interval starts straight into the owner ranks' buffers
+    (csrc/rb2_comm.h p2p_map).  The mappings are kept from batch to batch and re-made when a rank must grow
+    (second batch larger), dropped for a send/recv batch (RB2_P2P=0) and made again afterwards."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    o = orc.Oracle(so)
+    c = Cluster(so, 3)
+    sizes = [sz(3000, 600), sz(9000, 1500), sz(2000, 400), sz(2500, 500), sz(2500, 500)]
+    for k, n in enumerate(sizes):
+        rd = uniform_reads(n, 40, 50 + k, n_frac=0.01) if k != 2 else varlen_reads(n, 60, 52, 5)
+        if k == 3:
+            monkeypatch.setenv("RB2_P2P", "0")
+        o.insert_multi(encode_batch(rd))
+        c.insert([encode_batch(p) for p in split(rd, 3)])
+        monkeypatch.delenv("RB2_P2P", raising=False)
+    st = c.eng[0].stats()
+    assert st["flat_batches"] == len(sizes) and st["p2p_batches"] == len(sizes) - 1
+    assert np.array_equal(c.text(), o.text())
     c.close()

@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_sharded_nccl.py tests/test_cluster_gpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 900 python -m pytest tests/test_sharded_gpu.py -m gpu -x -q 2>&1 | tail -5
+RB2_TRACE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/r2_n2_cached.json 2> gpurun_out/r2_n2_cached.err; echo "rc=$?"
+grep "rb2 trace" gpurun_out/r2_n2_cached.err | grep "rank 0" | tail -4
+cut -c1-400 gpurun_out/r2_n2_cached.json

@@ -47,6 +47,7 @@ def main():
                   f"exchange {st['ms_exchange']:.1f} ms of {st['ms_total']:.1f} ms, {st['exch_bytes']} bytes received, "
                   f"dense batches {st['flat_batches']}, {'direct delivery' if st['p2p_batches'] else 'send/recv'} {st['p2p_batches']}", flush=True)
             bad += not ok
+        e.quiesce()
         e.close()
     flag = torch.tensor([bad], device="cuda")
     dist.broadcast(flag, 0)
