@@ -1860,9 +1860,9 @@ enum { PH_H2D, PH_TRANSPOSE, PH_MEMBERS, PH_GROUPS, PH_MERGE, PH_DIR, PH_DIR2, P
 struct FlatState {
 	bool on = false; int cur = 0; uint64_t n = 0; uint32_t pending = 0; // pending: phases whose events wait for the next host sync
 	bool valid = false, blocksStale = false; // the array holds the current index (resident between dense batches) / the leaf blocks do not
-	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt; DevBuf<TileDesc> desc;
+	DevBuf<uint8_t> s[2]; DevBuf<int64_t> dir[2]; DevBuf<uint32_t> tileCnt; DevBuf<TileDesc> desc; DevBuf<uint8_t> sliceBkt;
 	DevBuf<uint8_t> chunkBytes; DevBuf<uint64_t> chunkPre, scanU64, midU64;
-	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); desc.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
+	void release() { for (int k = 0; k < 2; ++k) { s[k].release(); dir[k].release(); } tileCnt.release(); desc.release(); sliceBkt.release(); chunkBytes.release(); chunkPre.release(); scanU64.release(); midU64.release(); }
 };
 
 struct rb2_engine {

@@ -100,7 +100,10 @@ struct RecView {
 // reaches across it from the left.
 struct alignas(16) TileDesc { uint64_t i0; uint32_t r0, carry; }; // carry = (symbols of the crossing run behind the boundary, capped at the slice size) << 3 | symbol
 
-__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, uint32_t slice, TileDesc *desc)
+// sliceBkt (sharded engines, else null): the bucket of the slice's first record -- nearly every slice lies inside one
+// bucket, so the merge looks the bucket up once per slice instead of bisecting the bucket table for every record
+__global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, uint64_t nSlices, uint64_t nNew, uint32_t slice, TileDesc *desc,
+                                                  const Ctl *ctl, int nb, uint8_t *sliceBkt)
 {
 	const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
 	if (t > nSlices) return;
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, u
 	}
 	TileDesc d; d.i0 = o0 - before; d.r0 = r0; d.carry = carry;
 	desc[t] = d;
+	if (sliceBkt) sliceBkt[t] = (uint8_t)bucket_of(ctl->recBkt, (uint32_t)nb, r0 < R ? r0 : (R ? R - 1 : 0));
 }
 
 // Sharded build, direct delivery: entry dst of this rank's column output (the rank of a string after this column)
@@ -125,20 +129,14 @@ __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, u
 // most 5 x 36 pieces (symbol x source sub-bucket), each contiguous on both sides; base[k] is the address in THIS
 // rank's address space (a peer mapping over NVLink, rb2_comm.h p2p_map) of where entry 0 WOULD go if piece k
 // started there, so that the store is base[k][dst].
+// A record's piece follows from its symbol a and its (source) sub-bucket b: pieceOf[a*36+b].
 #define ROUTE_MAXPC 192
-struct PeerRoute { uint32_t np, pad; uint32_t so[ROUTE_MAXPC]; int64_t *base[ROUTE_MAXPC]; };
-
-__device__ __forceinline__ void route_store(const PeerRoute *rt, uint32_t dst, int64_t g)
-{
-	int lo = 0, hi = (int)rt->np - 1; // last piece that starts at or in front of dst
-	while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(rt->so + mid) <= dst) lo = mid; else hi = mid - 1; }
-	rt->base[lo][dst] = g;
-}
+struct PeerRoute { int64_t *base[ROUTE_MAXPC]; uint8_t pieceOf[6 * 36]; };
 
 __global__ void k_route_store(PeerRoute *dst, const PeerRoute v)
 {
-	if (threadIdx.x == 0) { dst->np = v.np; dst->pad = 0; }
-	for (uint32_t k = threadIdx.x; k < ROUTE_MAXPC; k += blockDim.x) { dst->so[k] = v.so[k]; dst->base[k] = v.base[k]; }
+	for (uint32_t k = threadIdx.x; k < ROUTE_MAXPC; k += blockDim.x) dst->base[k] = v.base[k];
+	for (uint32_t k = threadIdx.x; k < 6 * 36; k += blockDim.x) dst->pieceOf[k] = v.pieceOf[k];
 }
 
 struct FlatArgs {
@@ -151,6 +149,7 @@ struct FlatArgs {
 	// symbols (recOff[b*7+a] symbols a) further right in the whole index than in the local array
 	const int64_t *recOff; int nb;
 	const PeerRoute *route; // sharded, direct delivery: where gLNext[dst] really lives (null: gLNext is a local array)
+	const uint8_t *sliceBkt; // sharded: bucket of every slice's first record (k_flat_geo)
 };
 
 // ---- the merge: one warp per slice, no block-wide synchronisation ---------------------------------------------

@@ -134,10 +134,11 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	ph_begin(e, PH_MERGE);
 	// leanP: all-singleton column -- the records are the state arrays themselves (position = leanP[r], symbol = asym[r], count 1, r symbols in front)
 	const RecView V = leanP ? RecView{ leanP, 0, 0, asym ? asym : e->asym.p } : RecView{ e->recP.p, e->recPre.p, e->recSC.p, 0 };
-	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, slice, f.desc.p);
+	if (e->comm) f.sliceBkt.need(nNew / fs2::kSlice + 4);
+	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, slice, f.desc.p, e->dctl, e->nb, e->comm ? f.sliceBkt.p : (uint8_t*)0);
 	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
-	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb, route };
+	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb, route, e->comm ? f.sliceBkt.p : (const uint8_t*)0 };
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * (wide ? fs4::kMinCta : fs2::kMinCta));
 	if (wide) {
 		if (V.sc) LAUNCH(e, (fs4::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);

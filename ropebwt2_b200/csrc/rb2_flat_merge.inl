@@ -47,7 +47,19 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	const uint32_t skip = (uint32_t)(d0.i0 - a0);      // old symbols of the window in front of the slice's first one
 	// lane a < 6: start of bucket a behind this column + #a in front of the directory boundary (fetched now, used by the
 	// rank epilogue: the load's latency hides under the merge)
-	const int64_t baseLane = lane < 6 ? cpostLane + A.oldDir[(a0 / FT_DIR) * 6 + lane] : 0;
+	int64_t baseLane = lane < 6 ? cpostLane + A.oldDir[(a0 / FT_DIR) * 6 + lane] : 0;
+	// sharded engines: the bucket of the slice's records gives the shift into whole-index coordinates and (direct delivery)
+	// the peer array each symbol's ranks go to; one bucket for the whole slice except where a bucket boundary crosses it
+	bool oneBkt = true;
+	int64_t *routeLane = 0;
+	if (A.recOff) {
+		const uint32_t b0 = A.sliceBkt[slice];
+		oneBkt = r0 + nr <= A.ctl->recBkt[b0 + 1];
+		if (lane < 6) {
+			if (oneBkt) baseLane += A.recOff[b0 * 7 + lane];
+			if (A.route) routeLane = A.route->base[A.route->pieceOf[lane * 36 + b0]];
+		}
+	}
 	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells l*FS_PCL .. +FS_PCL-1) -----------
 #pragma unroll
 	for (int j = 0; j < FS_CPL; ++j) reinterpret_cast<uint4*>(&W.mask[0][0])[lane + 32 * j] = make_uint4(0, 0, 0, 0);
@@ -146,16 +158,19 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			const uint32_t dst = !valid ? NONE32 : (reg ? pf.dst : in.dst[k]);
 			const uint32_t a = !valid ? 0u : (reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]));
 			const int64_t base = __shfl_sync(FULLMASK, baseLane, (int)a);
+			int64_t *rp = A.route ? (int64_t*)__shfl_sync(FULLMASK, (long long)routeLane, (int)a) : A.gLNext;
 			if (dst == NONE32) continue;
 			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
 			const uint32_t c = xo / FT_CH;
 			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
 			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
 			int64_t g = base + raw_symbol(rr, a) + part;
-			if (A.recOff) // sharded: which of my buckets the record belongs to -> whole-index coordinates
-				g += A.recOff[bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k) * 7 + a];
-			if (A.route) route_store(A.route, dst, g); // straight into the next owner's state array (a peer store)
-			else A.gLNext[dst] = g;
+			if (!oneBkt) { // (a bucket boundary inside the slice: look the record's own bucket up)
+				const uint32_t b = (uint32_t)bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k);
+				g += A.recOff[b * 7 + a];
+				if (A.route) rp = A.route->base[A.route->pieceOf[a * 36 + b]];
+			}
+			rp[dst] = g; // (direct delivery: straight into the next owner's state array, a peer store over NVLink)
 		}
 	}
 	__syncwarp(); // the inputs and W.mask / W.pre may be reused

@@ -425,7 +425,9 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		uint64_t curG[RB2_MAX_RANKS], curM[RB2_MAX_RANKS], mglobNext[NBMAX];
 		uint32_t gBktN[NBA], mBktN[NBA];
 		memset(curG, 0, sizeof(curG)); memset(curM, 0, sizeof(curM)); memset(mglobNext, 0, sizeof(mglobNext));
-		int nMyPieces = 0;
+		int nMyPieces = 0, nMyOut = 0;
+		uint8_t pieceOfMine[6 * NBMAX]; // (symbol, source sub-bucket of mine) -> index among the pieces I send
+		memset(pieceOfMine, 0, sizeof(pieceOfMine));
 		uint32_t *hPlan = e->hPlan + (col & 1) * 2 * (NBMAX * 6 + 8); // the copy of the previous column may still be queued
 		for (int t = 0; t < NBMAX; ++t) {
 			const int a = t / 6, x = t % 6, dst = e->owner[t];
@@ -445,12 +447,14 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 					pcG.back().n += ng; pcM.back().n += nm;
 				} else {
 					pcG.push_back(pg); pcM.push_back(pm);
+					if (src == me) ++nMyOut;
 					if (dst == me) { // rebase table of the member ranges I receive
 						hPlan[nMyPieces] = (uint32_t)pg.dof;
 						hPlan[NBMAX * 6 + 8 + nMyPieces] = (uint32_t)pm.dof - (uint32_t)pm.so;
 						++nMyPieces;
 					}
 				}
+				if (src == me) pieceOfMine[a * NBMAX + sb] = (uint8_t)(nMyOut - 1);
 				curG[dst] += ng; curM[dst] += nm; mglobNext[t] += nm;
 			}
 		}
@@ -464,26 +468,30 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		// stream while the merge runs; the interval starts (ranks) follow behind the merge.
 		const uint32_t Gn = (uint32_t)curG[me], Mn = (uint32_t)curM[me];
 		const bool singles = GglobN == MglobN;
+		// (RB2_EXCH_SERIAL=1, an experiment switch: on the main stream in front of the merge instead of beside it)
+		static const bool exchSerial = getenv("RB2_EXCH_SERIAL") && atoi(getenv("RB2_EXCH_SERIAL"));
 		auto exchange_early = [&]() {
+			cudaStream_t xs = exchSerial ? e->st : e->st2;
 			e->gSize[cs].need(useSizes ? (size_t)Gn + 64 : 0); e->gOff[cs].need((size_t)Gn + 64); e->sid[cs].need((size_t)Mn + 64);
 			cm->group_begin();
-			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), e->st2);
-			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), e->st2);
-			cm->exchange(e->sid[1].p, e->sid[cs].p, 4, pcM.data(), (int)pcM.size(), e->st2);
-			cm->group_end(e->st2);
-			RB2_CUDA(cudaEventRecord(e->evEarly, e->st2));
+			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), xs);
+			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), xs);
+			cm->exchange(e->sid[1].p, e->sid[cs].p, 4, pcM.data(), (int)pcM.size(), xs);
+			cm->group_end(xs);
+			RB2_CUDA(cudaEventRecord(e->evEarly, xs));
 		};
 		// direct delivery: the pieces of MY output order and where each lands (the next column's buffer of its target rank)
 		const bool deliver = direct && MglobN > 0;
 		if (deliver && nrec > 0) {
 			PeerRoute rt; memset(&rt, 0, sizeof(rt));
-			for (size_t k = 0; k < pcG.size(); ++k) if (pcG[k].src == me && pcG[k].n) {
-				if (rt.np >= ROUTE_MAXPC) RB2_FATAL("internal: more than %d output pieces", ROUTE_MAXPC);
-				rt.so[rt.np] = (uint32_t)pcG[k].so;
-				rt.base[rt.np] = peerGL[gcur ^ 1][pcG[k].dst] + (int64_t)pcG[k].dof - (int64_t)pcG[k].so;
-				++rt.np;
+			int np = 0;
+			for (size_t k = 0; k < pcG.size(); ++k) if (pcG[k].src == me) {
+				if (np >= ROUTE_MAXPC) RB2_FATAL("internal: more than %d output pieces", ROUTE_MAXPC);
+				rt.base[np++] = peerGL[gcur ^ 1][pcG[k].dst] + (int64_t)pcG[k].dof - (int64_t)pcG[k].so;
 			}
+			if (np != nMyOut) RB2_FATAL("internal: output pieces miscounted");
 			// (no piece at all: every record of mine ends its string -- none has a target)
+			memcpy(rt.pieceOf, pieceOfMine, sizeof(rt.pieceOf));
 			LAUNCH(e, k_route_store, 1, 128, 0, e->dRoute, rt);
 		}
 		auto merge = [&]() {
@@ -495,9 +503,9 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		};
 		// the dense merge is fully asynchronous, so it is queued first; the block merge synchronises with the host
 		wait_late(); // (ranks without members get here with the previous column's transfer possibly still in flight)
-		if (MglobN > 0 && !flat) exchange_early();
+		if (MglobN > 0 && (!flat || exchSerial)) exchange_early();
 		merge();
-		if (MglobN > 0 && flat) exchange_early();
+		if (MglobN > 0 && flat && !exchSerial) exchange_early();
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
 		if (MglobN > 0) {
