@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 	if (k < A.M) {
 		a4 = *reinterpret_cast<const uint32_t*>(A.asym + k);
 		for (int i = 0; i < 4; ++i) if (k + i < A.M) {
-			id[i] = A.sid[k + i];
+			if (A.sidNext) id[i] = A.sid[k + i];
 			const uint32_t a = (a4 >> (8 * i)) & 0xff;
 #pragma unroll
 			for (int x = 0; x < 6; ++x) c[x] += a == x;
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(256) k_column_singletons(SingleArgs A)
 			}
 		}
 		if (a) {
-			A.sidNext[d] = id[i];
+			if (A.sidNext) A.sidNext[d] = id[i]; // (null: the merge kernel delivers the ids, rb2_flat.cuh PeerRoute)
 			if (!A.lean) A.gOffNext[d] = d;
 			if (A.sizes6) A.gSizeNext[d] = sza;
 		}
@@ -1881,9 +1881,9 @@ struct rb2_engine {
 	int64_t *dDirOffPre, *hDirOffPre; // the same in front of the column (dense regime: record positions are pre-column)
 	uint32_t *hPlan; DevBuf<uint32_t> plan;
 	cudaStream_t st2; cudaEvent_t evEarly, evMerge; // second stream: the part of the exchange that overlaps the merge
-	DevBuf<int64_t> gLrx[2]; // sharded: interval starts of the current / the next column (alternating)
+	DevBuf<int64_t> gLrx[2]; DevBuf<uint32_t> sidrx[2]; // sharded: interval starts / string ids of the current and the next column (alternating)
 	PeerRoute *dRoute;       // direct delivery: the merge epilogue's routing table of the column
-	int64_t *peerGL[2][RB2_MAX_RANKS]; bool p2pMapped; // every rank's gLrx[k] in my address space (kept across batches)
+	int64_t *peerGL[2][RB2_MAX_RANKS]; uint32_t *peerSid[2][RB2_MAX_RANKS]; bool p2pMapped; // every rank's gLrx[k] / sidrx[k] in my address space (kept across batches)
 	// RB2_GPUS > 1 (rb2_cluster.inl): this engine is a proxy in front of nChild sharded engines
 	int nChild; rb2_engine *child[RB2_MAX_RANKS]; rb2_group *grp;
 	FlatState flat; DevBuf<uint32_t> recPre;
@@ -2091,7 +2091,7 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	memset(&e->stats, 0, sizeof(e->stats));
 	e->dev = device; e->so = sorting_order;
 	e->nChild = 0; e->grp = 0;
-	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0; e->dRoute = 0; e->p2pMapped = false; memset(e->peerGL, 0, sizeof(e->peerGL));
+	e->rank = 0; e->nranks = 1; e->comm = 0; e->dDirOff = 0; e->hDirOff = 0; e->dDirOffPre = 0; e->hDirOffPre = 0; e->hPlan = 0; e->dRoute = 0; e->p2pMapped = false; memset(e->peerGL, 0, sizeof(e->peerGL)); memset(e->peerSid, 0, sizeof(e->peerSid));
 	RB2_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
 	RB2_CUDA(cudaMalloc(&e->dctl, sizeof(Ctl)));
 	RB2_CUDA(cudaMallocHost(&e->hctl, sizeof(Ctl)));
@@ -2182,9 +2182,10 @@ extern "C" void rb2_destroy(rb2_engine_t *e)
 	RB2_CUDA(cudaFree(e->dRankOut)); RB2_CUDA(cudaFreeHost(e->hRankOut));
 	RB2_CUDA(cudaFree(e->dMaxLen));
 	if (e->comm && e->p2pMapped) { // not collective: close what I imported; my own buffers are freed below (rb2_sharded_quiesce is the collective, ordered way)
-		e->comm->p2p_unmap((void**)e->peerGL[0]); e->comm->p2p_unmap((void**)e->peerGL[1]); e->p2pMapped = false;
+		for (int k = 0; k < 2; ++k) { e->comm->p2p_unmap((void**)e->peerGL[k]); e->comm->p2p_unmap((void**)e->peerSid[k]); }
+		e->p2pMapped = false;
 	}
-	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); e->gLrx[0].release(); e->gLrx[1].release(); if (e->dRoute) RB2_CUDA(cudaFree(e->dRoute)); }
+	if (e->comm) { delete e->comm; cudaStreamDestroy(e->st2); cudaEventDestroy(e->evEarly); cudaEventDestroy(e->evMerge); RB2_CUDA(cudaFree(e->dDirOff)); RB2_CUDA(cudaFreeHost(e->hDirOff)); RB2_CUDA(cudaFree(e->dDirOffPre)); RB2_CUDA(cudaFreeHost(e->hDirOffPre)); RB2_CUDA(cudaFreeHost(e->hPlan)); e->plan.release(); e->gLrx[0].release(); e->gLrx[1].release(); e->sidrx[0].release(); e->sidrx[1].release(); if (e->dRoute) RB2_CUDA(cudaFree(e->dRoute)); }
 	e->flat.release(); e->recPre.release();
 	for (int p = 0; p < PH_N; ++p) for (int k = 0; k < 2; ++k) cudaEventDestroy(e->ev[p][k]);
 	for (int k = 0; k < 2; ++k) cudaEventDestroy(e->evTot[k]);

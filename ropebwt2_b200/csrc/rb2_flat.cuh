@@ -131,11 +131,13 @@ __global__ void __launch_bounds__(256) k_flat_geo(const RecView V, uint32_t R, u
 // started there, so that the store is base[k][dst].
 // A record's piece follows from its symbol a and its (source) sub-bucket b: pieceOf[a*36+b].
 #define ROUTE_MAXPC 192
-struct PeerRoute { int64_t *base[ROUTE_MAXPC]; uint8_t pieceOf[6 * 36]; };
+// In an all-singleton column the string ids travel the same way (base32: the owner's id array), so such a column
+// needs no send/recv at all.
+struct PeerRoute { int64_t *base[ROUTE_MAXPC]; uint32_t *base32[ROUTE_MAXPC]; uint8_t pieceOf[6 * 36]; };
 
 __global__ void k_route_store(PeerRoute *dst, const PeerRoute v)
 {
-	for (uint32_t k = threadIdx.x; k < ROUTE_MAXPC; k += blockDim.x) dst->base[k] = v.base[k];
+	for (uint32_t k = threadIdx.x; k < ROUTE_MAXPC; k += blockDim.x) { dst->base[k] = v.base[k]; dst->base32[k] = v.base32[k]; }
 	for (uint32_t k = threadIdx.x; k < 6 * 36; k += blockDim.x) dst->pieceOf[k] = v.pieceOf[k];
 }
 
@@ -150,6 +152,7 @@ struct FlatArgs {
 	const int64_t *recOff; int nb;
 	const PeerRoute *route; // sharded, direct delivery: where gLNext[dst] really lives (null: gLNext is a local array)
 	const uint8_t *sliceBkt; // sharded: bucket of every slice's first record (k_flat_geo)
+	const uint32_t *sidCur;  // direct delivery, all-singleton column: string id of record r, delivered through route->base32
 };
 
 // ---- the merge: one warp per slice, no block-wide synchronisation ---------------------------------------------
@@ -175,7 +178,7 @@ struct SliceIn {
 };
 
 // record k = lane of a slice, fetched one slice ahead (the loads' latency hides under the previous slice's merge)
-struct RecRegs { int64_t P; uint32_t pre, sc, dst; bool have; };
+struct RecRegs { int64_t P; uint32_t pre, sc, dst, sid; bool have; };
 
 // one output cell: 32 old symbols from local index oldIdx on, a gap pushed in at every bit of m, the new planes on top
 __device__ __forceinline__ Cell slice_cell(const uint32_t *old, uint32_t oldIdx, const uint32_t (&mk)[4])

@@ -117,7 +117,7 @@ static void flat_begin(rb2_engine *e, uint64_t addLocal)
 
 // one column: merge nrec records (inserting `inserted` symbols) into the flat array
 static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, int64_t *gLNext, const int64_t *leanP = 0, const uint8_t *asym = 0,
-                               const PeerRoute *route = 0)
+                               const PeerRoute *route = 0, const uint32_t *sidCur = 0)
 {
 	FlatState &f = e->flat;
 	const uint64_t nNew = f.n + inserted;
@@ -138,7 +138,7 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	LAUNCH(e, k_flat_geo, cdiv(nTiles + 1, 256), 256, 0, V, nrec, nTiles, nNew, slice, f.desc.p, e->dctl, e->nb, e->comm ? f.sliceBkt.p : (uint8_t*)0);
 	if (nTiles >= 0xfffffff0ull) RB2_FATAL("flat array of %llu symbols: more than 2^32 slices", (unsigned long long)nNew);
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
-	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb, route, e->comm ? f.sliceBkt.p : (const uint8_t*)0 };
+	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb, route, e->comm ? f.sliceBkt.p : (const uint8_t*)0, sidCur };
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * (wide ? fs4::kMinCta : fs2::kMinCta));
 	if (wide) {
 		if (V.sc) LAUNCH(e, (fs4::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);
@@ -206,7 +206,7 @@ static void release_batch_scratch(rb2_engine *e)
 	RB2_CUDA(cudaStreamSynchronize(e->st));
 	e->sbuf.release(); e->T.release(); e->asym.release(); e->sizes6.release(); e->recP.release(); e->recSC.release(); e->recDst.release(); e->recPre.release();
 	for (int k = 0; k < 2; ++k) { e->gL[k].release(); e->gSize[k].release(); e->gOff[k].release(); e->sid[k].release(); }
-	if (e->comm && !e->p2pMapped) { e->gLrx[0].release(); e->gLrx[1].release(); } // (not while peers map them)
+	if (e->comm && !e->p2pMapped) { e->gLrx[0].release(); e->gLrx[1].release(); e->sidrx[0].release(); e->sidrx[1].release(); } // (not while peers map them)
 	e->strEnd.release(); e->tileA.release(); e->tileB.release(); e->grpCta.release();
 	FlatState &f = e->flat;
 	f.s[f.cur ^ 1].release(); f.dir[f.cur ^ 1].release(); f.desc.release();

@@ -51,13 +51,17 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	// sharded engines: the bucket of the slice's records gives the shift into whole-index coordinates and (direct delivery)
 	// the peer array each symbol's ranks go to; one bucket for the whole slice except where a bucket boundary crosses it
 	bool oneBkt = true;
-	int64_t *routeLane = 0;
+	int64_t *routeLane = 0; uint32_t *route32Lane = 0;
 	if (A.recOff) {
 		const uint32_t b0 = A.sliceBkt[slice];
 		oneBkt = r0 + nr <= A.ctl->recBkt[b0 + 1];
 		if (lane < 6) {
 			if (oneBkt) baseLane += A.recOff[b0 * 7 + lane];
-			if (A.route) routeLane = A.route->base[A.route->pieceOf[lane * 36 + b0]];
+			if (A.route) {
+				const uint32_t pc = A.route->pieceOf[lane * 36 + b0];
+				routeLane = A.route->base[pc];
+				if (!GENERAL && A.sidCur) route32Lane = A.route->base32[pc];
+			}
 		}
 	}
 	// ---- (1) masks := 0; raw prefix counts of the old cells (lane l: cells l*FS_PCL .. +FS_PCL-1) -----------
@@ -159,6 +163,8 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			const uint32_t a = !valid ? 0u : (reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]));
 			const int64_t base = __shfl_sync(FULLMASK, baseLane, (int)a);
 			int64_t *rp = A.route ? (int64_t*)__shfl_sync(FULLMASK, (long long)routeLane, (int)a) : A.gLNext;
+			const bool ids = !GENERAL && A.sidCur != 0; // (uniform)
+			uint32_t *rp32 = ids ? (uint32_t*)__shfl_sync(FULLMASK, (long long)route32Lane, (int)a) : (uint32_t*)0;
 			if (dst == NONE32) continue;
 			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
 			const uint32_t c = xo / FT_CH;
@@ -168,8 +174,9 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			if (!oneBkt) { // (a bucket boundary inside the slice: look the record's own bucket up)
 				const uint32_t b = (uint32_t)bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k);
 				g += A.recOff[b * 7 + a];
-				if (A.route) rp = A.route->base[A.route->pieceOf[a * 36 + b]];
+				if (A.route) { const uint32_t pc = A.route->pieceOf[a * 36 + b]; rp = A.route->base[pc]; if (ids) rp32 = A.route->base32[pc]; }
 			}
+			if (ids) rp32[dst] = reg ? pf.sid : A.sidCur[r0 + k]; // the string itself moves to the owner of its next sub-bucket
 			rp[dst] = g; // (direct delivery: straight into the next owner's state array, a peer store over NVLink)
 		}
 	}
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 		issue(s, sl, ok ? A.desc[sl] : none, ok ? A.desc[sl + 1] : none);
 	}
 	__syncwarp();
-	RecRegs pf = { 0, 0, 0, 0, false }, pfNext = { 0, 0, 0, 0, false };
+	RecRegs pf = { 0, 0, 0, 0, 0, false }, pfNext = { 0, 0, 0, 0, 0, false };
 	const int64_t cpostLane = lane < 8 ? A.ctl->cpost[lane] : 0; // start of bucket `lane` behind this column
 	for (uint32_t n = 0; ; ++n) {
 		const uint32_t s = n % FS_STAGES, ph = (n / FS_STAGES) & 1u;
@@ -225,6 +232,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 					pfNext.P = A.V.P[r]; pfNext.dst = A.recDst[r];
 					pfNext.pre = GENERAL ? A.V.pre[r] : r;
 					pfNext.sc = GENERAL ? A.V.sc[r] : (uint32_t)A.V.asym[r];
+					if (!GENERAL && A.sidCur) pfNext.sid = A.sidCur[r];
 				}
 			}
 		}

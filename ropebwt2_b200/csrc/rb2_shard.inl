@@ -168,7 +168,7 @@ static void shard_unmap_peers(rb2_engine *e)
 {
 	if (!e->p2pMapped) return;
 	RB2_CUDA(cudaStreamSynchronize(e->st));
-	e->comm->p2p_unmap((void**)e->peerGL[0]); e->comm->p2p_unmap((void**)e->peerGL[1]);
+	for (int k = 0; k < 2; ++k) { e->comm->p2p_unmap((void**)e->peerGL[k]); e->comm->p2p_unmap((void**)e->peerSid[k]); }
 	e->comm->barrier(e->st);
 	e->p2pMapped = false;
 }
@@ -266,10 +266,11 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		const char *ws = getenv("RB2_P2P");
 		const int want = ws && *ws ? atoi(ws) : 1;
 		const size_t capG = (size_t)mAll + 64;
-		const bool fits = e->gLrx[0].cap >= capG && e->gLrx[1].cap >= capG;
+		const bool fits = e->gLrx[0].cap >= capG && e->gLrx[1].cap >= capG && e->sidrx[0].cap >= capG && e->sidrx[1].cap >= capG;
 		size_t freeB = 0, totB = 0;
 		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-		const size_t extra = (e->gLrx[0].cap < capG ? capG * 9 : 0) + (e->gLrx[1].cap < capG ? capG * 9 : 0);
+		const size_t extra = (e->gLrx[0].cap < capG ? capG * 9 : 0) + (e->gLrx[1].cap < capG ? capG * 9 : 0) +
+		                     (e->sidrx[0].cap < capG ? capG * 5 : 0) + (e->sidrx[1].cap < capG ? capG * 5 : 0);
 		uint32_t mine = (want && flat && extra + ((size_t)2 << 30) < freeB ? 1u : 0u) | (e->p2pMapped && fits ? 2u : 0u), got[RB2_MAX_RANKS];
 		cm->allgather_host(&mine, 4, got, e->st);
 		bool keep = true;
@@ -277,10 +278,12 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		for (int r = 0; r < P; ++r) { direct = direct && (got[r] & 1u); keep = keep && (got[r] & 2u); }
 		if (!direct || !keep) shard_unmap_peers(e); // (a send/recv batch grows these buffers on demand: they must not stay mapped)
 		if (direct && !e->p2pMapped) {
-			e->gLrx[0].need(capG); e->gLrx[1].need(capG);
+			e->gLrx[0].need(capG); e->gLrx[1].need(capG); e->sidrx[0].need(capG); e->sidrx[1].need(capG);
 			if (!e->dRoute) RB2_CUDA(cudaMalloc(&e->dRoute, sizeof(PeerRoute)));
-			if (!cm->p2p_map(e->gLrx[0].p, (void**)e->peerGL[0], e->st)) direct = false;
-			else if (!cm->p2p_map(e->gLrx[1].p, (void**)e->peerGL[1], e->st)) { cm->p2p_unmap((void**)e->peerGL[0]); direct = false; }
+			void *mineBuf[4] = { e->gLrx[0].p, e->gLrx[1].p, e->sidrx[0].p, e->sidrx[1].p };
+			void **peerTab[4] = { (void**)e->peerGL[0], (void**)e->peerGL[1], (void**)e->peerSid[0], (void**)e->peerSid[1] };
+			for (int k = 0; k < 4 && direct; ++k)
+				if (!cm->p2p_map(mineBuf[k], peerTab[k], e->st)) { for (int j = 0; j < k; ++j) cm->p2p_unmap(peerTab[j]); direct = false; }
 			e->p2pMapped = direct;
 		}
 	}
@@ -294,8 +297,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	const int cs = 0; // current state lives in buffer 0; buffer 1 receives a column's output in source order
 	int gcur = 0;     // (the interval starts alternate between gLrx[0] and gLrx[1]: peers may write the next while I read the current)
 	if (e->owner[0] == me) {
-		e->gLrx[0].need(Gglob + 64); e->gSize[0].need(Gglob + 64); e->gOff[0].need(Gglob + 64); e->sid[0].need(mAll + 64);
-		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gLrx[0].p, e->gSize[0].p, e->gOff[0].p, e->sid[0].p);
+		e->gLrx[0].need(Gglob + 64); e->gSize[0].need(Gglob + 64); e->gOff[0].need(Gglob + 64); e->sidrx[0].need(mAll + 64);
+		LAUNCH(e, k_init_state, cdiv(mAll, 256), 256, 0, sorted, (uint32_t)mAll, n0, e->gLrx[0].p, e->gSize[0].p, e->gOff[0].p, e->sidrx[0].p);
 		G = (uint32_t)Gglob; M = (uint32_t)mAll;
 	}
 	for (int b = 0; b < NBA; ++b) { gBkt[b] = b == 0 ? 0 : G; mBkt[b] = b == 0 ? 0 : M; }
@@ -309,6 +312,10 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		if ((uint64_t)col >= ncolAll) RB2_FATAL("internal: live strings beyond the last column");
 		Dir &d = e->dir[e->cur];
 		int64_t *const gLc = e->gLrx[gcur].p; // interval starts of this column (null on a rank without groups)
+		uint32_t *const sidc = e->sidrx[gcur].p; // string ids of this column
+		// all-singleton column without interval sizes, on every rank: with direct delivery the merge kernel hands
+		// the ids on as well and the column needs no send/recv at all
+		const bool colSingle = flat && !useSizes && Gglob == Mglob;
 		// ---- per-column capacity (contents of these buffers are dead here) ---------------------
 		// (a group yields at most one next group and one record per symbol, plus records for counts above the run limit)
 		const size_t gnMax = std::min<uint64_t>(M, 6ull * G);
@@ -356,7 +363,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			tv.n = P;
 			for (int r = 0; r <= P; ++r) tv.off[r] = (uint32_t)strOff[r];
 			for (int r = 0; r < P; ++r) tv.col[r] = (uint64_t)col < all[r].ncol ? e->T.p + tOff[r] + (size_t)col * t_stride(all[r].m) : (const uint8_t*)0;
-			LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, e->sid[cs].p, M, e->asym.p, e->tileB.p);
+			LAUNCH(e, k_member_fetch, nTile, 256, 0, tv, sidc, M, e->asym.p, e->tileB.p);
 			run_mid<6, uint32_t>(e, e->tileB.p, (uint64_t)nTile + 1, e->dctl->memTot, e->midTmp);
 			ph_end(e, PH_MEMBERS);
 			// ---- groups ---------------------------------------------------------------------
@@ -369,8 +376,8 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			}
 			if (G == M) {
 				LAUNCH(e, k_col_bases_single, 1, 1, 0, e->dctl, e->gOff[1].p, M, flat ? e->recPre.p : (uint32_t*)0);
-				SingleArgs sa = { e->sid[cs].p, e->asym.p, M, e->tileB.p, gLc, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
-				                  e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
+				SingleArgs sa = { sidc, e->asym.p, M, e->tileB.p, gLc, e->gSize[cs].p, useSizes ? e->sizes6.p : 0, e->dctl,
+				                  direct && colSingle ? (uint32_t*)0 : e->sid[1].p, e->gSize[1].p, e->gOff[1].p, e->recP.p, e->recSC.p, e->recDst.p, flat ? e->recPre.p : (uint32_t*)0, lean ? 1 : 0 };
 				if (e->so == RB2_SO_RCLO) LAUNCH(e, (k_column_singletons<true>), nTile, 256, 0, sa);
 				else LAUNCH(e, (k_column_singletons<false>), nTile, 256, 0, sa);
 				ph_end(e, PH_GROUPS);
@@ -388,7 +395,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 				else LAUNCH(e, (k_group_pass<1, false>), nGC, 256, 0, ga);
 				ph_end(e, PH_GROUPS);
 				ph_begin(e, PH_MEMBERS2);
-				LAUNCH(e, k_partition, nTile, 256, 0, e->sid[cs].p, e->asym.p, M, e->tileB.p, e->dctl, e->sid[1].p);
+				LAUNCH(e, k_partition, nTile, 256, 0, sidc, e->asym.p, M, e->tileB.p, e->dctl, e->sid[1].p);
 				ph_end(e, PH_MEMBERS2);
 			}
 			{ const double t0 = trace ? now_ms() : 0; ctl_pull(e); if (trace) trCtl += now_ms() - t0; }
@@ -472,22 +479,26 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		static const bool exchSerial = getenv("RB2_EXCH_SERIAL") && atoi(getenv("RB2_EXCH_SERIAL"));
 		auto exchange_early = [&]() {
 			cudaStream_t xs = exchSerial ? e->st : e->st2;
-			e->gSize[cs].need(useSizes ? (size_t)Gn + 64 : 0); e->gOff[cs].need((size_t)Gn + 64); e->sid[cs].need((size_t)Mn + 64);
 			cm->group_begin();
 			if (useSizes) cm->exchange(e->gSize[1].p, e->gSize[cs].p, 8, pcG.data(), (int)pcG.size(), xs);
 			if (!singles) cm->exchange(e->gOff[1].p, e->gOff[cs].p, 4, pcG.data(), (int)pcG.size(), xs);
-			cm->exchange(e->sid[1].p, e->sid[cs].p, 4, pcM.data(), (int)pcM.size(), xs);
+			cm->exchange(e->sid[1].p, e->sidrx[gcur ^ 1].p, 4, pcM.data(), (int)pcM.size(), xs);
 			cm->group_end(xs);
 			RB2_CUDA(cudaEventRecord(e->evEarly, xs));
 		};
 		// direct delivery: the pieces of MY output order and where each lands (the next column's buffer of its target rank)
 		const bool deliver = direct && MglobN > 0;
+		const bool deliverIds = deliver && colSingle; // (then nothing is left for exchange_early)
 		if (deliver && nrec > 0) {
 			PeerRoute rt; memset(&rt, 0, sizeof(rt));
 			int np = 0;
 			for (size_t k = 0; k < pcG.size(); ++k) if (pcG[k].src == me) {
 				if (np >= ROUTE_MAXPC) RB2_FATAL("internal: more than %d output pieces", ROUTE_MAXPC);
-				rt.base[np++] = peerGL[gcur ^ 1][pcG[k].dst] + (int64_t)pcG[k].dof - (int64_t)pcG[k].so;
+				rt.base[np] = peerGL[gcur ^ 1][pcG[k].dst] + (int64_t)pcG[k].dof - (int64_t)pcG[k].so;
+				// (all-singleton column: member pieces = group pieces)
+				rt.base32[np] = e->peerSid[gcur ^ 1][pcM[k].dst] + (int64_t)pcM[k].dof - (int64_t)pcM[k].so;
+				if (deliverIds && (pcM[k].so != pcG[k].so || pcM[k].n != pcG[k].n)) RB2_FATAL("internal: group and member pieces of an all-singleton column differ");
+				++np;
 			}
 			if (np != nMyOut) RB2_FATAL("internal: output pieces miscounted");
 			// (no piece at all: every record of mine ends its string -- none has a target)
@@ -496,16 +507,22 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 		}
 		auto merge = [&]() {
 			if (flat) { // (no records: my array does not change)
-				if (nrec > 0) flat_apply_records(e, nrec, M, deliver ? (int64_t*)0 : e->gL[1].p, lean ? gLc : (const int64_t*)0, 0, deliver ? e->dRoute : (const PeerRoute*)0);
+				if (deliverIds && nrec > 0 && !lean) RB2_FATAL("internal: all-singleton column with full records");
+				if (nrec > 0) flat_apply_records(e, nrec, M, deliver ? (int64_t*)0 : e->gL[1].p, lean ? gLc : (const int64_t*)0, 0, deliver ? e->dRoute : (const PeerRoute*)0,
+				                                 deliverIds ? sidc : (const uint32_t*)0);
 			}
 			else if (nrec > 0) apply_records(e, nrec, e->gL[1].p);
 			else rebuild_directory(e, false);
 		};
 		// the dense merge is fully asynchronous, so it is queued first; the block merge synchronises with the host
 		wait_late(); // (ranks without members get here with the previous column's transfer possibly still in flight)
-		if (MglobN > 0 && (!flat || exchSerial)) exchange_early();
+		if (MglobN > 0) { // the next column's arrays (their old contents are dead: this column's kernels are through)
+			e->gSize[cs].need(useSizes ? (size_t)Gn + 64 : 0); e->gOff[cs].need((size_t)Gn + 64);
+			if (!direct) e->sidrx[gcur ^ 1].need((size_t)Mn + 64);
+		}
+		if (MglobN > 0 && (!flat || exchSerial) && !deliverIds) exchange_early();
 		merge();
-		if (MglobN > 0 && flat && !exchSerial) exchange_early();
+		if (MglobN > 0 && flat && !exchSerial && !deliverIds) exchange_early();
 		e->stats.n_records += nrec;
 		++e->stats.n_columns;
 		if (MglobN > 0) {
@@ -528,7 +545,7 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 			}
 			gcur ^= 1;
 			// member ids / ranges arrived on the second stream: finish the member ranges on the main one
-			RB2_CUDA(cudaStreamWaitEvent(e->st, e->evEarly, 0));
+			if (!deliverIds) RB2_CUDA(cudaStreamWaitEvent(e->st, e->evEarly, 0));
 			if (singles) { if (Gn + 1 > 0) LAUNCH(e, k_fill_u32, cdiv((uint64_t)Gn + 1, 256), 256, 0, e->gOff[cs].p, Gn + 1, 0u, 1u); }
 			else if (Gn > 0) {
 				e->plan.need(2 * (NBMAX * 6 + 8));
