@@ -2106,10 +2106,10 @@ static rb2_engine *engine_create(int device, int sorting_order, bool multi)
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * 2 * sizeof(HalfSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(FastSmem))));
 	RB2_CUDA(cudaFuncSetAttribute(k_merge_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MERGE_WARPS * sizeof(GenSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(fs2::k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs2::SliceWarpSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(fs2::k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs2::SliceWarpSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(fs4::k_flat_merge<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs4::SliceWarpSmem))));
-	RB2_CUDA(cudaFuncSetAttribute(fs4::k_flat_merge<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(fs4::SliceWarpSmem))));
+#define RB2_MERGE_SMEM(NS, GEN, SH) RB2_CUDA(cudaFuncSetAttribute(NS::k_flat_merge<GEN, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FS_WARPS * sizeof(NS::SliceWarpSmem))))
+	RB2_MERGE_SMEM(fs2, true, false); RB2_MERGE_SMEM(fs2, false, false); RB2_MERGE_SMEM(fs4, true, false); RB2_MERGE_SMEM(fs4, false, false);
+	RB2_MERGE_SMEM(fs2, true, true); RB2_MERGE_SMEM(fs2, false, true); RB2_MERGE_SMEM(fs4, true, true); RB2_MERGE_SMEM(fs4, false, true);
+#undef RB2_MERGE_SMEM
 	{ cudaDeviceProp pr; RB2_CUDA(cudaGetDeviceProperties(&pr, device)); e->nSM = pr.multiProcessorCount; }
 	// six empty buckets, one empty leaf block each (rope_init, rope.c:55-69)
 	reserve_blocks(e, 4096);

@@ -140,13 +140,15 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	FlatArgs fa = { f.s[f.cur].p, f.dir[f.cur].p, f.s[f.cur ^ 1].p, nNew, f.tileCnt.p, V, e->recDst.p, nrec,
 	                f.desc.p, (uint32_t)nTiles, gLNext, e->dctl, e->comm ? e->dDirOffPre : (const int64_t*)0, e->nb, route, e->comm ? f.sliceBkt.p : (const uint8_t*)0, sidCur };
 	const uint32_t grid = (uint32_t)std::min<uint64_t>(cdiv(nTiles, FS_WARPS), (uint64_t)e->nSM * (wide ? fs4::kMinCta : fs2::kMinCta));
-	if (wide) {
-		if (V.sc) LAUNCH(e, (fs4::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);
-		else LAUNCH(e, (fs4::k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs4::SliceWarpSmem), fa);
+#define RB2_MERGE_LAUNCH(NS, GEN, SH) LAUNCH(e, (NS::k_flat_merge<GEN, SH>), grid, FS_WARPS * 32, FS_WARPS * sizeof(NS::SliceWarpSmem), fa)
+	if (e->comm) { // (a rank of a sharded build: whole-index coordinates, direct delivery)
+		if (wide) { if (V.sc) RB2_MERGE_LAUNCH(fs4, true, true); else RB2_MERGE_LAUNCH(fs4, false, true); }
+		else { if (V.sc) RB2_MERGE_LAUNCH(fs2, true, true); else RB2_MERGE_LAUNCH(fs2, false, true); }
 	} else {
-		if (V.sc) LAUNCH(e, (fs2::k_flat_merge<true>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs2::SliceWarpSmem), fa);
-		else LAUNCH(e, (fs2::k_flat_merge<false>), grid, FS_WARPS * 32, FS_WARPS * sizeof(fs2::SliceWarpSmem), fa);
+		if (wide) { if (V.sc) RB2_MERGE_LAUNCH(fs4, true, false); else RB2_MERGE_LAUNCH(fs4, false, false); }
+		else { if (V.sc) RB2_MERGE_LAUNCH(fs2, true, false); else RB2_MERGE_LAUNCH(fs2, false, false); }
 	}
+#undef RB2_MERGE_LAUNCH
 	ph_end(e, PH_MERGE);
 	ph_begin(e, PH_DIR);
 	flat_scan_dir(e, f.cur ^ 1, nNew);

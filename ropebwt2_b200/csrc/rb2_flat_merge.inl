@@ -36,7 +36,8 @@ __device__ __forceinline__ void slice_mark(SliceWork &W, uint32_t key, uint32_t 
 	}
 }
 
-template <bool GENERAL>
+// SHARDED: the engine is one rank of a sharded build (whole-index coordinates, direct delivery); compiled out otherwise
+template <bool GENERAL, bool SHARDED>
 __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W, const SliceIn &in, const uint32_t slice, const TileDesc d0, const TileDesc d1, const int lane, const RecRegs &pf, const int64_t cpostLane)
 {
 	const uint64_t o0 = (uint64_t)slice * FS_SLICE;
@@ -52,7 +53,7 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 	// the peer array each symbol's ranks go to; one bucket for the whole slice except where a bucket boundary crosses it
 	bool oneBkt = true;
 	int64_t *routeLane = 0; uint32_t *route32Lane = 0;
-	if (A.recOff) {
+	if (SHARDED) {
 		const uint32_t b0 = A.sliceBkt[slice];
 		oneBkt = r0 + nr <= A.ctl->recBkt[b0 + 1];
 		if (lane < 6) {
@@ -162,8 +163,8 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			const uint32_t dst = !valid ? NONE32 : (reg ? pf.dst : in.dst[k]);
 			const uint32_t a = !valid ? 0u : (reg ? (pf.sc & 7u) : (GENERAL ? (in.SC(k) & 7u) : (uint32_t)in.asym[k]));
 			const int64_t base = __shfl_sync(FULLMASK, baseLane, (int)a);
-			int64_t *rp = A.route ? (int64_t*)__shfl_sync(FULLMASK, (long long)routeLane, (int)a) : A.gLNext;
-			const bool ids = !GENERAL && A.sidCur != 0; // (uniform)
+			int64_t *rp = SHARDED && A.route ? (int64_t*)__shfl_sync(FULLMASK, (long long)routeLane, (int)a) : A.gLNext;
+			const bool ids = SHARDED && !GENERAL && A.sidCur != 0; // (uniform)
 			uint32_t *rp32 = ids ? (uint32_t*)__shfl_sync(FULLMASK, (long long)route32Lane, (int)a) : (uint32_t*)0;
 			if (dst == NONE32) continue;
 			const uint32_t xo = (uint32_t)((uint64_t)(reg ? pf.P : in.P[k]) - a0); // old symbols of the window in front of the record
@@ -171,7 +172,7 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 			const Raw6 rr = raw_unpack16(W.pre[c][0], W.pre[c][1], W.pre[c][2]);
 			const uint32_t part = __popc(cell_match(cell_load(in.old + c * 3), a) & low_mask(xo & (FT_CH - 1)));
 			int64_t g = base + raw_symbol(rr, a) + part;
-			if (!oneBkt) { // (a bucket boundary inside the slice: look the record's own bucket up)
+			if (SHARDED && !oneBkt) { // (a bucket boundary inside the slice: look the record's own bucket up)
 				const uint32_t b = (uint32_t)bucket_of(A.ctl->recBkt, (uint32_t)A.nb, r0 + k);
 				g += A.recOff[b * 7 + a];
 				if (A.route) { const uint32_t pc = A.route->pieceOf[a * 36 + b]; rp = A.route->base[pc]; if (ids) rp32 = A.route->base32[pc]; }
@@ -185,7 +186,7 @@ __device__ __forceinline__ void flat_merge_slice(const FlatArgs &A, SliceWork &W
 
 // main kernel: persistent warps, each its own producer for the old symbols (the bulk of the bytes); the slice's
 // records are read straight from the record arrays (coalesced: consecutive records, consecutive lanes)
-template <bool GENERAL>
+template <bool GENERAL, bool SHARDED>
 __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArgs A)
 {
 	RB2_DYN_SMEM(smraw);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 					pfNext.P = A.V.P[r]; pfNext.dst = A.recDst[r];
 					pfNext.pre = GENERAL ? A.V.pre[r] : r;
 					pfNext.sc = GENERAL ? A.V.sc[r] : (uint32_t)A.V.asym[r];
-					if (!GENERAL && A.sidCur) pfNext.sid = A.sidCur[r];
+					if (SHARDED && !GENERAL && A.sidCur) pfNext.sid = A.sidCur[r];
 				}
 			}
 		}
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(FS_WARPS * 32, FS_MINCTA) k_flat_merge(FlatArg
 		const uint32_t r0 = st.d0.r0;
 		SliceIn in = { st.old, A.V.P + r0, GENERAL ? A.V.pre + r0 : (const uint32_t*)0, GENERAL ? A.V.sc + r0 : (const uint32_t*)0, A.recDst + r0,
 		               GENERAL ? (const uint8_t*)0 : A.V.asym + r0, r0 };
-		flat_merge_slice<GENERAL>(A, S.W, in, slice, st.d0, st.d1, lane, pf, cpostLane);
+		flat_merge_slice<GENERAL, SHARDED>(A, S.W, in, slice, st.d0, st.d1, lane, pf, cpostLane);
 		pf = pfNext;
 		issue(s, nextSl, nd0, nd1); // (behind the slice's closing __syncwarp: every lane is done with the stage)
 		__syncwarp();               // the stage's new geometry is visible to every lane (they prefetch its records next time round)
