@@ -2282,6 +2282,8 @@ static FILE *column_log(void)
 }
 
 static void insert_string_range(rb2_engine *e, const uint8_t *s, uint32_t kBase, uint32_t m);
+// padding a batch's symbol matrix may carry before the batch is cut (RB2_SPLIT_SLACK bytes: the tests lower it)
+static size_t split_slack(void) { const char *v = getenv("RB2_SPLIT_SLACK"); return v && *v ? (size_t)atoll(v) : (size_t)64 << 20; }
 
 // One sub-batch whose strings already sit in device memory at `s` (len bytes, ends with NUL).
 static void insert_device_batch(rb2_engine *e, int64_t len, const uint8_t *s)
@@ -2329,7 +2331,7 @@ static void insert_string_range(rb2_engine *e, const uint8_t *s, uint32_t kBase,
 		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
 		const size_t need = (size_t)ncol * t_stride(m);
 		const bool tooBig = need > e->T.cap && need > (freeB + e->T.cap) / 2;
-		const bool wasteful = need > (size_t)8 * (size_t)len + ((size_t)64 << 20); // the matrix holds 4 bits per symbol: > 16x padding
+		const bool wasteful = need > (size_t)8 * (size_t)len + split_slack(); // the matrix holds 4 bits per symbol: > 16x padding
 		if ((tooBig || wasteful) && m > 1) {
 			ph_end(e, PH_TRANSPOSE);
 			insert_string_range(e, s, kBase, m / 2);

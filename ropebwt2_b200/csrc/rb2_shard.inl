@@ -180,9 +180,36 @@ extern "C" void rb2_sharded_quiesce(rb2_engine_t *e)
 	shard_unmap_peers(e);
 }
 
+static void insert_sharded_range(rb2_engine *e, const uint8_t *s, uint32_t kBase, uint32_t m);
+
 // One batch: every rank passes ITS strings (device resident, NUL-terminated, reversed; len may be 0).
 // Collective: all ranks of the communicator must call it.
 static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
+{
+	uint32_t m = 0;
+	if (len > 0) { // my strings: where each one ends
+		const uint32_t nT = cdiv(len, 4096);
+		e->tileA.need((size_t)nT + 2);
+		LAUNCH(e, k_count_nul, nT, 256, 0, s, len, e->tileA.p);
+		uint32_t *dTot = e->tileA.p + nT;
+		run_mid<1, uint32_t>(e, e->tileA.p, (uint64_t)nT, dTot, e->midTmp);
+		RB2_CUDA(cudaMemcpyAsync(&m, dTot, 4, cudaMemcpyDeviceToHost, e->st));
+		RB2_CUDA(cudaStreamSynchronize(e->st));
+		if (m == 0) RB2_FATAL("batch holds no terminated string");
+		e->strEnd.need(m);
+		LAUNCH(e, k_string_ends, nT, 256, 0, s, len, e->tileA.p, e->strEnd.p);
+	}
+	insert_sharded_range(e, s, 0, m);
+	e->stats.n_strings += m;
+	e->stats.n_symbols += len;
+}
+
+// Strings kBase .. kBase+m-1 of my share (string ends in e->strEnd; m may be 0).  Like the one-GPU engine
+// (insert_string_range) the ranks cut a batch in two when its symbol matrices -- dense rectangles of (longest
+// string + 1) columns, replicated on every rank -- would not fit or would be mostly padding (one long string among
+// short ones): the cut is made in the GLOBAL string order (rank, position), so input order is preserved, and every
+// rank takes the same decision from the all-gathered shapes.
+static void insert_sharded_range(rb2_engine *e, const uint8_t *s, uint32_t kBase, uint32_t m)
 {
 	Comm *cm = e->comm;
 	const int P = cm->n, me = cm->rank;
@@ -198,25 +225,21 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 
 	// ---- my strings: split, lengths ----------------------------------------------------------
 	ph_begin(e, PH_TRANSPOSE);
-	uint32_t m = 0; unsigned long long maxlen = 0;
-	const uint32_t nT = cdiv(len, 4096);
-	if (len > 0) {
-		e->tileA.need((size_t)nT + 2);
-		LAUNCH(e, k_count_nul, nT, 256, 0, s, len, e->tileA.p);
-		uint32_t *dTot = e->tileA.p + nT;
-		run_mid<1, uint32_t>(e, e->tileA.p, (uint64_t)nT, dTot, e->midTmp);
-		RB2_CUDA(cudaMemcpyAsync(&m, dTot, 4, cudaMemcpyDeviceToHost, e->st));
-		RB2_CUDA(cudaStreamSynchronize(e->st));
-		if (m == 0) RB2_FATAL("batch holds no terminated string");
-		e->strEnd.need(m);
-		LAUNCH(e, k_string_ends, nT, 256, 0, s, len, e->tileA.p, e->strEnd.p);
+	unsigned long long maxlen = 0;
+	int64_t len = 0;
+	if (m) {
+		int64_t ends[2] = { -1, 0 };
 		RB2_CUDA(cudaMemsetAsync(e->dMaxLen, 0, 8, e->st));
-		LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, 0u, m, e->dMaxLen);
+		LAUNCH(e, k_maxlen, cdiv(m, 256), 256, 0, e->strEnd.p, kBase, m, e->dMaxLen);
 		RB2_CUDA(cudaMemcpyAsync(&maxlen, e->dMaxLen, 8, cudaMemcpyDeviceToHost, e->st));
+		if (kBase) RB2_CUDA(cudaMemcpyAsync(&ends[0], e->strEnd.p + kBase - 1, 8, cudaMemcpyDeviceToHost, e->st));
+		RB2_CUDA(cudaMemcpyAsync(&ends[1], e->strEnd.p + kBase + m - 1, 8, cudaMemcpyDeviceToHost, e->st));
 		RB2_CUDA(cudaStreamSynchronize(e->st));
+		len = ends[1] - ends[0];
 	}
 	// ---- shapes of all ranks; replicate the column-major symbol matrices --------------------------
-	struct Shape { uint64_t m, ncol, len; } mine = { m, m ? maxlen + 1 : 0, (uint64_t)len }, all[RB2_MAX_RANKS];
+	struct Shape { uint64_t m, ncol, len, freeB, tcap; } mine = { m, m ? maxlen + 1 : 0, (uint64_t)len, 0, e->T.cap }, all[RB2_MAX_RANKS];
+	{ size_t freeB = 0, totB = 0; RB2_CUDA(cudaMemGetInfo(&freeB, &totB)); mine.freeB = freeB; }
 	cm->allgather_host(&mine, sizeof(mine), all, e->st);
 	uint64_t mAll = 0, lenAll = 0, tBytes = 0, ncolAll = 0;
 	uint64_t strOff[RB2_MAX_RANKS + 1], tOff[RB2_MAX_RANKS + 1];
@@ -230,13 +253,21 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (mAll == 0) RB2_FATAL("mr_insert_multi: empty batch (mrope.c:268)");
 	if (mAll >= 0xfffffff0ull) RB2_FATAL("a sharded batch is limited to 2^32 strings");
 	{
-		size_t freeB = 0, totB = 0;
-		RB2_CUDA(cudaMemGetInfo(&freeB, &totB));
-		if (tBytes > e->T.cap && tBytes > freeB + e->T.cap)
-			RB2_FATAL("replicated symbol matrices (%.1f GB) do not fit in HBM", tBytes * 1e-9);
+		bool tooBig = false;
+		for (int r = 0; r < P; ++r) tooBig = tooBig || (tBytes > all[r].tcap && tBytes > (all[r].freeB + all[r].tcap) / 2);
+		const bool wasteful = tBytes > 8 * lenAll + split_slack(); // the matrices hold 4 bits per symbol: > 16x padding
+		if ((tooBig || wasteful) && mAll > 1) {
+			ph_end(e, PH_TRANSPOSE);
+			const uint64_t cut = mAll / 2, lo = strOff[me];
+			const uint32_t k1 = (uint32_t)(cut <= lo ? 0 : std::min<uint64_t>(cut - lo, m));
+			insert_sharded_range(e, s, kBase, k1);
+			insert_sharded_range(e, s, kBase + k1, m - k1);
+			return;
+		}
+		if (tooBig) RB2_FATAL("one string of %llu symbols does not fit in HBM as a column-major symbol matrix on every rank", (unsigned long long)ncolAll);
 	}
 	e->T.need(tBytes + 16);
-	if (m) LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, 0u, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
+	if (m) LAUNCH(e, k_transpose, cdiv(m, TR_S), 256, 0, s, e->strEnd.p, kBase, m, (int64_t)all[me].ncol, e->T.p + tOff[me]);
 	{
 		uint8_t *dst[RB2_MAX_RANKS]; size_t bytes[RB2_MAX_RANKS];
 		for (int r = 0; r < P; ++r) { dst[r] = e->T.p + tOff[r]; bytes[r] = t_stride(all[r].m) * all[r].ncol; }
@@ -578,8 +609,6 @@ static void insert_sharded_batch(rb2_engine *e, int64_t len, const uint8_t *s)
 	if (trace) fprintf(stderr, "[rb2 trace] rank %d: split+replicate+regime %.1f ms, peer mappings %.1f ms, columns %.1f ms, unmap+finish %.1f ms (direct=%d); "
 	                   "in the column loop the host waited %.1f ms for the columns' counts and %.1f ms in the table all-gathers\n",
 	                   me, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], (int)direct, trCtl, trGather);
-	e->stats.n_strings += m;
-	e->stats.n_symbols += len;
 	e->stats.pool_blocks = e->hctl->poolUsed;
 	e->stats.pool_capacity = e->poolCap;
 }

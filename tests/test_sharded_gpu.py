@@ -151,3 +151,23 @@ def test_direct_delivery_across_batches(so, monkeypatch):
     assert st["flat_batches"] == len(sizes) and st["p2p_batches"] == len(sizes) - 1
     assert np.array_equal(c.text(), o.text())
     c.close()
+
+
+@pytest.mark.parametrize("so", [0, 1])
+def test_one_long_string_among_short_ones_sharded(so, monkeypatch):
+    """A length outlier in a sharded batch: the ranks cut the batch together, in the global string
+    order, instead of replicating a mostly empty symbol matrix on every rank."""
+    from conftest import EMU
+    if EMU:
+        monkeypatch.setenv("RB2_SPLIT_SLACK", "4096")
+    rng = np.random.default_rng(78)
+    short = [rng.integers(1, 5, size=int(rng.integers(5, 40))).astype(np.uint8) for _ in range(sz(3000, 300))]
+    contig = rng.integers(1, 5, size=sz(150_000, 2_000)).astype(np.uint8)
+    strs = short[:len(short) // 3] + [contig] + short[len(short) // 3:]
+    o = orc.Oracle(so)
+    o.insert_multi(encode_batch(strs))
+    c = Cluster(so, 3)
+    c.insert([encode_batch(p) for p in split(strs, 3)])
+    assert c.eng[0].stats()["n_columns"] > len(contig)  # (several sub-batches: more columns than the longest string)
+    assert np.array_equal(c.text(), o.text())
+    c.close()
