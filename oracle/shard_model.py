@@ -11,6 +11,12 @@ coordinates; see oracle/bcr_oracle.c): per group, symbols are inserted in $,A,C,
 $,T,G,C,A,N, mrope.c:209-210) order at gL + sizes of the earlier symbols, and the next interval
 start of the strings that inserted a is C_post[a] + occ_pre(a, insertion point).
 
+Direct delivery is modelled too: from the gathered tables ALONE every rank derives,
+for each of its output groups, the rank and the slot in that rank's next-column array where the group
+belongs (the engine's PeerRoute: piece (a, x, y) goes from owner(x, y) to owner(a, x), the pieces of one
+target in y order) and "stores" it there; the arrays assembled from those stores must equal the ones the
+send/recv formulation (sort by (sub-bucket, y, source rank, source order)) produces.
+
 Ranks talk through `comm.allgather(obj) -> [obj of rank 0, obj of rank 1, ...]` only, so the same
 code runs in one process (world 1) and under a gloo process group (tests/test_dist_gloo.py).
 """
@@ -72,6 +78,7 @@ class ShardModel:
             records = {}                                                     # s -> [(P, a, count)]
             nxt = {a: [] for a in range(1, 6)}                               # a -> [(s, P_of_record, gSize', members)]
             mem_tab = [[0] * 6 for _ in range(36)]
+            grp_tab = [[0] * 6 for _ in range(36)]                            # groups I hand on, per (source sub-bucket, symbol)
             for s, gL, gSize, members in groups:
                 by = {a: [k for k in members if strings[k][col] == a] for a in range(6)}
                 P = gL
@@ -82,9 +89,11 @@ class ShardModel:
                         mem_tab[s][a] += len(by[a])
                         if a:
                             nxt[a].append((s, P, sza, by[a]))
+                            grp_tab[s][a] += 1
                     P += sza
             # -- gather the tables; post-column totals and bucket starts -------------------------------
             tabs = self.comm.allgather(mem_tab)
+            gtabs = self.comm.allgather(grp_tab)
             post = [[self.tot[s][a] + sum(t[s][a] for t in tabs) for a in range(6)] for s in range(36)]
             cpost = [sum(sum(post[t]) for t in range(a * 6)) for a in range(6)]
             # -- ranks against the PRE-column index, then the merge -------------------------------------
@@ -105,6 +114,25 @@ class ShardModel:
             mine = [(t, y, src, i, g) for src, lst in enumerate(everything) for i, (t, y, *g) in enumerate(lst) if self.own[t] == self.rank]
             mine.sort(key=lambda e: (e[0], e[1], e[2], e[3]))                # (sub-bucket, y, source rank, source order)
             groups = [[t, g[0], g[1], g[2]] for t, y, src, i, g in mine]
+            # -- the same by direct delivery: (rank, slot) of every output group from the gathered tables -----
+            route, cur = {}, [0] * self.world                                # (a, source sub-bucket) -> [target rank, next slot]
+            for t in range(6, 36):
+                a, x = divmod(t, 6)
+                for y in range(6):
+                    sb = x * 6 + y
+                    ng = gtabs[self.own[sb]][sb][a]
+                    if ng and self.own[sb] == self.rank:
+                        route[(a, sb)] = [self.own[t], cur[self.own[t]]]
+                    cur[self.own[t]] += ng
+            stores = []                                                      # what my "merge epilogue" writes into the peers' arrays
+            for (t, y, *g) in out:
+                r = route[(t // 6, (t % 6) * 6 + y)]
+                stores.append((r[0], r[1], [t, g[0], g[1], g[2]]))
+                r[1] += 1
+            landed = [(slot, g) for lst in self.comm.allgather(stores) for (dst, slot, g) in lst if dst == self.rank]
+            landed.sort(key=lambda e: e[0])
+            assert [slot for slot, _ in landed] == list(range(cur[self.rank])), "direct delivery: a slot filled twice or not at all"
+            assert [g for _, g in landed] == groups, "direct delivery differs from the send/recv order"
             live = sum(len(g[2]) for lst in everything for (_, _, *g) in lst)
             col += 1
 

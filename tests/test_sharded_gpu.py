@@ -162,7 +162,7 @@ def test_one_long_string_among_short_ones_sharded(so, monkeypatch):
         monkeypatch.setenv("RB2_SPLIT_SLACK", "4096")
     rng = np.random.default_rng(78)
     short = [rng.integers(1, 5, size=int(rng.integers(5, 40))).astype(np.uint8) for _ in range(sz(3000, 300))]
-    contig = rng.integers(1, 5, size=sz(150_000, 2_000)).astype(np.uint8)
+    contig = rng.integers(1, 5, size=sz(60_000, 2_000)).astype(np.uint8)
     strs = short[:len(short) // 3] + [contig] + short[len(short) // 3:]
     o = orc.Oracle(so)
     o.insert_multi(encode_batch(strs))
