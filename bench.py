@@ -67,23 +67,53 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled during the timed region.  NVML in-process (pynvml: what
+    nvidia-smi itself reads) when it is importable -- spawning nvidia-smi five times a second next to a collective
+    job delays the rank that does it -- else the nvidia-smi query of the profiling recipe."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip()]
+        return int(ids[index]) if ids and all(x.strip().isdigit() for x in ids) and index < len(ids) else index
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        active = {nm for bit, nm in self.NVML_REASONS.items() if mask & bit}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        return [str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
+                "%.1f" % (n.nvmlDeviceGetPowerUsage(h) / 1000.0)] + ["Active" if nm in active else "Not Active" for nm in names]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.1 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
@@ -97,7 +127,8 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": "NVML in-process (pynvml), every 0.1 s" if self.nvml is not None else "nvidia-smi --query-gpu, every 0.2 s"}
 
 
 def ref_binary():
