@@ -60,7 +60,7 @@ typedef struct {
 	double  ms_directory;               /* item planning + directory rebuild */
 	double  ms_merge_general;           /* sparse regime: k_merge_fast + k_merge_general (over-full / multi-item / empty blocks) */
 	int64_t general_items;              /* sparse regime: work items k_merge_half handed on */
-	double  ms_exchange;                /* sharded build: string-state transfer between ranks */
+	double  ms_exchange;                /* sharded build: ncclSend/ncclRecv of the interval starts behind the merge (0 with direct delivery) */
 	int64_t exch_bytes;                 /* sharded build: bytes of string state this rank received */
 	double  ms_convert;                 /* dense regime: leaf blocks <-> flat symbol array at the ends of a batch */
 	int64_t flat_batches;               /* batches that ran in the dense regime (k_flat_merge instead of the block merges) */
