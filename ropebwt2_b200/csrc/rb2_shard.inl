@@ -284,8 +284,15 @@ static void insert_sharded_range(rb2_engine *e, const uint8_t *s, uint32_t kBase
 	cm->allgather_host(&myVote, 4, votes, e->st);
 	bool flat = true;
 	for (int r = 0; r < P; ++r) flat = flat && votes[r] != 0;
-	if (flat) flat_begin(e, addLocal);
-	else { ensure_blocks(e); blocks_edited(e); } // a sparse batch edits the leaf blocks
+	if (flat) {
+		if (!e->flat.valid) { // the array is built from the leaf blocks: their bucket table and my offsets must be current on the device
+			for (int b = 0; b < NBA; ++b) h->blkBkt[b] = e->blkBkt[b];
+			h->nb = NBMAX; h->tables = 1;
+			ctl_push(e);
+			shard_dir_offsets(e, e->gtot);
+		}
+		flat_begin(e, addLocal);
+	} else { ensure_blocks(e); blocks_edited(e); } // a sparse batch edits the leaf blocks
 	if (!flat) reserve_blocks(e, (uint64_t)h->poolUsed + (lenAll * 2 / RB2_FILL) / P * 5 / 4 + 4096);
 	mark();
 	// ---- direct delivery of the interval starts (dense regime): every rank maps every rank's two state buffers ----

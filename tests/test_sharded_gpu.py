@@ -139,16 +139,19 @@ def test_direct_delivery_across_batches(so, monkeypatch):
     monkeypatch.setenv("RB2_FLAT", "1")
     o = orc.Oracle(so)
     c = Cluster(so, 3)
-    sizes = [sz(3000, 600), sz(9000, 1500), sz(2000, 400), sz(2500, 500), sz(2500, 500)]
+    sizes = [sz(3000, 600), sz(9000, 1500), sz(2000, 400), sz(2500, 500), sz(2500, 500), sz(2500, 500), sz(12000, 2000)]
     for k, n in enumerate(sizes):
         rd = uniform_reads(n, 40, 50 + k, n_frac=0.01) if k != 2 else varlen_reads(n, 60, 52, 5)
         if k == 3:
             monkeypatch.setenv("RB2_P2P", "0")
+        if k == 5:
+            monkeypatch.setenv("RB2_FLAT", "0")  # a sparse batch in between: leaf blocks rebuilt, mappings dropped
         o.insert_multi(encode_batch(rd))
         c.insert([encode_batch(p) for p in split(rd, 3)])
         monkeypatch.delenv("RB2_P2P", raising=False)
+        monkeypatch.setenv("RB2_FLAT", "1")
     st = c.eng[0].stats()
-    assert st["flat_batches"] == len(sizes) and st["p2p_batches"] == len(sizes) - 1
+    assert st["flat_batches"] == len(sizes) - 1 and st["p2p_batches"] == len(sizes) - 2
     assert np.array_equal(c.text(), o.text())
     c.close()
 
@@ -169,5 +172,26 @@ def test_one_long_string_among_short_ones_sharded(so, monkeypatch):
     c = Cluster(so, 3)
     c.insert([encode_batch(p) for p in split(strs, 3)])
     assert c.eng[0].stats()["n_columns"] > len(contig)  # (several sub-batches: more columns than the longest string)
+    assert np.array_equal(c.text(), o.text())
+    c.close()
+
+
+@pytest.mark.parametrize("P", [2, 4])
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_regimes_alternate_sharded(so, P, monkeypatch):
+    """Sparse and dense batches alternating on a sharded index: the array is rebuilt from the leaf blocks of a non-empty
+    index (sparse -> dense) and the blocks from the array (dense -> sparse) on every rank."""
+    o = orc.Oracle(so)
+    c = Cluster(so, P)
+    for k, flat in enumerate(["0", "1", "1", "0", "1"]):
+        monkeypatch.setenv("RB2_FLAT", flat)
+        # (equal lengths: the last column of a sparse batch inserts every sentinel and splits leaf blocks, so the
+        #  bucket table of the blocks changes behind the last control-block upload of that batch)
+        rd = uniform_reads(sz(2500, 700) + 137 * k, sz(50, 30), 70 + k, n_frac=0.01)
+        o.insert_multi(encode_batch(rd))
+        c.insert([encode_batch(p) for p in split(rd, P)])
+        for e in c.eng:
+            assert np.array_equal(e.counts(), o.counts())
+    assert c.eng[0].stats()["flat_batches"] == 3
     assert np.array_equal(c.text(), o.text())
     c.close()
