@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SUBSET = ("test_resident_array_across_batches or test_regimes_alternate or test_forced_dense_multi_batch or test_edge_cases "
           "or (test_golden_fixtures and not batches) or test_rope_api or (test_uniform_one_batch and (1-2 or 0-3 or 2-4)) "
-          "or (test_three_batches and 1-2)")
+          "or (test_three_batches and 1-2) or (test_direct_delivery and 1) or (test_regimes_alternate_sharded and 2-2)")
 
 
 def test_gpu_parity_tests_on_the_cpu_emulator():

@@ -195,3 +195,25 @@ def test_regimes_alternate_sharded(so, P, monkeypatch):
     assert c.eng[0].stats()["flat_batches"] == 3
     assert np.array_equal(c.text(), o.text())
     c.close()
+
+
+@pytest.mark.parametrize("so", [0, 1])
+def test_blocks_fetched_between_dense_batches_sharded(so, monkeypatch):
+    """The leaf blocks of a sharded index are rebuilt on demand from the resident arrays (every fetch between two dense
+    batches), the next batch goes on with the arrays, a reset starts over."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    o = orc.Oracle(so)
+    c = Cluster(so, 3)
+    for k in range(3):
+        rd = uniform_reads(sz(3000, 500), sz(40, 25), 90 + k, n_frac=0.01)
+        o.insert_multi(encode_batch(rd))
+        c.insert([encode_batch(p) for p in split(rd, 3)])
+        assert np.array_equal(c.text(), o.text()), k
+    for e in c.eng:
+        e.reset()
+    o = orc.Oracle(so)
+    rd = varlen_reads(sz(2000, 400), 50, 93, 1)
+    o.insert_multi(encode_batch(rd))
+    c.insert([encode_batch(p) for p in split(rd, 3)])
+    assert np.array_equal(c.text(), o.text())
+    c.close()
