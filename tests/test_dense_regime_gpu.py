@@ -158,3 +158,34 @@ def test_long_reads_in_the_dense_regime(monkeypatch, so):
     assert np.array_equal(m.counts(), o.counts())
     assert np.array_equal(text(m), o.text())
     m.close()
+
+
+@pytest.mark.parametrize("so", [0, 1, 2])
+def test_restore_then_dense_batches(monkeypatch, tmp_path, so):
+    """BASELINE config 5 shape: mr_restore of a dumped index, then batches in the dense regime (the array is built from
+    the restored leaf blocks), then a dump of the result that restores to the same text."""
+    monkeypatch.setenv("RB2_FLAT", "1")
+    n = sz(12000, 1500)
+    rd = uniform_reads(n, sz(60, 30), 31 + so, n_frac=0.002)
+    a, b = n // 2, n * 3 // 4
+    o, m = orc.Oracle(so), MRope(so)
+    buf = encode_batch(rd[:a], True, so == 2)
+    o.insert_multi(buf)
+    m.insert_multi(buf)
+    p = str(tmp_path / "half.fmr")
+    m.dump(p)
+    m.close()
+    m2 = MRope.restore(p)
+    for part in (rd[a:b], rd[b:]):
+        buf = encode_batch(part, True, so == 2)
+        o.insert_multi(buf)
+        m2.insert_multi(buf)
+    assert m2.stats()["flat_batches"] == 2
+    assert np.array_equal(m2.counts(), o.counts())
+    assert np.array_equal(text(m2), o.text())
+    q = str(tmp_path / "whole.fmr")
+    m2.dump(q)
+    m3 = MRope.restore(q)
+    assert np.array_equal(text(m3), o.text())
+    m2.close()
+    m3.close()
