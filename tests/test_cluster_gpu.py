@@ -9,6 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
+from conftest import not_on_emu
 from oracle import oracle as orc
 from ropebwt2_b200 import MRope, load
 from ropebwt2_b200.synth import encode_batch, genome_reads, reads_to_lines, varlen_reads
@@ -51,6 +52,7 @@ def test_mrope_api_over_four_ranks(cluster4, so, tmp_path, monkeypatch):
     one.close()
 
 
+@not_on_emu  # (the drop-in binary links the real library)
 @pytest.mark.skipif(not os.path.exists(DROPIN), reason="drop-in binary not built (oracle/Makefile: make dropin)")
 def test_reference_driver_uses_all_ranks():
     """RB2_GPUS=4 ropebwt2_b200 -LRs: the reference's main.c, unmodified, on four ranks"""
