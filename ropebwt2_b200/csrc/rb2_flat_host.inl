@@ -155,7 +155,7 @@ static void flat_apply_records(rb2_engine *e, uint32_t nrec, uint64_t inserted, 
 	ph_end(e, PH_DIR);
 	++e->stats.n_merge_launches;
 	e->stats.merge_blocks += nTiles;
-	e->stats.merge_bytes_rw += (int64_t)(flat_bytes(f.n) + flat_bytes(nNew)) + (int64_t)nrec * (leanP ? 21 : 28); // old array read, new written (3 bits per symbol), records (13 / 20 B) read, ranks (8 B) written
+	e->stats.merge_bytes_rw += (int64_t)(flat_bytes(f.n) + flat_bytes(nNew)) + (int64_t)nrec * ((leanP ? 21 : 28) + (sidCur ? 8 : 0)); // old array read, new written (3 bits per symbol), records (13 / 20 B) read, ranks (8 B) written (+ ids read and delivered)
 	f.cur ^= 1; f.n = nNew;
 	f.pending |= (1u << PH_MERGE) | (1u << PH_DIR);
 	if (getenv("RB2_FLAT_DEBUG") && nNew <= 4096 && !leanP && gLNext) { // developer aid: dump tiny arrays column by column
